@@ -1,0 +1,161 @@
+/*
+ * vsrb200.h — C-ABI of libvsrb200.so: the B200 (sm_100a) kernels behind the
+ * Real-BasicVSR / BasicVSR hot path of santurini/vsrlab.
+ *
+ * The reference has no FFI of its own (it is pure PyTorch); every entry point
+ * below replaces the stock torch library call(s) named in its comment, cited as
+ * reference file:line relative to the reference repo root.  INTEGRATION.md shows
+ * the ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative VSRB_E_* code on failure;
+ *    vsrb_last_error() returns a human-readable reason (thread-local).
+ *  - all pointers are DEVICE pointers owned by the caller unless stated; the
+ *    library never allocates, frees or synchronises; kernels are enqueued on the
+ *    `stream` argument (a cudaStream_t passed as void*).
+ *  - activations are NHWC ("channels-last"); `dtype` selects the activation
+ *    element type AND the arithmetic path: VSRB_BF16 = bf16 operands, fp32
+ *    accumulate, tcgen05/TMEM tensor-core implicit GEMM fed by TMA;
+ *    VSRB_F32 = fp32 operands and accumulate on the FFMA pipes ("fp32 mode").
+ *  - flows are fp32 channels-last [N,h,w,2] (x then y displacement, pixels),
+ *    which is what the reference hands to flow_warp (basicvsr.py:54,69).
+ */
+#ifndef VSRB200_H
+#define VSRB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VSRB_VERSION 100
+
+/* error codes */
+#define VSRB_OK            0
+#define VSRB_E_ARG        -1   /* invalid argument / unsupported shape            */
+#define VSRB_E_CUDA       -2   /* CUDA runtime / driver error                      */
+#define VSRB_E_NODEVICE   -3   /* no sm_100 device / driver entry point missing    */
+#define VSRB_E_SMEM       -4   /* tile does not fit shared memory / TMEM           */
+
+/* dtypes */
+#define VSRB_BF16 0
+#define VSRB_F32  1
+
+/* activations fused in the conv epilogue */
+#define VSRB_ACT_NONE  0
+#define VSRB_ACT_RELU  1       /* reference conv.py:19,87 ; spynet.py:16-18        */
+#define VSRB_ACT_LRELU 2       /* LeakyReLU(slope); reference conv.py:98           */
+
+/* padding modes of the backward warp (reference spynet.py:95) */
+#define VSRB_PAD_ZEROS  0
+#define VSRB_PAD_BORDER 1
+
+/* conv epilogues (what happens to acc + bias) */
+#define VSRB_EPI_NHWC   0  /* act(acc+bias) [+ residual] -> NHWC `out`; with geom.pixshuf=2 the store
+                              is the PixelShuffle(2) of the result (upsampling.py:10-12)                */
+#define VSRB_EPI_CLEAN  1  /* 3-channel residue: x_nchw_f32 += acc+bias in place, and the refreshed
+                              frame is also written NHWC for the next stem (realbasicvsr.py:28-29)      */
+#define VSRB_EPI_FLOW   2  /* flow = flow_up + relu(acc+bias), fp32 [B,h,w,2] (spynet.py:56-65)         */
+#define VSRB_EPI_SR     3  /* sr_nchw_f32 = acc+bias + bilinear_x4(lq) (basicvsr.py:81-82; ac=False)   */
+
+/* Geometry of one convolution's weights: everything the packer and the launcher
+ * must agree on.  Stride 1, 'same' padding (kh//2, kw//2), dilation 1. */
+typedef struct vsrb_conv_geom {
+    int32_t kh, kw;         /* 1, 3 or 7                                                        */
+    int32_t n_seg;          /* 1 or 2 input segments (a fused torch.cat along channels)         */
+    int32_t seg_c[2];       /* real channels of each segment                                    */
+    int32_t seg_off[2];     /* where the segment sits on the OIHW input-channel axis            */
+    int32_t cout;           /* real output channels                                             */
+    int32_t pixshuf;        /* 0, or 2 = output channel 4c+2i+j is stored at pixel (2y+i,2x+j)  */
+    int32_t groups;         /* independent weight sets applied to consecutive image groups      */
+    int32_t dtype;          /* VSRB_BF16 or VSRB_F32                                            */
+    int32_t transpose;      /* reserved (dgrad): 0                                              */
+} vsrb_conv_geom;
+
+typedef struct vsrb_conv_args {
+    vsrb_conv_geom geom;
+    const void*  in[2];       /* NHWC inputs, one per segment                                    */
+    int32_t      in_c[2];     /* channels allocated per pixel in in[s] (>= padded seg_c[s])      */
+    int32_t      batch, h, w; /* input (== pre-shuffle output) extent                            */
+    int32_t      imgs_per_group; /* images per weight group (batch = groups*imgs_per_group)      */
+    const void*  packed;      /* buffer written by vsrb_pack_conv_weight                         */
+    int32_t      act;         /* VSRB_ACT_*                                                      */
+    float        slope;       /* LeakyReLU slope                                                 */
+    int32_t      epilogue;    /* VSRB_EPI_*                                                      */
+    void*        out;         /* EPI_NHWC: NHWC output (dtype); EPI_CLEAN: NHWC refreshed frame  */
+    int32_t      out_c;       /* channels allocated per pixel in `out`                           */
+    int64_t      out_img_stride;   /* EPI_NHWC: elements between consecutive images of a group in
+                                      `out` (0 = dense); lets a step write straight into frame t
+                                      of a [N,T,h,w,C] feature bank                               */
+    int64_t      out_group_stride; /* EPI_NHWC: elements between the first images of two groups   */
+    const void*  residual;    /* EPI_NHWC: optional NHWC tensor added after act (same extent)    */
+    int32_t      res_c;
+    float*       f32_io;      /* EPI_CLEAN: x [B,3,h,w] updated in place; EPI_FLOW: flow out
+                                 [B,h,w,2]; EPI_SR: sr [B,3,4h,4w]                               */
+    const float* f32_in;      /* EPI_FLOW: flow_up [B,h,w,2]; EPI_SR: lq [B,3,aux_h,aux_w]       */
+    int32_t      aux_h, aux_w;/* EPI_SR: extent of the low-resolution skip frame                 */
+    int32_t      max_ctas;    /* 0 = one persistent CTA per SM                                   */
+} vsrb_conv_args;
+
+/* ---- library ------------------------------------------------------------------------- */
+int         vsrb_version(void);
+const char* vsrb_last_error(void);
+/* sm count / compute capability of the current device */
+int         vsrb_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+int64_t     vsrb_launch_count(void);
+/* 0 if no kernel reported a pipeline time-out since the last call (debug aid) */
+int         vsrb_debug_status(void* stream);
+
+/* ---- convolution: replaces nn.Conv2d -> F.conv2d (+ the pointwise op that follows it) --
+ * reference: conv.py:89-92,101-103 (ResidualConv/ResidualBlock), conv.py:21 (ConvReLU),
+ * upsampling.py:10-12 (PixelShufflePack), basicvsr.py:75-82 (point_conv, conv_last, skip),
+ * realbasicvsr.py:28-29 (cleaner residue), spynet.py:56-65 (SpynetModule + flow add).   */
+size_t vsrb_packed_weight_bytes(const vsrb_conv_geom* g);
+/* w: fp32 OIHW [groups][cout][cin_total][kh][kw] on device (cin_total = the conv's real
+ * in_channels; segments index into it), bias: fp32 [groups][cout] or NULL.             */
+int    vsrb_pack_conv_weight(const vsrb_conv_geom* g, const float* w, int32_t cin_total,
+                             const float* bias, void* packed, void* stream);
+int    vsrb_conv2d_fwd(const vsrb_conv_args* a, void* stream);
+
+/* ---- backward warp: replaces flow_warp = meshgrid + normalise + F.grid_sample ---------
+ * reference: spynet.py:95-106; callers basicvsr.py:54,69.
+ * x,out: NHWC [n,h,w,c] of `dtype`, c % 8 == 0; flow fp32 [n,h,w,2].                    */
+int vsrb_flow_warp(const void* x, int64_t x_img_stride /* elements, 0 = dense */, const float* flow,
+                   int64_t flow_img_stride /* float2 elements, 0 = dense */, void* out, int32_t n,
+                   int32_t h, int32_t w, int32_t c, int32_t dtype, int32_t padding_mode, void* stream);
+
+/* ---- layout: module-boundary NCHW fp32 <-> internal NHWC ------------------------------
+ * (the reference keeps NCHW throughout; these sit at the nn.Module boundary)            */
+int vsrb_nchw_to_nhwc(const float* src, void* dst, int32_t n, int32_t c, int32_t h, int32_t w,
+                      int32_t c_dst, int32_t dtype, void* stream);   /* channels >= c are zeroed */
+int vsrb_nhwc_to_nchw(const void* src, float* dst, int32_t n, int32_t c, int32_t h, int32_t w,
+                      int32_t c_src, int32_t dtype, void* stream);
+
+/* ---- SPyNet glue ------------------------------------------------------------------------
+ * reference spynet.py:38-48 (normalise + 5x avg_pool2d), :71-80 (resize to /32),
+ * :54-61 (x2 flow upsample, border warp, concat), :83-91 (resize back + rescale).       */
+/* frames [F,3,h,w] fp32 NCHW -> finest pyramid level [F,Hp,Wp,4] fp32 (r,g,b,0), normalised
+ * by mean/std (host floats), resized bilinear align_corners=False when (Hp,Wp)!=(h,w). */
+int vsrb_spynet_pyramid_base(const float* frames, float* lvl, int32_t F, int32_t h, int32_t w,
+                             int32_t Hp, int32_t Wp, const float* mean3, const float* std3, void* stream);
+/* 2x2 average pool of an [F,H,W,4] fp32 level into [F,H/2,W/2,4] */
+int vsrb_avgpool2_c4(const float* in, float* out, int32_t F, int32_t H, int32_t W, void* stream);
+/* One pyramid level's network input.  pair p uses frames ref_idx[p], supp_idx[p] (device
+ * int32 arrays).  flow_prev [P,Hl/2,Wl/2,2] or NULL (level 0: zero flow).  Writes
+ * flow_up [P,Hl,Wl,2] fp32 = 2*up2(flow_prev) (align_corners=True) and the 8-channel
+ * input (ref rgb, border-warped supp rgb, flow_up xy) into conv_in [P,Hl,Wl,c_in], padded
+ * with zeros to c_in channels.                                                          */
+int vsrb_spynet_level_input(const float* lvl, const int32_t* ref_idx, const int32_t* supp_idx,
+                            const float* flow_prev, float* flow_up, void* conv_in,
+                            int32_t P, int32_t Hl, int32_t Wl, int32_t c_in, int32_t dtype, void* stream);
+/* flow [P,Hp,Wp,2] -> [P,h,w,2], bilinear align_corners=False, x*=w/Wp, y*=h/Hp */
+int vsrb_flow_resize(const float* flow_in, float* flow_out, int32_t P, int32_t Hp, int32_t Wp,
+                     int32_t h, int32_t w, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VSRB200_H */

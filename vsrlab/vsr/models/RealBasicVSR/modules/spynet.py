@@ -1,0 +1,52 @@
+"""SPyNet + flow_warp with the reference's names
+(reference src/vsr/models/RealBasicVSR/modules/spynet.py:13-21 SpynetModule,
+:23-93 Spynet, :95-106 flow_warp)."""
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+
+from vsrlab.core import PROJECT_ROOT
+from vsrlab.core.modules.conv import ConvReLU
+from vsrlab_b200 import functional as VF
+
+
+class SpynetModule(nn.Module):
+    """8 -> 32 -> 64 -> 32 -> 16 -> 2, 7x7, ReLU after every conv (spynet.py:13-21)."""
+
+    def __init__(self):
+        super().__init__()
+        self.basic_module = nn.Sequential(ConvReLU(8, 32, 7, 1, 3), ConvReLU(32, 64, 7, 1, 3),
+                                          ConvReLU(64, 32, 7, 1, 3), ConvReLU(32, 16, 7, 1, 3),
+                                          ConvReLU(16, 2, 7, 1, 3))
+
+    def forward(self, x):
+        return VF.conv_chain(x, [m.conv[0] for m in self.basic_module], act="relu")
+
+
+class Spynet(nn.Module):
+    def __init__(self, pretrained: bool = False):
+        super().__init__()
+        self.basic_module = nn.ModuleList([SpynetModule() for _ in range(6)])
+        self.register_buffer('mean', torch.Tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1))
+        self.register_buffer('std', torch.Tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1))
+        if pretrained:
+            # same blob location and key remap as reference spynet.py:32-36
+            state_dict = torch.load(f'{PROJECT_ROOT}/src/optical_flow/weights/spynet-sintel.pth')
+            new_dict = OrderedDict([(key[13:34] + '.0' + key[34:], state_dict[key]) for key in state_dict.keys()])
+            self.basic_module.load_state_dict(new_dict)
+
+    def compute_flow(self, ref, supp):
+        """Flow on inputs whose sides are multiples of 32 (spynet.py:38-67)."""
+        return VF.spynet_flow(self, ref, supp, resize=False)
+
+    def forward(self, ref, supp):
+        """Flow from `ref` to `supp`, [T,2,h,w] fp32 (spynet.py:69-93)."""
+        return VF.spynet_flow(self, ref, supp, resize=True)
+
+
+def flow_warp(x, flow, interpolation='bilinear', padding_mode='zeros', align_corners=True):
+    """Bilinear backward warp; `flow` is channels-last [T,h,w,2] (spynet.py:95-106)."""
+    if interpolation != 'bilinear' or not align_corners:
+        raise NotImplementedError("the hot path only uses bilinear / align_corners=True (reference spynet.py:95)")
+    return VF.flow_warp(x, flow, padding_mode)

@@ -1,0 +1,294 @@
+// C-ABI plumbing: errors, device info, conv geometry, weight packing, conv dispatch.
+#include <stdarg.h>
+
+#include <atomic>
+
+#include "common.cuh"
+
+namespace vsrb {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+__device__ int g_debug_flag = 0;
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+int* debug_flag() {
+    int* p = nullptr;
+    cudaGetSymbolAddress(reinterpret_cast<void**>(&p), g_debug_flag);
+    return p;
+}
+
+// ---------------------------------------------------------------------------------------
+int make_plan(const vsrb_conv_geom* g, ConvPlan* p) {
+    VSRB_CHECK_ARG(g && p, "null geometry");
+    VSRB_CHECK_ARG(g->kh >= 1 && g->kh <= 7 && (g->kh & 1) && g->kw >= 1 && g->kw <= 7 && (g->kw & 1),
+                   "kernel %dx%d unsupported (odd sizes 1..7)", g->kh, g->kw);
+    VSRB_CHECK_ARG(g->n_seg == 1 || g->n_seg == 2, "n_seg must be 1 or 2, got %d", g->n_seg);
+    VSRB_CHECK_ARG(g->cout >= 1 && g->cout <= 1024, "cout %d unsupported", g->cout);
+    VSRB_CHECK_ARG(g->groups >= 1, "groups must be >= 1");
+    VSRB_CHECK_ARG(g->dtype == VSRB_BF16 || g->dtype == VSRB_F32, "bad dtype %d", g->dtype);
+    VSRB_CHECK_ARG(g->pixshuf == 0 || (g->pixshuf == 2 && g->cout % 64 == 0),
+                   "pixshuf needs factor 2 and cout %% 64 == 0");
+    VSRB_CHECK_ARG(g->transpose == 0, "transpose packing not implemented");
+    memset(p, 0, sizeof(*p));
+    p->kh = g->kh; p->kw = g->kw; p->n_seg = g->n_seg; p->groups = g->groups;
+    p->pixshuf = g->pixshuf; p->dtype = g->dtype;
+    p->cout = g->cout;
+    p->cout_pad = (int)round_up(g->cout, 16);
+    if (p->cout_pad <= 128) { p->n_tile = p->cout_pad; p->n_blocks = 1; }
+    else if (p->cout_pad % 128 == 0) { p->n_tile = 128; p->n_blocks = p->cout_pad / 128; }
+    else if (p->cout_pad % 64 == 0) { p->n_tile = 64; p->n_blocks = p->cout_pad / 64; }
+    else { p->n_tile = 16; p->n_blocks = p->cout_pad / 16; }
+    p->stages_per_tile = 0;
+    p->wblock_bytes = 0;
+    for (int s = 0; s < g->n_seg; ++s) {
+        SegPlan& sp = p->seg[s];
+        VSRB_CHECK_ARG(g->seg_c[s] >= 1 && g->seg_off[s] >= 0, "bad segment %d", s);
+        sp.c = g->seg_c[s];
+        sp.off = g->seg_off[s];
+        sp.cpad = (int)round_up(sp.c, 16);
+        sp.ck = (sp.cpad % 64 == 0) ? 64 : (sp.cpad % 32 == 0 ? 32 : 16);
+        sp.chunks = sp.cpad / sp.ck;
+        sp.rowbytes = sp.ck * 2;
+        sp.swz_mask = sp.ck == 64 ? 7 : (sp.ck == 32 ? 3 : 1);
+        sp.layout = sp.ck == 64 ? 2 : (sp.ck == 32 ? 4 : 6);
+        p->cin_packed += sp.c;
+        p->b_stage_bytes[s] = p->kh * p->n_tile * sp.rowbytes;
+        p->stages_per_tile += sp.chunks * p->kw;
+        p->wblock_bytes += (size_t)sp.chunks * p->kw * p->b_stage_bytes[s];
+    }
+    p->bias_bytes = round_up((size_t)p->groups * p->cout_pad * sizeof(float), 1024);
+    if (p->dtype == VSRB_BF16)
+        p->total_bytes = p->bias_bytes + (size_t)p->groups * p->n_blocks * p->wblock_bytes;
+    else
+        p->total_bytes = p->bias_bytes +
+                         (size_t)p->groups * p->kh * p->kw * p->cin_packed * p->cout_pad * sizeof(float);
+    return VSRB_OK;
+}
+
+// packed output channel n' -> original output channel (PixelShuffle(2) groups sub-pixels together)
+__host__ __device__ static inline int orig_cout(int np, int cout, int pixshuf) {
+    if (!pixshuf) return np;
+    int cq = cout / 4;
+    int q = np / cq, c = np - q * cq;
+    return 4 * c + q;
+}
+
+struct PackParams {
+    int kh, kw, n_seg, groups, pixshuf;
+    int seg_c[2], seg_off[2], seg_ck[2], seg_chunks[2], seg_rowbytes[2], seg_mask[2], seg_bstage[2];
+    int cin_total, cin_packed, cout, cout_pad, n_tile, n_blocks;
+    size_t wblock_bytes, bias_bytes;
+};
+
+__global__ void pack_bias_kernel(PackParams pp, const float* __restrict__ bias, float* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int total = pp.groups * pp.cout_pad;
+    if (i >= total) return;
+    int g = i / pp.cout_pad, np = i - g * pp.cout_pad;
+    float v = 0.f;
+    if (bias && np < pp.cout) v = bias[(size_t)g * pp.cout + orig_cout(np, pp.cout, pp.pixshuf)];
+    out[i] = v;
+}
+
+// Tensor-core image: [group][n_block][stage (seg, chunk, kx)][ky][n][ck] bf16, each stage
+// region stored exactly as it must sit in shared memory (swizzled K-major rows).
+__global__ void pack_tc_kernel(PackParams pp, const float* __restrict__ w, uint8_t* __restrict__ out) {
+    size_t elems_per_block = pp.wblock_bytes / 2;
+    size_t total = (size_t)pp.groups * pp.n_blocks * elems_per_block;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        size_t blk = i / elems_per_block;
+        size_t r = i - blk * elems_per_block;
+        int g = (int)(blk / pp.n_blocks), qb = (int)(blk % pp.n_blocks);
+        // locate segment / stage
+        int s = 0;
+        size_t seg0_elems = (size_t)pp.seg_chunks[0] * pp.kw * pp.seg_bstage[0] / 2;
+        size_t base_bytes = 0;
+        if (r >= seg0_elems) { s = 1; r -= seg0_elems; base_bytes = seg0_elems * 2; }
+        size_t st_elems = (size_t)pp.seg_bstage[s] / 2;
+        int local = (int)(r / st_elems);
+        size_t e = r - (size_t)local * st_elems;
+        int chunk = local / pp.kw, kx = local - chunk * pp.kw;
+        int ck = pp.seg_ck[s];
+        int row = (int)(e / ck), kk = (int)(e - (size_t)row * ck);
+        int ky = row / pp.n_tile, n = row - ky * pp.n_tile;
+        int np = qb * pp.n_tile + n;
+        int ci = chunk * ck + kk;
+        float v = 0.f;
+        if (np < pp.cout && ci < pp.seg_c[s]) {
+            int o = orig_cout(np, pp.cout, pp.pixshuf);
+            v = w[((((size_t)g * pp.cout + o) * pp.cin_total + pp.seg_off[s] + ci) * pp.kh + ky) * pp.kw + kx];
+        }
+        uint32_t off = (uint32_t)row * pp.seg_rowbytes[s] + (uint32_t)kk * 2;
+        off ^= ((off >> 7) & pp.seg_mask[s]) << 4;
+        size_t dst = blk * pp.wblock_bytes + base_bytes + (size_t)local * pp.seg_bstage[s] + off;
+        *reinterpret_cast<__nv_bfloat16*>(out + dst) = __float2bfloat16_rn(v);
+    }
+}
+
+// fp32 image: [group][tap][cin_packed][cout_pad]
+__global__ void pack_f32_kernel(PackParams pp, const float* __restrict__ w, float* __restrict__ out) {
+    size_t per_g = (size_t)pp.kh * pp.kw * pp.cin_packed * pp.cout_pad;
+    size_t total = per_g * pp.groups;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        int g = (int)(i / per_g);
+        size_t r = i - (size_t)g * per_g;
+        int np = (int)(r % pp.cout_pad);
+        r /= pp.cout_pad;
+        int cp = (int)(r % pp.cin_packed);
+        int tap = (int)(r / pp.cin_packed);
+        int ky = tap / pp.kw, kx = tap - ky * pp.kw;
+        int s = 0, ci = cp;
+        if (pp.n_seg == 2 && cp >= pp.seg_c[0]) { s = 1; ci = cp - pp.seg_c[0]; }
+        float v = 0.f;
+        if (np < pp.cout) {
+            int o = orig_cout(np, pp.cout, pp.pixshuf);
+            v = w[((((size_t)g * pp.cout + o) * pp.cin_total + pp.seg_off[s] + ci) * pp.kh + ky) * pp.kw + kx];
+        }
+        out[i] = v;
+    }
+}
+
+int launch_pack(const vsrb_conv_geom* g, const ConvPlan& p, const float* w, int cin_total, const float* bias,
+                void* packed, cudaStream_t s) {
+    PackParams pp;
+    memset(&pp, 0, sizeof(pp));
+    pp.kh = p.kh; pp.kw = p.kw; pp.n_seg = p.n_seg; pp.groups = p.groups; pp.pixshuf = p.pixshuf;
+    for (int i = 0; i < p.n_seg; ++i) {
+        pp.seg_c[i] = p.seg[i].c; pp.seg_off[i] = p.seg[i].off; pp.seg_ck[i] = p.seg[i].ck;
+        pp.seg_chunks[i] = p.seg[i].chunks; pp.seg_rowbytes[i] = p.seg[i].rowbytes;
+        pp.seg_mask[i] = p.seg[i].swz_mask; pp.seg_bstage[i] = p.b_stage_bytes[i];
+        VSRB_CHECK_ARG(p.seg[i].off + p.seg[i].c <= cin_total, "segment %d exceeds cin_total %d", i, cin_total);
+    }
+    pp.cin_total = cin_total; pp.cin_packed = p.cin_packed; pp.cout = p.cout; pp.cout_pad = p.cout_pad;
+    pp.n_tile = p.n_tile; pp.n_blocks = p.n_blocks; pp.wblock_bytes = p.wblock_bytes; pp.bias_bytes = p.bias_bytes;
+    int nb = p.groups * p.cout_pad;
+    pack_bias_kernel<<<ceil_div(nb, 256), 256, 0, s>>>(pp, bias, reinterpret_cast<float*>(packed));
+    VSRB_LAUNCH_CHECK();
+    uint8_t* wp = reinterpret_cast<uint8_t*>(packed) + p.bias_bytes;
+    if (p.dtype == VSRB_BF16) {
+        size_t total = (size_t)p.groups * p.n_blocks * p.wblock_bytes / 2;
+        int blocks = (int)((total + 255) / 256);
+        if (blocks > 4096) blocks = 4096;
+        pack_tc_kernel<<<blocks, 256, 0, s>>>(pp, w, wp);
+    } else {
+        size_t total = (size_t)p.groups * p.kh * p.kw * p.cin_packed * p.cout_pad;
+        int blocks = (int)((total + 255) / 256);
+        if (blocks > 4096) blocks = 4096;
+        pack_f32_kernel<<<blocks, 256, 0, s>>>(pp, w, reinterpret_cast<float*>(wp));
+    }
+    VSRB_LAUNCH_CHECK();
+    return VSRB_OK;
+}
+
+void fill_epi(const vsrb_conv_args* a, const ConvPlan& p, EpiParams* e) {
+    e->mode = a->epilogue; e->act = a->act; e->slope = a->slope;
+    e->H = a->h; e->W = a->w;
+    e->cout_pad = p.cout_pad; e->cq = p.pixshuf ? p.cout / 4 : 0; e->pixshuf = p.pixshuf;
+    e->out = a->out; e->out_c = a->out_c; e->res = a->residual; e->res_c = a->res_c;
+    {
+        long long oh = p.pixshuf ? 2LL * a->h : a->h, ow = p.pixshuf ? 2LL * a->w : a->w;
+        e->out_img_stride = a->out_img_stride ? a->out_img_stride : oh * ow * a->out_c;
+        e->out_group_stride = a->out_group_stride ? a->out_group_stride : e->out_img_stride * a->imgs_per_group;
+        e->imgs_per_group = a->imgs_per_group;
+    }
+    e->f32_io = a->f32_io; e->f32_in = a->f32_in; e->aux_h = a->aux_h; e->aux_w = a->aux_w;
+    e->bias = reinterpret_cast<const float*>(a->packed);
+}
+
+}  // namespace vsrb
+
+using namespace vsrb;
+
+extern "C" {
+
+int vsrb_version(void) { return VSRB_VERSION; }
+const char* vsrb_last_error(void) { return g_err; }
+int64_t vsrb_launch_count(void) { return g_launches.load(); }
+
+int vsrb_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor) {
+    int dev = 0;
+    VSRB_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    VSRB_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    return VSRB_OK;
+}
+
+int vsrb_debug_status(void* stream) {
+    int v = 0;
+    int* p = debug_flag();
+    VSRB_CUDA(cudaMemcpyAsync(&v, p, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    VSRB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    if (v) {
+        int z = 0;
+        VSRB_CUDA(cudaMemcpyAsync(p, &z, sizeof(int), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+        VSRB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    }
+    return v;
+}
+
+size_t vsrb_packed_weight_bytes(const vsrb_conv_geom* g) {
+    ConvPlan p;
+    if (make_plan(g, &p) != VSRB_OK) return 0;
+    return p.total_bytes;
+}
+
+int vsrb_pack_conv_weight(const vsrb_conv_geom* g, const float* w, int32_t cin_total, const float* bias,
+                          void* packed, void* stream) {
+    ConvPlan p;
+    int rc = make_plan(g, &p);
+    if (rc != VSRB_OK) return rc;
+    VSRB_CHECK_ARG(w && packed, "null weight / packed pointer");
+    return launch_pack(g, p, w, cin_total, bias, packed, (cudaStream_t)stream);
+}
+
+int vsrb_conv2d_fwd(const vsrb_conv_args* a, void* stream) {
+    VSRB_CHECK_ARG(a, "null args");
+    ConvPlan p;
+    int rc = make_plan(&a->geom, &p);
+    if (rc != VSRB_OK) return rc;
+    VSRB_CHECK_ARG(a->batch >= 1 && a->h >= 1 && a->w >= 1, "bad extent %dx%dx%d", a->batch, a->h, a->w);
+    VSRB_CHECK_ARG(a->imgs_per_group >= 1 && a->imgs_per_group * p.groups == a->batch,
+                   "batch %d != groups %d * imgs_per_group %d", a->batch, p.groups, a->imgs_per_group);
+    VSRB_CHECK_ARG(a->packed, "null packed weights");
+    for (int s = 0; s < p.n_seg; ++s) {
+        VSRB_CHECK_ARG(a->in[s], "null input segment %d", s);
+        int need = p.dtype == VSRB_BF16 ? p.seg[s].cpad : p.seg[s].c;
+        VSRB_CHECK_ARG(a->in_c[s] >= need, "segment %d: %d channels allocated, need %d", s, a->in_c[s], need);
+    }
+    switch (a->epilogue) {
+        case VSRB_EPI_NHWC:
+            VSRB_CHECK_ARG(a->out && a->out_c >= (p.pixshuf ? p.cout / 4 : p.cout_pad),
+                           "EPI_NHWC: out_c %d too small", a->out_c);
+            VSRB_CHECK_ARG(!a->residual || (!p.pixshuf && a->res_c >= p.cout_pad), "bad residual");
+            VSRB_CHECK_ARG(a->out_c % 8 == 0 && (!a->residual || a->res_c % 8 == 0), "channel strides must be %% 8");
+            break;
+        case VSRB_EPI_CLEAN:
+            VSRB_CHECK_ARG(p.cout == 3 && a->f32_io && a->out && a->out_c >= 3 && a->out_c <= 16 && !p.pixshuf,
+                           "EPI_CLEAN needs cout==3, f32_io, out with 3..16 channels");
+            break;
+        case VSRB_EPI_FLOW:
+            VSRB_CHECK_ARG(p.cout == 2 && a->f32_io && a->f32_in && !p.pixshuf, "EPI_FLOW needs cout==2, f32_io, f32_in");
+            break;
+        case VSRB_EPI_SR:
+            VSRB_CHECK_ARG(p.cout == 3 && a->f32_io && a->f32_in && a->aux_h >= 1 && a->aux_w >= 1 && !p.pixshuf,
+                           "EPI_SR needs cout==3, f32_io, f32_in, aux_h/w");
+            break;
+        default:
+            VSRB_CHECK_ARG(false, "unknown epilogue %d", a->epilogue);
+    }
+    if (p.dtype == VSRB_BF16) return launch_conv_tc(a, p, (cudaStream_t)stream);
+    return launch_conv_f32(a, p, (cudaStream_t)stream);
+}
+
+}  // extern "C"

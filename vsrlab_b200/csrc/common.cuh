@@ -1,0 +1,264 @@
+// Internal helpers shared by every translation unit of libvsrb200.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/vsrb200.h"
+
+namespace vsrb {
+
+// ---------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+void count_launch();
+int* debug_flag();   // device flag raised by kernels on a pipeline time-out
+
+#define VSRB_CHECK_ARG(cond, ...)                      \
+    do {                                               \
+        if (!(cond)) {                                 \
+            vsrb::set_error(__VA_ARGS__);              \
+            return VSRB_E_ARG;                         \
+        }                                              \
+    } while (0)
+
+#define VSRB_CUDA(call)                                                                   \
+    do {                                                                                  \
+        cudaError_t e__ = (call);                                                         \
+        if (e__ != cudaSuccess) {                                                         \
+            vsrb::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),      \
+                            __FILE__, __LINE__);                                          \
+            return VSRB_E_CUDA;                                                           \
+        }                                                                                 \
+    } while (0)
+
+#define VSRB_LAUNCH_CHECK()                                                               \
+    do {                                                                                  \
+        vsrb::count_launch();                                                             \
+        cudaError_t e__ = cudaGetLastError();                                             \
+        if (e__ != cudaSuccess) {                                                         \
+            vsrb::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__),  \
+                            __FILE__, __LINE__);                                          \
+            return VSRB_E_CUDA;                                                           \
+        }                                                                                 \
+    } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline size_t round_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
+
+// ---------------------------------------------------------------------------------------
+// conv geometry shared by packer and launchers
+// ---------------------------------------------------------------------------------------
+struct SegPlan {
+    int c;         // real channels
+    int cpad;      // padded to 16
+    int ck;        // channels per K chunk: 16, 32 or 64   (tensor-core path)
+    int chunks;    // cpad / ck
+    int rowbytes;  // ck * 2: the shared-memory row of one pixel / one filter row
+    int swz_mask;  // 1, 3, 7  (bits of addr>>7 XORed into addr>>4)
+    int layout;    // UMMA layout_type: 6 (32B), 4 (64B), 2 (128B)
+    int off;       // offset on the OIHW input-channel axis
+};
+
+struct ConvPlan {
+    int kh, kw, n_seg, groups, pixshuf, dtype;
+    SegPlan seg[2];
+    int cin_packed;        // sum of real segment channels (fp32 path K extent per tap)
+    int cout, cout_pad;    // cout_pad = round_up(cout, 16)
+    int n_tile, n_blocks;  // tensor-core path: output channels per CTA, CTAs along N
+    int stages_per_tile;   // sum over segments of chunks*kw
+    int b_stage_bytes[2];  // kh * n_tile * rowbytes
+    size_t wblock_bytes;   // packed weights of one (group, n_block)
+    size_t bias_bytes;     // groups*cout_pad floats rounded to 1 KiB
+    size_t total_bytes;
+};
+
+int make_plan(const vsrb_conv_geom* g, ConvPlan* p);   // returns VSRB_OK or error
+
+// ---------------------------------------------------------------------------------------
+// epilogue shared by the tensor-core and the fp32 conv kernels
+// ---------------------------------------------------------------------------------------
+struct EpiParams {
+    int mode, act;
+    float slope;
+    int H, W;             // conv extent
+    int cout_pad, cq;     // cq = cout/4 when pixshuf
+    int pixshuf;
+    void* out;
+    int out_c;
+    long long out_img_stride, out_group_stride;   // elements
+    int imgs_per_group;
+    const void* res;
+    int res_c;
+    float* f32_io;
+    const float* f32_in;
+    int aux_h, aux_w;
+    const float* bias;    // [groups][cout_pad], packed channel order
+};
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
+    __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&u);
+    return __bfloat1622float2(t);
+}
+
+template <typename T> struct Act;   // activation storage helpers
+template <> struct Act<__nv_bfloat16> {
+    static constexpr int kDtype = VSRB_BF16;
+    __device__ static void load16(const void* p, float (&v)[16]) {
+        const uint4* q = reinterpret_cast<const uint4*>(p);
+        uint4 a = __ldg(q), b = __ldg(q + 1);
+        uint32_t u[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float2 f = unpack_bf16(u[i]);
+            v[2 * i] = f.x;
+            v[2 * i + 1] = f.y;
+        }
+    }
+    __device__ static void store16(void* p, const float (&v)[16]) {
+        uint4 a, b;
+        a.x = pack_bf16(v[0], v[1]);   a.y = pack_bf16(v[2], v[3]);
+        a.z = pack_bf16(v[4], v[5]);   a.w = pack_bf16(v[6], v[7]);
+        b.x = pack_bf16(v[8], v[9]);   b.y = pack_bf16(v[10], v[11]);
+        b.z = pack_bf16(v[12], v[13]); b.w = pack_bf16(v[14], v[15]);
+        uint4* q = reinterpret_cast<uint4*>(p);
+        q[0] = a;
+        q[1] = b;
+    }
+    __device__ static void store_n(void* p, const float* v, int n) {   // n <= 16, generic
+        __nv_bfloat16* q = reinterpret_cast<__nv_bfloat16*>(p);
+        for (int i = 0; i < n; ++i) q[i] = __float2bfloat16_rn(v[i]);
+    }
+};
+template <> struct Act<float> {
+    static constexpr int kDtype = VSRB_F32;
+    __device__ static void load16(const void* p, float (&v)[16]) {
+        const float4* q = reinterpret_cast<const float4*>(p);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float4 f = __ldg(q + i);
+            v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
+        }
+    }
+    __device__ static void store16(void* p, const float (&v)[16]) {
+        float4* q = reinterpret_cast<float4*>(p);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) q[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    }
+    __device__ static void store_n(void* p, const float* v, int n) {
+        float* q = reinterpret_cast<float*>(p);
+        for (int i = 0; i < n; ++i) q[i] = v[i];
+    }
+};
+
+// ATen upsample_bilinear2d(align_corners=False) source tap for one axis
+__device__ __forceinline__ void up_tap(int dst, float scale, int in_size, int& i0, int& i1, float& l1) {
+    float src = (dst + 0.5f) * scale - 0.5f;
+    src = src < 0.f ? 0.f : src;
+    i0 = (int)src;
+    if (i0 > in_size - 1) i0 = in_size - 1;
+    i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+    l1 = src - (float)i0;
+}
+
+// One pixel (b,y,x), 16 consecutive packed output channels starting at n0 (multiple of 16),
+// v = raw accumulators.  `g` = weight group of image b.
+template <typename T>
+__device__ __forceinline__ void epi_store16(const EpiParams& e, int g, int b, int y, int x, int n0, float (&v)[16]) {
+    const float4* bp = reinterpret_cast<const float4*>(e.bias + (size_t)g * e.cout_pad + n0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float4 f = __ldg(bp + i);
+        v[4 * i] += f.x; v[4 * i + 1] += f.y; v[4 * i + 2] += f.z; v[4 * i + 3] += f.w;
+    }
+    if (e.act == VSRB_ACT_RELU) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+    } else if (e.act == VSRB_ACT_LRELU) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = v[i] >= 0.f ? v[i] : v[i] * e.slope;
+    }
+    if (e.mode == VSRB_EPI_NHWC) {
+        int Y = y, X = x, OH = e.H, OW = e.W, c0 = n0;
+        if (e.pixshuf) {
+            int q = n0 / e.cq;
+            c0 = n0 - q * e.cq;
+            Y = 2 * y + (q >> 1);
+            X = 2 * x + (q & 1);
+            OH = 2 * e.H;
+            OW = 2 * e.W;
+        }
+        if (e.res) {
+            float r[16];
+            size_t pix = ((size_t)b * OH + Y) * OW + X;
+            Act<T>::load16(reinterpret_cast<const T*>(e.res) + pix * e.res_c + c0, r);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += r[i];
+        }
+        long long o = (long long)g * e.out_group_stride + (long long)(b - g * e.imgs_per_group) * e.out_img_stride +
+                      ((long long)Y * OW + X) * e.out_c + c0;
+        Act<T>::store16(reinterpret_cast<T*>(e.out) + o, v);
+    } else if (e.mode == VSRB_EPI_CLEAN) {
+        if (n0 != 0) return;
+        float nv[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) nv[i] = 0.f;
+        size_t plane = (size_t)e.H * e.W;
+        float* xp = e.f32_io + (size_t)b * 3 * plane + (size_t)y * e.W + x;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float t = xp[c * plane] + v[c];
+            xp[c * plane] = t;
+            nv[c] = t;
+        }
+        size_t pix = ((size_t)b * e.H + y) * e.W + x;
+        T* op = reinterpret_cast<T*>(e.out) + pix * e.out_c;
+        if (e.out_c >= 16) Act<T>::store16(op, nv);
+        else Act<T>::store_n(op, nv, e.out_c);
+    } else if (e.mode == VSRB_EPI_FLOW) {
+        if (n0 != 0) return;
+        size_t pix = ((size_t)b * e.H + y) * e.W + x;
+        float2 f = __ldg(reinterpret_cast<const float2*>(e.f32_in) + pix);
+        reinterpret_cast<float2*>(e.f32_io)[pix] = make_float2(f.x + v[0], f.y + v[1]);
+    } else {   // VSRB_EPI_SR
+        if (n0 != 0) return;
+        int ih = e.aux_h, iw = e.aux_w;
+        float sy = (float)ih / (float)e.H, sx = (float)iw / (float)e.W;
+        int y0, y1, x0, x1;
+        float ly, lx;
+        up_tap(y, sy, ih, y0, y1, ly);
+        up_tap(x, sx, iw, x0, x1, lx);
+        float hy = 1.f - ly, hx = 1.f - lx;
+        size_t iplane = (size_t)ih * iw, oplane = (size_t)e.H * e.W;
+        const float* lp = e.f32_in + (size_t)b * 3 * iplane;
+        float* op = e.f32_io + (size_t)b * 3 * oplane + (size_t)y * e.W + x;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float* cp = lp + c * iplane;
+            float a00 = __ldg(cp + y0 * iw + x0), a01 = __ldg(cp + y0 * iw + x1);
+            float a10 = __ldg(cp + y1 * iw + x0), a11 = __ldg(cp + y1 * iw + x1);
+            float up = hy * (hx * a00 + lx * a01) + ly * (hx * a10 + lx * a11);
+            op[c * oplane] = v[c] + up;
+        }
+    }
+}
+#endif  // __CUDACC__
+
+// launchers implemented in the kernel translation units
+int launch_conv_tc(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t s);
+int launch_conv_f32(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t s);
+int launch_pack(const vsrb_conv_geom* g, const ConvPlan& p, const float* w, int cin_total, const float* bias,
+                void* packed, cudaStream_t s);
+void fill_epi(const vsrb_conv_args* a, const ConvPlan& p, EpiParams* e);
+
+}  // namespace vsrb

@@ -1,0 +1,396 @@
+// Memory-bound resampling kernels: backward warp (flow_warp), layout changes, SPyNet glue.
+// All activations NHWC; every gather is a 16-byte vector of consecutive channels.
+#include "common.cuh"
+
+namespace vsrb {
+
+// ---------------------------------------------------------------------------------------
+// flow_warp  (reference spynet.py:95-106)
+//
+// A CTA owns 256 consecutive pixels.  Phase 1: the 256 flow vectors are read with one
+// coalesced float2 load per thread and turned, ONCE per pixel, into four tap offsets and
+// four bilinear weights that are staged in shared memory.  Phase 2: C/VEC threads per pixel
+// each gather four 16-byte channel vectors (coalesced: the C/VEC threads of a pixel read one
+// contiguous C*sizeof(T) run per tap), blend in fp32 and store one 16-byte vector.
+// Algorithmic traffic: C*sizeof(T) read + 8 B flow + C*sizeof(T) written per pixel.
+// ---------------------------------------------------------------------------------------
+struct TapSet {
+    int off[4];     // pixel index of the tap inside the image, or -1 when it contributes zero
+    float wgt[4];
+};
+
+__device__ __forceinline__ void sample_pos(float px, float py, int w, int h, float& ix, float& iy) {
+    // the reference normalises to [-1,1] and grid_sample(align_corners=True) maps back
+    float nx = 2.0f * px / (float)max(w - 1, 1) - 1.0f;
+    float ny = 2.0f * py / (float)max(h - 1, 1) - 1.0f;
+    ix = (nx + 1.0f) / 2.0f * (float)(w - 1);
+    iy = (ny + 1.0f) / 2.0f * (float)(h - 1);
+}
+
+__device__ __forceinline__ void make_taps(float ix, float iy, int w, int h, int border, TapSet& t) {
+    if (border) {
+        ix = fminf(fmaxf(ix, 0.f), (float)(w - 1));
+        iy = fminf(fmaxf(iy, 0.f), (float)(h - 1));
+    }
+    float fx = floorf(ix), fy = floorf(iy);
+    float wx1 = ix - fx, wy1 = iy - fy, wx0 = 1.f - wx1, wy0 = 1.f - wy1;
+    // guard the float->int conversion for wild flows
+    fx = fminf(fmaxf(fx, -2.f), (float)w);
+    fy = fminf(fmaxf(fy, -2.f), (float)h);
+    int x0 = (int)fx, y0 = (int)fy;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        int xi = x0 + (k & 1), yi = y0 + (k >> 1);
+        bool ok = xi >= 0 && xi < w && yi >= 0 && yi < h;
+        t.off[k] = ok ? yi * w + xi : -1;
+        t.wgt[k] = ((k & 1) ? wx1 : wx0) * ((k >> 1) ? wy1 : wy0);
+    }
+}
+
+template <typename T> struct Vec16;
+template <> struct Vec16<__nv_bfloat16> {
+    static constexpr int N = 8;
+    __device__ static void load(const __nv_bfloat16* p, float (&v)[8]) {
+        uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+        float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+    }
+    __device__ static void store(__nv_bfloat16* p, const float (&v)[8]) {
+        uint4 u;
+        u.x = pack_bf16(v[0], v[1]); u.y = pack_bf16(v[2], v[3]);
+        u.z = pack_bf16(v[4], v[5]); u.w = pack_bf16(v[6], v[7]);
+        *reinterpret_cast<uint4*>(p) = u;
+    }
+};
+template <> struct Vec16<float> {
+    static constexpr int N = 4;
+    __device__ static void load(const float* p, float (&v)[4]) {
+        float4 f = __ldg(reinterpret_cast<const float4*>(p));
+        v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+    }
+    __device__ static void store(float* p, const float (&v)[4]) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+
+static constexpr int kWarpPix = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(256) flow_warp_kernel(const T* __restrict__ x, long long x_stride,
+                                                        const float2* __restrict__ flow, long long f_stride,
+                                                        T* __restrict__ out, int n, int h, int w, int c, int border) {
+    __shared__ TapSet taps[kWarpPix];
+    constexpr int VEC = Vec16<T>::N;
+    const int tpp = c / VEC;                         // threads (16-byte vectors) per pixel
+    const long long total = (long long)n * h * w;
+    const long long pix0 = (long long)blockIdx.x * kWarpPix;
+    {
+        long long pix = pix0 + threadIdx.x;
+        if (pix < total) {
+            int xx = (int)(pix % w);
+            int yy = (int)((pix / w) % h);
+            float2 f = __ldg(flow + (pix / ((long long)h * w)) * f_stride + pix % ((long long)h * w));
+            float ix, iy;
+            sample_pos((float)xx + f.x, (float)yy + f.y, w, h, ix, iy);
+            make_taps(ix, iy, w, h, border, taps[threadIdx.x]);
+        }
+    }
+    __syncthreads();
+    const int work = kWarpPix * tpp;
+    for (int i = threadIdx.x; i < work; i += 256) {
+        const int lp = i / tpp, part = i - lp * tpp;
+        const long long pix = pix0 + lp;
+        if (pix >= total) break;
+        const TapSet t = taps[lp];
+        const T* img = x + (pix / ((long long)h * w)) * x_stride + part * VEC;
+        float acc[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (t.off[k] >= 0) {
+                float v[VEC];
+                Vec16<T>::load(img + (long long)t.off[k] * c, v);
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) acc[j] = fmaf(v[j], t.wgt[k], acc[j]);
+            }
+        }
+        Vec16<T>::store(out + pix * c + part * VEC, acc);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// layout
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int n, int c, int h, int w, int c_dst) {
+    const long long plane = (long long)h * w;
+    const long long total = (long long)n * plane;
+    for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < total;
+         pix += (long long)gridDim.x * blockDim.x) {
+        const long long img = pix / plane, r = pix - img * plane;
+        const float* sp = src + img * c * plane + r;
+        T* dp = dst + pix * c_dst;
+        for (int k = 0; k < c_dst; ++k) {
+            float v = k < c ? __ldg(sp + k * plane) : 0.f;
+            dp[k] = (T)v;
+        }
+    }
+}
+
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, float* __restrict__ dst, int n, int c, int h, int w, int c_src) {
+    const long long plane = (long long)h * w;
+    const long long total = (long long)n * c * plane;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i % plane;
+        const long long nc = i / plane;
+        const int k = (int)(nc % c);
+        const long long img = nc / c;
+        dst[i] = (float)src[(img * plane + r) * c_src + k];
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// SPyNet glue
+// ---------------------------------------------------------------------------------------
+__global__ void pyramid_base_kernel(const float* __restrict__ frames, float4* __restrict__ lvl, int F, int h, int w, int Hp,
+                                    int Wp, float m0, float m1, float m2, float s0, float s1, float s2) {
+    const long long total = (long long)F * Hp * Wp;
+    const float sy = (float)h / (float)Hp, sx = (float)w / (float)Wp;
+    const long long plane = (long long)h * w;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int X = (int)(i % Wp), Y = (int)((i / Wp) % Hp);
+        const long long f = i / ((long long)Wp * Hp);
+        int y0, y1, x0, x1;
+        float ly, lx;
+        up_tap(Y, sy, h, y0, y1, ly);
+        up_tap(X, sx, w, x0, x1, lx);
+        const float hy = 1.f - ly, hx = 1.f - lx;
+        float v[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float* p = frames + (f * 3 + c) * plane;
+            float a00 = __ldg(p + y0 * w + x0), a01 = __ldg(p + y0 * w + x1);
+            float a10 = __ldg(p + y1 * w + x0), a11 = __ldg(p + y1 * w + x1);
+            v[c] = hy * (hx * a00 + lx * a01) + ly * (hx * a10 + lx * a11);
+        }
+        lvl[i] = make_float4((v[0] - m0) / s0, (v[1] - m1) / s1, (v[2] - m2) / s2, 0.f);
+    }
+}
+
+__global__ void avgpool2_c4_kernel(const float4* __restrict__ in, float4* __restrict__ out, int F, int H, int W) {
+    const int Ho = H / 2, Wo = W / 2;
+    const long long total = (long long)F * Ho * Wo;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int X = (int)(i % Wo), Y = (int)((i / Wo) % Ho);
+        const long long f = i / ((long long)Wo * Ho);
+        const float4* p = in + (f * H + 2 * Y) * W + 2 * X;
+        float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + W), d = __ldg(p + W + 1);
+        out[i] = make_float4((((a.x + b.x) + c.x) + d.x) * 0.25f, (((a.y + b.y) + c.y) + d.y) * 0.25f,
+                             (((a.z + b.z) + c.z) + d.z) * 0.25f, 0.f);
+    }
+}
+
+// ATen upsample_bilinear2d(align_corners=True) source tap for one axis
+__device__ __forceinline__ void up_tap_ac(int dst, int in_size, int out_size, int& i0, int& i1, float& l1) {
+    const float scale = out_size > 1 ? (float)(in_size - 1) / (float)(out_size - 1) : 0.f;
+    const float src = scale * (float)dst;
+    i0 = (int)src;
+    if (i0 > in_size - 1) i0 = in_size - 1;
+    i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+    l1 = src - (float)i0;
+}
+
+template <typename T>
+__global__ void level_input_kernel(const float4* __restrict__ lvl, const int* __restrict__ ref_idx,
+                                   const int* __restrict__ supp_idx, const float2* __restrict__ flow_prev,
+                                   float2* __restrict__ flow_up, T* __restrict__ conv_in, int P, int Hl, int Wl, int c_in) {
+    const long long plane = (long long)Hl * Wl;
+    const long long total = (long long)P * plane;
+    const int Hi = Hl / 2, Wi = Wl / 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int X = (int)(i % Wl), Y = (int)((i / Wl) % Hl);
+        const int p = (int)(i / plane);
+        float2 fu = make_float2(0.f, 0.f);
+        if (flow_prev) {
+            int y0, y1, x0, x1;
+            float ly, lx;
+            up_tap_ac(Y, Hi, Hl, y0, y1, ly);
+            up_tap_ac(X, Wi, Wl, x0, x1, lx);
+            const float hy = 1.f - ly, hx = 1.f - lx;
+            const float2* fp = flow_prev + (long long)p * Hi * Wi;
+            float2 a00 = __ldg(fp + y0 * Wi + x0), a01 = __ldg(fp + y0 * Wi + x1);
+            float2 a10 = __ldg(fp + y1 * Wi + x0), a11 = __ldg(fp + y1 * Wi + x1);
+            fu.x = (hy * (hx * a00.x + lx * a01.x) + ly * (hx * a10.x + lx * a11.x)) * 2.0f;
+            fu.y = (hy * (hx * a00.y + lx * a01.y) + ly * (hx * a10.y + lx * a11.y)) * 2.0f;
+        }
+        flow_up[i] = fu;
+        float ix, iy;
+        sample_pos((float)X + fu.x, (float)Y + fu.y, Wl, Hl, ix, iy);
+        TapSet t;
+        make_taps(ix, iy, Wl, Hl, 1, t);
+        const float4* sp = lvl + (long long)__ldg(supp_idx + p) * plane;
+        float wr = 0.f, wg = 0.f, wb = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (t.off[k] >= 0) {
+                float4 v = __ldg(sp + t.off[k]);
+                wr = fmaf(v.x, t.wgt[k], wr);
+                wg = fmaf(v.y, t.wgt[k], wg);
+                wb = fmaf(v.z, t.wgt[k], wb);
+            }
+        }
+        const float4 r = __ldg(lvl + (long long)__ldg(ref_idx + p) * plane + (long long)Y * Wl + X);
+        float v[16] = {r.x, r.y, r.z, wr, wg, wb, fu.x, fu.y, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        T* op = conv_in + i * c_in;
+        if (c_in == 16) Act<T>::store16(op, v);
+        else {
+            for (int k = 0; k < c_in; ++k) op[k] = (T)(k < 8 ? v[k] : 0.f);
+        }
+    }
+}
+
+__global__ void flow_resize_kernel(const float2* __restrict__ fin, float2* __restrict__ fout, int P, int Hp, int Wp, int h,
+                                   int w) {
+    const long long total = (long long)P * h * w;
+    const float sy = (float)Hp / (float)h, sx = (float)Wp / (float)w;
+    const float rx = (float)((double)w / (double)Wp), ry = (float)((double)h / (double)Hp);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int X = (int)(i % w), Y = (int)((i / w) % h);
+        const long long p = i / ((long long)w * h);
+        int y0, y1, x0, x1;
+        float ly, lx;
+        up_tap(Y, sy, Hp, y0, y1, ly);
+        up_tap(X, sx, Wp, x0, x1, lx);
+        const float hy = 1.f - ly, hx = 1.f - lx;
+        const float2* fp = fin + p * Hp * Wp;
+        float2 a00 = __ldg(fp + y0 * Wp + x0), a01 = __ldg(fp + y0 * Wp + x1);
+        float2 a10 = __ldg(fp + y1 * Wp + x0), a11 = __ldg(fp + y1 * Wp + x1);
+        float vx = hy * (hx * a00.x + lx * a01.x) + ly * (hx * a10.x + lx * a11.x);
+        float vy = hy * (hx * a00.y + lx * a01.y) + ly * (hx * a10.y + lx * a11.y);
+        fout[i] = make_float2(vx * rx, vy * ry);
+    }
+}
+
+static inline int grid_for(long long total, int block) {
+    long long b = (total + block - 1) / block;
+    if (b > 148 * 32) b = 148 * 32;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+}  // namespace vsrb
+
+using namespace vsrb;
+
+extern "C" {
+
+int vsrb_flow_warp(const void* x, int64_t x_img_stride, const float* flow, int64_t flow_img_stride, void* out, int32_t n,
+                   int32_t h, int32_t w, int32_t c, int32_t dtype, int32_t padding_mode, void* stream) {
+    const long long xs = x_img_stride ? x_img_stride : (long long)h * w * c;
+    const long long fs = flow_img_stride ? flow_img_stride : (long long)h * w;
+    VSRB_CHECK_ARG(x && flow && out && n >= 1 && h >= 1 && w >= 1, "flow_warp: bad arguments");
+    VSRB_CHECK_ARG(padding_mode == VSRB_PAD_ZEROS || padding_mode == VSRB_PAD_BORDER, "flow_warp: bad padding mode");
+    VSRB_CHECK_ARG((long long)h * w < (1LL << 31), "flow_warp: image too large");
+    const long long total = (long long)n * h * w;
+    const int blocks = (int)((total + kWarpPix - 1) / kWarpPix);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == VSRB_BF16) {
+        VSRB_CHECK_ARG(c % 8 == 0, "flow_warp: bf16 needs c %% 8 == 0 (got %d)", c);
+        flow_warp_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), xs,
+                                                               reinterpret_cast<const float2*>(flow), fs,
+                                                               reinterpret_cast<__nv_bfloat16*>(out), n, h, w, c, padding_mode);
+    } else if (dtype == VSRB_F32) {
+        VSRB_CHECK_ARG(c % 4 == 0, "flow_warp: fp32 needs c %% 4 == 0 (got %d)", c);
+        flow_warp_kernel<float><<<blocks, 256, 0, s>>>(reinterpret_cast<const float*>(x), xs,
+                                                       reinterpret_cast<const float2*>(flow), fs,
+                                                       reinterpret_cast<float*>(out), n, h, w, c, padding_mode);
+    } else {
+        VSRB_CHECK_ARG(false, "flow_warp: bad dtype");
+    }
+    VSRB_LAUNCH_CHECK();
+    return VSRB_OK;
+}
+
+int vsrb_nchw_to_nhwc(const float* src, void* dst, int32_t n, int32_t c, int32_t h, int32_t w, int32_t c_dst, int32_t dtype,
+                      void* stream) {
+    VSRB_CHECK_ARG(src && dst && n >= 1 && c >= 1 && c_dst >= c, "nchw_to_nhwc: bad arguments");
+    const long long total = (long long)n * h * w;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == VSRB_BF16)
+        nchw_to_nhwc_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, s>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n, c, h,
+                                                                                 w, c_dst);
+    else
+        nchw_to_nhwc_kernel<float><<<grid_for(total, 256), 256, 0, s>>>(src, reinterpret_cast<float*>(dst), n, c, h, w, c_dst);
+    VSRB_LAUNCH_CHECK();
+    return VSRB_OK;
+}
+
+int vsrb_nhwc_to_nchw(const void* src, float* dst, int32_t n, int32_t c, int32_t h, int32_t w, int32_t c_src, int32_t dtype,
+                      void* stream) {
+    VSRB_CHECK_ARG(src && dst && n >= 1 && c >= 1 && c_src >= c, "nhwc_to_nchw: bad arguments");
+    const long long total = (long long)n * c * h * w;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == VSRB_BF16)
+        nhwc_to_nchw_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(src), dst, n,
+                                                                                 c, h, w, c_src);
+    else
+        nhwc_to_nchw_kernel<float><<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const float*>(src), dst, n, c, h, w, c_src);
+    VSRB_LAUNCH_CHECK();
+    return VSRB_OK;
+}
+
+int vsrb_spynet_pyramid_base(const float* frames, float* lvl, int32_t F, int32_t h, int32_t w, int32_t Hp, int32_t Wp,
+                             const float* mean3, const float* std3, void* stream) {
+    VSRB_CHECK_ARG(frames && lvl && mean3 && std3 && F >= 1 && Hp % 32 == 0 && Wp % 32 == 0 && Hp >= h && Wp >= w,
+                   "pyramid_base: bad arguments");
+    const long long total = (long long)F * Hp * Wp;
+    pyramid_base_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(frames, reinterpret_cast<float4*>(lvl), F, h, w, Hp,
+                                                                                 Wp, mean3[0], mean3[1], mean3[2], std3[0], std3[1],
+                                                                                 std3[2]);
+    VSRB_LAUNCH_CHECK();
+    return VSRB_OK;
+}
+
+int vsrb_avgpool2_c4(const float* in, float* out, int32_t F, int32_t H, int32_t W, void* stream) {
+    VSRB_CHECK_ARG(in && out && F >= 1 && H % 2 == 0 && W % 2 == 0, "avgpool2: bad arguments");
+    const long long total = (long long)F * (H / 2) * (W / 2);
+    avgpool2_c4_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(in),
+                                                                                reinterpret_cast<float4*>(out), F, H, W);
+    VSRB_LAUNCH_CHECK();
+    return VSRB_OK;
+}
+
+int vsrb_spynet_level_input(const float* lvl, const int32_t* ref_idx, const int32_t* supp_idx, const float* flow_prev,
+                            float* flow_up, void* conv_in, int32_t P, int32_t Hl, int32_t Wl, int32_t c_in, int32_t dtype,
+                            void* stream) {
+    VSRB_CHECK_ARG(lvl && ref_idx && supp_idx && flow_up && conv_in && P >= 1 && c_in >= 8, "level_input: bad arguments");
+    VSRB_CHECK_ARG(!flow_prev || (Hl % 2 == 0 && Wl % 2 == 0), "level_input: level extent must be even");
+    const long long total = (long long)P * Hl * Wl;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == VSRB_BF16) {
+        VSRB_CHECK_ARG(c_in == 16, "level_input: bf16 path expects 16 allocated channels");
+        level_input_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, s>>>(
+            reinterpret_cast<const float4*>(lvl), ref_idx, supp_idx, reinterpret_cast<const float2*>(flow_prev),
+            reinterpret_cast<float2*>(flow_up), reinterpret_cast<__nv_bfloat16*>(conv_in), P, Hl, Wl, c_in);
+    } else {
+        VSRB_CHECK_ARG(c_in % 4 == 0, "level_input: fp32 channel stride must be %% 4");
+        level_input_kernel<float><<<grid_for(total, 256), 256, 0, s>>>(
+            reinterpret_cast<const float4*>(lvl), ref_idx, supp_idx, reinterpret_cast<const float2*>(flow_prev),
+            reinterpret_cast<float2*>(flow_up), reinterpret_cast<float*>(conv_in), P, Hl, Wl, c_in);
+    }
+    VSRB_LAUNCH_CHECK();
+    return VSRB_OK;
+}
+
+int vsrb_flow_resize(const float* flow_in, float* flow_out, int32_t P, int32_t Hp, int32_t Wp, int32_t h, int32_t w, void* stream) {
+    VSRB_CHECK_ARG(flow_in && flow_out && P >= 1, "flow_resize: bad arguments");
+    const long long total = (long long)P * h * w;
+    flow_resize_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float2*>(flow_in), reinterpret_cast<float2*>(flow_out), P, Hp, Wp, h, w);
+    VSRB_LAUNCH_CHECK();
+    return VSRB_OK;
+}
+
+}  // extern "C"

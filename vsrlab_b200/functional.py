@@ -1,0 +1,458 @@
+"""Host side of the hot path: schedules the sm_100a kernels for the reference's
+nn.Module forwards (Real-BasicVSR / BasicVSR / SPyNet / ResidualBlock / ...).
+
+Everything here is orchestration: NHWC workspaces, packed-weight cache, which
+kernel runs on what.  All arithmetic happens in libvsrb200.so.  Precision mode:
+
+* ``fp32``  - fp32 activations, FFMA convolution; matches the reference's fp32
+  path to <= 1e-4 max-abs.  Default outside autocast (reference test.py runs fp32).
+* ``bf16``  - bf16 NHWC activations, tcgen05/TMEM implicit-GEMM convolution with fp32
+  accumulate; flows, the cleaner's running frame and the output stay fp32.
+  Default under ``torch.autocast`` (reference train.py:93), or force it with
+  ``vsrlab_b200.set_precision("bf16")`` / ``VSRLAB_B200_PRECISION=bf16``.
+"""
+from __future__ import annotations
+
+import contextlib
+import os
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+from ._lib import (ACT_LRELU, ACT_NONE, ACT_RELU, BF16, EPI_CLEAN, EPI_FLOW, EPI_NHWC, EPI_SR, F32, PAD_BORDER, PAD_ZEROS,
+                   VsrbError)
+
+_forced: Optional[int] = None
+_NAMES = {"bf16": BF16, "fp32": F32, "f32": F32}
+
+# tunables (frames / images per launch batch; sized so a layer's in+out stays L2-resident)
+CLEAN_CHUNK = int(os.environ.get("VSRB_CLEAN_CHUNK", "6"))
+TAIL_CHUNK = int(os.environ.get("VSRB_TAIL_CHUNK", "2"))
+
+
+def set_precision(mode: Optional[str]) -> None:
+    """Force 'bf16' / 'fp32', or None to follow autocast."""
+    global _forced
+    _forced = None if mode is None else _NAMES[mode]
+
+
+@contextlib.contextmanager
+def precision(mode: str):
+    global _forced
+    old = _forced
+    _forced = _NAMES[mode]
+    try:
+        yield
+    finally:
+        _forced = old
+
+
+def current_dtype() -> int:
+    if _forced is not None:
+        return _forced
+    env = os.environ.get("VSRLAB_B200_PRECISION")
+    if env:
+        return _NAMES[env]
+    return BF16 if torch.is_autocast_enabled() else F32
+
+
+# --------------------------------------------------------------------------------------
+# caches
+# --------------------------------------------------------------------------------------
+_packed: Dict[tuple, ops.PackedConv] = {}
+_ws: Dict[tuple, torch.Tensor] = {}
+_consts: Dict[tuple, object] = {}
+
+
+def packed(convs: Sequence[torch.nn.Conv2d], segs: Sequence[Tuple[int, int]], dt: int, pixshuf: int = 0) -> ops.PackedConv:
+    key = (tuple(id(c) for c in convs), tuple(segs), dt, pixshuf)
+    pc = _packed.get(key)
+    if pc is None or pc.stamp != ops.PackedConv.stamp_of(convs):
+        pc = ops.PackedConv(convs, segs, dt, pixshuf)
+        _packed[key] = pc
+    return pc
+
+
+def ws(name: str, shape: Sequence[int], dtype: torch.dtype, device) -> torch.Tensor:
+    """Named scratch tensor, grown on demand and reused across calls (never shrinks)."""
+    n = 1
+    for s in shape:
+        n *= int(s)
+    key = (name, dtype, str(device))
+    t = _ws.get(key)
+    if t is None or t.numel() < n:
+        t = torch.empty(max(n, 1), dtype=dtype, device=device)
+        _ws[key] = t
+    return t[:n].view(*shape)
+
+
+def clear_caches() -> None:
+    _packed.clear()
+    _ws.clear()
+    _consts.clear()
+
+
+def _check_input(x: torch.Tensor, what: str) -> torch.Tensor:
+    ops.require_cuda(x, what)
+    if x.dtype != torch.float32:
+        x = x.float()
+    return x
+
+
+def _no_training(mod: torch.nn.Module) -> None:
+    if torch.is_grad_enabled() and mod.training and any(p.requires_grad for p in mod.parameters()):
+        raise NotImplementedError(
+            "vsrlab_b200: the backward (dgrad/wgrad/warp-grad) kernels are not built yet; call the model under "
+            "torch.no_grad() or in eval() mode.")
+
+
+def _act_c(c: int, dt: int) -> int:
+    """channels allocated per pixel for a c-channel activation"""
+    return (c + 15) // 16 * 16 if dt == BF16 else (c + 3) // 4 * 4
+
+
+def _to_nhwc(x: torch.Tensor, dt: int, name: str, c_alloc: Optional[int] = None) -> Tuple[torch.Tensor, int]:
+    n, c, h, w = x.shape
+    ca = c_alloc or _act_c(c, dt)
+    t = ws(name, (n, h, w, ca), ops.TORCH_DT[dt], x.device)
+    ops.nchw_to_nhwc(x.contiguous(), t, n, c, h, w, ca, dt)
+    return t, ca
+
+
+def _to_nchw(t: torch.Tensor, n: int, c: int, h: int, w: int, c_src: int, dt: int) -> torch.Tensor:
+    out = torch.empty(n, c, h, w, dtype=torch.float32, device=t.device)
+    ops.nhwc_to_nchw(t, out, n, c, h, w, c_src, dt)
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# module-level entry points (NCHW fp32 in / out, like the reference modules)
+# --------------------------------------------------------------------------------------
+_ACTS = {"none": ACT_NONE, "relu": ACT_RELU, "lrelu": ACT_LRELU}
+
+
+def conv2d(x: torch.Tensor, conv: torch.nn.Conv2d, act: str = "none", slope: float = 0.1, pixel_shuffle: int = 0) -> torch.Tensor:
+    """act(conv(x)) [+ PixelShuffle]: ConvReLU (conv.py:21), PixelShufflePack (upsampling.py:10-12)."""
+    x = _check_input(x, "input")
+    dt = current_dtype()
+    n, c, h, w = x.shape
+    xin, ca = _to_nhwc(x, dt, "m_in")
+    pc = packed([conv], [(0, c)], dt, pixel_shuffle)
+    r = pixel_shuffle or 1
+    co = conv.out_channels // (r * r)
+    oc = _act_c(co, dt) if r > 1 else pc.cout_pad
+    out = ws("m_out", (n, h * r, w * r, oc), ops.TORCH_DT[dt], x.device)
+    ops.conv2d_fwd(pc, [xin], [ca], n, h, w, act=_ACTS[act], slope=slope, out=out, out_c=oc)
+    return _to_nchw(out, n, co, h * r, w * r, oc, dt)
+
+
+def conv_chain(x: torch.Tensor, convs: Sequence[torch.nn.Conv2d], act: str = "relu") -> torch.Tensor:
+    """act(conv(...act(conv(x)))) - SpynetModule (spynet.py:13-21)."""
+    x = _check_input(x, "input")
+    dt = current_dtype()
+    n, c, h, w = x.shape
+    cur, ca = _to_nhwc(x, dt, "m_in")
+    for j, conv in enumerate(convs):
+        pc = packed([conv], [(0, conv.in_channels)], dt)
+        oc = pc.cout_pad
+        out = ws(f"m_chain{j % 2}", (n, h, w, oc), ops.TORCH_DT[dt], x.device)
+        ops.conv2d_fwd(pc, [cur], [ca], n, h, w, act=_ACTS[act], out=out, out_c=oc)
+        cur, ca = out, oc
+    return _to_nchw(cur, n, convs[-1].out_channels, h, w, ca, dt)
+
+
+def _run_resblocks(cur, ca, stem_pc, block_pcs, n, h, w, mid_c, dt, device, tag, final_out=None, final_strides=(0, 0),
+                   extra_in=None, extra_c=0, groups=1):
+    """stem (+LeakyReLU) then residual blocks on NHWC buffers; returns (tensor, channels).
+    If `final_out` is given the last conv of the chain writes there (raw address allowed)."""
+    tdt = ops.TORCH_DT[dt]
+    bufs = [ws(f"{tag}_r{i}", (n, h, w, mid_c), tdt, device) for i in range(3)]
+    nconv = (1 if stem_pc is not None else 0) + 2 * len(block_pcs)
+    done = 0
+
+    def target(i):
+        nonlocal done
+        done += 1
+        if done == nconv and final_out is not None:
+            return final_out, final_strides
+        return bufs[i], (0, 0)
+
+    free = [0, 1, 2]
+    if stem_pc is not None:
+        o, st = target(free[0])
+        ins, cs = ([cur, extra_in], [ca, extra_c]) if extra_in is not None else ([cur], [ca])
+        ops.conv2d_fwd(stem_pc, ins, cs, n, h, w, act=ACT_LRELU, slope=0.1, out=o, out_c=mid_c,
+                       out_img_stride=st[0], out_group_stride=st[1])
+        cur, ca, cur_i = o, mid_c, free[0]
+    else:
+        cur_i = -1
+    for (p1, p2) in block_pcs:
+        avail = [i for i in (0, 1, 2) if i != cur_i]
+        t1, _ = target(avail[0])
+        ops.conv2d_fwd(p1, [cur], [ca], n, h, w, act=ACT_RELU, out=t1, out_c=mid_c)
+        o, st = target(avail[1])
+        ops.conv2d_fwd(p2, [t1], [mid_c], n, h, w, act=ACT_NONE, out=o, out_c=mid_c, residual=cur, res_c=ca,
+                       out_img_stride=st[0], out_group_stride=st[1])
+        cur, ca, cur_i = o, mid_c, avail[1]
+    return cur, ca
+
+
+def residual_stack(x: torch.Tensor, stem: Optional[torch.nn.Conv2d], blocks: Sequence[torch.nn.Module]) -> torch.Tensor:
+    """ResidualBlock / ResidualConv forward (conv.py:89-92, 101-103)."""
+    x = _check_input(x, "input")
+    dt = current_dtype()
+    n, c, h, w = x.shape
+    mid = stem.out_channels if stem is not None else blocks[0].conv1.out_channels
+    mid_c = _act_c(mid, dt)
+    cur, ca = _to_nhwc(x, dt, "m_in", None if stem is not None else mid_c)
+    stem_pc = packed([stem], [(0, c)], dt) if stem is not None else None
+    bpcs = [(packed([b.conv1], [(0, mid)], dt), packed([b.conv2], [(0, mid)], dt)) for b in blocks]
+    cur, ca = _run_resblocks(cur, ca, stem_pc, bpcs, n, h, w, mid_c, dt, x.device, "m")
+    return _to_nchw(cur, n, mid, h, w, ca, dt)
+
+
+def flow_warp(x: torch.Tensor, flow: torch.Tensor, padding_mode: str = "zeros") -> torch.Tensor:
+    """flow_warp(x [T,c,h,w], flow [T,h,w,2]) (spynet.py:95-106)."""
+    x = _check_input(x, "input")
+    flow = _check_input(flow, "flow").contiguous()
+    dt = current_dtype()
+    n, c, h, w = x.shape
+    vec = 8 if dt == BF16 else 4
+    ca = (c + vec - 1) // vec * vec
+    xin, _ = _to_nhwc(x, dt, "m_in", ca)
+    out = ws("m_out", (n, h, w, ca), ops.TORCH_DT[dt], x.device)
+    ops.flow_warp(xin, flow, out, n, h, w, ca, dt, PAD_BORDER if padding_mode == "border" else PAD_ZEROS)
+    return _to_nchw(out, n, c, h, w, ca, dt)
+
+
+# --------------------------------------------------------------------------------------
+# SPyNet
+# --------------------------------------------------------------------------------------
+def _spynet_consts(sp) -> Tuple[List[float], List[float]]:
+    key = ("spynet_norm", id(sp), sp.mean.data_ptr(), sp.mean._version, sp.std._version)
+    v = _consts.get(key)
+    if v is None:
+        v = (sp.mean.detach().flatten().cpu().tolist(), sp.std.detach().flatten().cpu().tolist())
+        _consts[key] = v
+    return v
+
+
+def _spynet_run(sp, frames: torch.Tensor, ref_idx: torch.Tensor, supp_idx: torch.Tensor, dt: int, resize: bool = True) -> torch.Tensor:
+    """frames [F,3,h,w] fp32 contiguous; pair p = (frames[ref_idx[p]], frames[supp_idx[p]]).
+    Returns flows [P,h,w,2] fp32 (channels-last, the layout flow_warp consumes)."""
+    F_, _, h, w = frames.shape
+    dev = frames.device
+    if resize:
+        Hp, Wp = (h + 31) // 32 * 32, (w + 31) // 32 * 32
+    else:
+        if h % 32 or w % 32:
+            raise VsrbError("Spynet.compute_flow needs sides that are multiples of 32 (reference spynet.py:49)")
+        Hp, Wp = h, w
+    mean, std = _spynet_consts(sp)
+    tdt = ops.TORCH_DT[dt]
+    lv = [ws(f"sp_pyr{k}", (F_, Hp >> k, Wp >> k, 4), torch.float32, dev) for k in range(6)]
+    ops.spynet_pyramid_base(frames, lv[0], F_, h, w, Hp, Wp, mean, std)
+    for k in range(1, 6):
+        ops.avgpool2_c4(lv[k - 1], lv[k], F_, Hp >> (k - 1), Wp >> (k - 1))
+    P = ref_idx.numel()
+    cin0 = 16 if dt == BF16 else 8
+    chans = [cin0, _act_c(32, dt), _act_c(64, dt), _act_c(32, dt), _act_c(16, dt)]
+    full = [ws(f"sp_act{j}", (P, Hp, Wp, chans[j]), tdt, dev) for j in range(5)]
+    fup_full = ws("sp_fup", (P, Hp, Wp, 2), torch.float32, dev)
+    fl_full = [ws(f"sp_flow{j}", (P, Hp, Wp, 2), torch.float32, dev) for j in range(2)]
+    flow_prev = None
+    for level in range(6):
+        k = 5 - level
+        Hl, Wl = Hp >> k, Wp >> k
+        npx = P * Hl * Wl
+        act = [full[j].view(-1)[: npx * chans[j]].view(P, Hl, Wl, chans[j]) for j in range(5)]
+        fup = fup_full.view(-1)[: npx * 2].view(P, Hl, Wl, 2)
+        fl = fl_full[level % 2].view(-1)[: npx * 2].view(P, Hl, Wl, 2)
+        ops.spynet_level_input(lv[k], ref_idx, supp_idx, flow_prev, fup, act[0], P, Hl, Wl, cin0, dt)
+        mods = sp.basic_module[level].basic_module
+        for j in range(5):
+            conv = mods[j].conv[0]
+            pc = packed([conv], [(0, conv.in_channels)], dt)
+            if j < 4:
+                ops.conv2d_fwd(pc, [act[j]], [chans[j]], P, Hl, Wl, act=ACT_RELU, out=act[j + 1], out_c=chans[j + 1])
+            else:   # flow = flow_up + relu(conv) fused in the epilogue (spynet.py:65)
+                ops.conv2d_fwd(pc, [act[j]], [chans[j]], P, Hl, Wl, act=ACT_RELU, epilogue=EPI_FLOW, f32_in=fup, f32_io=fl)
+        flow_prev = fl
+    if (Hp, Wp) == (h, w):
+        return flow_prev.clone()
+    out = torch.empty(P, h, w, 2, dtype=torch.float32, device=dev)
+    ops.flow_resize(flow_prev, out, P, Hp, Wp, h, w)
+    return out
+
+
+def spynet_flow(sp, ref: torch.Tensor, supp: torch.Tensor, resize: bool = True) -> torch.Tensor:
+    """Spynet.forward / compute_flow: [T,3,h,w] x2 -> [T,2,h,w] (spynet.py:38-93)."""
+    ref = _check_input(ref, "ref")
+    supp = _check_input(supp, "supp")
+    t = ref.shape[0]
+    frames = torch.cat([ref, supp], 0).contiguous()
+    idx = torch.arange(2 * t, dtype=torch.int32, device=ref.device)
+    flows = _spynet_run(sp, frames, idx[:t].contiguous(), idx[t:].contiguous(), current_dtype(), resize)
+    return flows.permute(0, 3, 1, 2).contiguous()
+
+
+def _pair_indices(n: int, t: int, device) -> Tuple[torch.Tensor, torch.Tensor]:
+    """First n*(t-1) pairs: backward flows (ref=frame i, supp=i+1); then forward (ref=i+1, supp=i).
+    Reference basicvsr.py:30-37."""
+    key = ("pairs", n, t, str(device))
+    v = _consts.get(key)
+    if v is None:
+        base = (torch.arange(n, dtype=torch.int32).view(n, 1) * t + torch.arange(t - 1, dtype=torch.int32).view(1, t - 1)).reshape(-1)
+        ref = torch.cat([base, base + 1]).to(device)
+        supp = torch.cat([base + 1, base]).to(device)
+        v = (ref.contiguous(), supp.contiguous())
+        _consts[key] = v
+    return v
+
+
+def basicvsr_flows(bv, lrs: torch.Tensor):
+    """BasicVSR.compute_flow: (flow_forward, flow_backward), each [n*(t-1),2,h,w] (basicvsr.py:30-37)."""
+    lrs = _check_input(lrs, "lrs")
+    n, t, c, h, w = lrs.shape
+    ref, supp = _pair_indices(n, t, lrs.device)
+    flows = _spynet_run(bv.spynet, lrs.contiguous().view(n * t, c, h, w), ref, supp, current_dtype())
+    m = n * (t - 1)
+    fb = flows[:m].permute(0, 3, 1, 2).contiguous()
+    ff = flows[m:].permute(0, 3, 1, 2).contiguous()
+    return ff, fb
+
+
+# --------------------------------------------------------------------------------------
+# cleaner / BasicVSR / Real-BasicVSR
+# --------------------------------------------------------------------------------------
+def _cleaner_run(cl, x: torch.Tensor, dt: int) -> torch.Tensor:
+    """x [B,3,h,w] fp32 contiguous, refined in place (realbasicvsr.py:24-30).
+    Returns the NHWC copy of the refined frames (input of the propagation stems)."""
+    B, c, h, w = x.shape
+    dev = x.device
+    tdt = ops.TORCH_DT[dt]
+    mid = cl.resblock.conv[0].out_channels
+    mid_c = _act_c(mid, dt)
+    clr = _act_c(3, dt)
+    x_nhwc = ws("x_nhwc", (B, h, w, clr), tdt, dev)
+    ops.nchw_to_nhwc(x, x_nhwc, B, c, h, w, clr, dt)
+    stem = packed([cl.resblock.conv[0]], [(0, 3)], dt)
+    blocks = [(packed([b.conv1], [(0, mid)], dt), packed([b.conv2], [(0, mid)], dt)) for b in cl.resblock.res_block]
+    last = packed([cl.conv], [(0, mid)], dt)
+    chunk = max(1, min(B, CLEAN_CHUNK))
+    for _ in range(cl.steps):
+        for b0 in range(0, B, chunk):
+            nb = min(chunk, B - b0)
+            cur, ca = _run_resblocks(x_nhwc[b0:b0 + nb], clr, stem, blocks, nb, h, w, mid_c, dt, dev, "cl")
+            ops.conv2d_fwd(last, [cur], [ca], nb, h, w, act=ACT_NONE, epilogue=EPI_CLEAN, out=x_nhwc[b0:b0 + nb], out_c=clr,
+                           f32_io=x[b0:b0 + nb])
+    return x_nhwc
+
+
+def cleaner_forward(cl, x: torch.Tensor) -> torch.Tensor:
+    x = _check_input(x, "input")
+    if not x.is_contiguous():
+        raise RuntimeError("IterativeRefinement works in place on a view of its input; pass a contiguous tensor")
+    n, t, c, h, w = x.shape
+    _cleaner_run(cl, x.view(n * t, c, h, w), current_dtype())
+    return x
+
+
+def _basicvsr_run(bv, lrs: torch.Tensor, dt: int, x_nhwc: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """lrs [n,t,3,h,w] fp32 contiguous -> sr [n,t,3,s*h,s*w] fp32 (basicvsr.py:39-83)."""
+    n, t, c, h, w = lrs.shape
+    dev = lrs.device
+    tdt = ops.TORCH_DT[dt]
+    es = ops.ESIZE[dt]
+    mid = bv.mid_channels
+    mid_c = _act_c(mid, dt)
+    clr = _act_c(3, dt)
+    x_flat = lrs.view(n * t, c, h, w)
+    if x_nhwc is None:
+        x_nhwc = ws("x_nhwc", (n * t, h, w, clr), tdt, dev)
+        ops.nchw_to_nhwc(x_flat, x_nhwc, n * t, c, h, w, clr, dt)
+
+    # ---- optical flow, both directions in one batch (basicvsr.py:30-37) -----------------
+    flows = None
+    if t > 1:
+        ref, supp = _pair_indices(n, t, dev)
+        flows = _spynet_run(bv.spynet, x_flat, ref, supp, dt)          # [2*n*(t-1), h, w, 2]
+        m = n * (t - 1)
+        flows_b, flows_f = flows[:m], flows[m:]
+
+    # ---- bidirectional propagation: both directions run as two weight groups ------------
+    x5 = x_nhwc.view(n, t, h, w, clr)
+    pairs = ws("lr_pairs", (t, 2 * n, h, w, clr), tdt, dev)
+    pairs.copy_(torch.cat([x5.flip(1), x5], 0).transpose(0, 1))      # step s: [frame t-1-s | frame s]
+    bank = ws("feat_bank", (2, n, t, h, w, mid_c), tdt, dev)           # [0]=backward, [1]=forward features
+    fbk, ffw = bank[0], bank[1]
+    frame_el = h * w * mid_c
+    bwd, fwd = bv.backward_resblocks, bv.forward_resblocks
+    stem = packed([bwd.conv[0], fwd.conv[0]], [(3, mid), (0, 3)], dt)   # cat([lr_i, feat]) order kept via seg_off
+    blocks = [(packed([a.conv1, b.conv1], [(0, mid)], dt), packed([a.conv2, b.conv2], [(0, mid)], dt))
+              for a, b in zip(bwd.res_block, fwd.res_block)]
+    warped = ws("feat_warp", (2 * n, h, w, mid_c), tdt, dev)
+    for s in range(t):
+        if s == 0:
+            warped.zero_()
+        else:
+            ops.flow_warp(fbk.data_ptr() + (t - s) * frame_el * es, flows_b.data_ptr() + (t - 1 - s) * h * w * 8, warped[:n],
+                          n, h, w, mid_c, dt, PAD_ZEROS, x_img_stride=t * frame_el, flow_img_stride=(t - 1) * h * w)
+            ops.flow_warp(ffw.data_ptr() + (s - 1) * frame_el * es, flows_f.data_ptr() + (s - 1) * h * w * 8, warped[n:],
+                          n, h, w, mid_c, dt, PAD_ZEROS, x_img_stride=t * frame_el, flow_img_stride=(t - 1) * h * w)
+        o_b = fbk.data_ptr() + (t - 1 - s) * frame_el * es
+        o_f = ffw.data_ptr() + s * frame_el * es
+        _run_resblocks(warped, mid_c, stem, blocks, 2 * n, h, w, mid_c, dt, dev, "pp", final_out=o_b,
+                       final_strides=(t * frame_el, (o_f - o_b) // es), extra_in=pairs[s], extra_c=clr, groups=2)
+
+    # ---- fusion + upsampling + reconstruction, batched over frames (basicvsr.py:75-83) --
+    n_up = len(bv.upsample)
+    scale = 2 ** n_up
+    H, W = h * scale, w * scale
+    sr = torch.empty(n, t, 3, H, W, dtype=torch.float32, device=dev)
+    sr_flat = sr.view(n * t, 3, H, W)
+    point = packed([bv.point_conv[0]], [(0, mid), (mid, mid)], dt)
+    ups = [packed([u.upconv], [(0, mid)], dt, 2) for u in bv.upsample]
+    cl0 = packed([bv.conv_last[0]], [(0, mid)], dt)
+    cl2 = packed([bv.conv_last[2]], [(0, bv.conv_last[2].in_channels)], dt)
+    c_last = _act_c(bv.conv_last[0].out_channels, dt)
+    fb_flat, ff_flat = fbk.view(n * t, h, w, mid_c), ffw.view(n * t, h, w, mid_c)
+    B = n * t
+    chunk = max(1, min(B, TAIL_CHUNK))
+    for b0 in range(0, B, chunk):
+        nb = min(chunk, B - b0)
+        cur = ws("tl_p", (nb, h, w, mid_c), tdt, dev)
+        ops.conv2d_fwd(point, [fb_flat[b0:b0 + nb], ff_flat[b0:b0 + nb]], [mid_c, mid_c], nb, h, w, act=ACT_LRELU, slope=0.1,
+                       out=cur, out_c=mid_c)
+        hh, ww = h, w
+        for i, up in enumerate(ups):
+            nxt = ws(f"tl_u{i}", (nb, 2 * hh, 2 * ww, mid_c), tdt, dev)
+            ops.conv2d_fwd(up, [cur], [mid_c], nb, hh, ww, act=ACT_NONE, out=nxt, out_c=mid_c)
+            cur, hh, ww = nxt, 2 * hh, 2 * ww
+        hr = ws("tl_h", (nb, H, W, c_last), tdt, dev)
+        ops.conv2d_fwd(cl0, [cur], [mid_c], nb, H, W, act=ACT_LRELU, slope=0.1, out=hr, out_c=c_last)
+        ops.conv2d_fwd(cl2, [hr], [c_last], nb, H, W, act=ACT_NONE, epilogue=EPI_SR, f32_io=sr_flat[b0:b0 + nb],
+                       f32_in=x_flat[b0:b0 + nb], aux_hw=(h, w))
+    return sr
+
+
+def basicvsr_forward(bv, lrs: torch.Tensor) -> torch.Tensor:
+    _no_training(bv)
+    lrs = _check_input(lrs, "lrs").contiguous()
+    return _basicvsr_run(bv, lrs, current_dtype())
+
+
+def realbasicvsr_forward(model, lr: torch.Tensor):
+    """(sr, lq) = RealBasicVSR.forward; `lq` is `lr` itself, refined in place (realbasicvsr.py:11-15, 26-29)."""
+    _no_training(model)
+    ops.require_cuda(lr, "lr")
+    if lr.dtype != torch.float32:
+        raise VsrbError("RealBasicVSR refines its input in place and needs an fp32 tensor (reference realbasicvsr.py:29)")
+    if not lr.is_contiguous():
+        raise RuntimeError("RealBasicVSR works in place on a view of its input; pass a contiguous tensor")
+    dt = current_dtype()
+    n, t, c, h, w = lr.shape
+    x_nhwc = _cleaner_run(model.cleaner, lr.view(n * t, c, h, w), dt)
+    sr = _basicvsr_run(model.basicvsr, lr, dt, x_nhwc)
+    return sr, lr

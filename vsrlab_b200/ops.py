@@ -1,0 +1,140 @@
+"""Tensor-level wrappers around the C-ABI: they only turn torch tensors into raw
+device pointers + sizes and enqueue on torch's current CUDA stream.  torch is
+used for device memory and streams, nothing else."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, BF16, EPI_CLEAN, EPI_FLOW, EPI_NHWC, EPI_SR, F32, PAD_BORDER, PAD_ZEROS
+
+TORCH_DT = {BF16: torch.bfloat16, F32: torch.float32}
+ESIZE = {BF16: 2, F32: 4}
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t) -> Optional[C.c_void_p]:
+    if t is None:
+        return None
+    if isinstance(t, int):
+        return C.c_void_p(t)
+    return C.c_void_p(t.data_ptr())
+
+
+def require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise L.VsrbError(f"{what} lives on {t.device}: vsrlab_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+
+
+class PackedConv:
+    """Device image of one convolution's weights (or of `groups` same-shaped convolutions)
+    in the layout the kernels consume; see vsrb_pack_conv_weight in include/vsrb200.h."""
+
+    def __init__(self, convs: Sequence[torch.nn.Conv2d], segs: Sequence[Tuple[int, int]], dtype: int, pixshuf: int = 0):
+        lib = L.load()
+        w0 = convs[0].weight
+        require_cuda(w0, "conv weight")
+        cout, cin, kh, kw = w0.shape
+        g = L.ConvGeom()
+        g.kh, g.kw, g.n_seg = kh, kw, len(segs)
+        for i, (off, c) in enumerate(segs):
+            g.seg_off[i], g.seg_c[i] = off, c
+        g.cout, g.pixshuf, g.groups, g.dtype, g.transpose = cout, pixshuf, len(convs), dtype, 0
+        self.geom = g
+        self.cout, self.cin, self.kh, self.kw = cout, cin, kh, kw
+        self.cout_pad = (cout + 15) // 16 * 16
+        self.dtype = dtype
+        self.stamp = self.stamp_of(convs)
+        w = torch.stack([c.weight.detach().to(torch.float32) for c in convs]).contiguous()
+        b = None
+        if convs[0].bias is not None:
+            b = torch.stack([c.bias.detach().to(torch.float32) for c in convs]).contiguous()
+        nbytes = lib.vsrb_packed_weight_bytes(C.byref(g))
+        if nbytes == 0:
+            raise L.VsrbError(f"unsupported conv geometry: {lib.vsrb_last_error().decode()}")
+        self.buf = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+        L.check(lib.vsrb_pack_conv_weight(C.byref(g), _p(w), cin, _p(b), _p(self.buf), _stream()), "vsrb_pack_conv_weight")
+
+    @staticmethod
+    def stamp_of(convs) -> tuple:
+        return tuple((c.weight.data_ptr(), c.weight._version, 0 if c.bias is None else c.bias._version) for c in convs)
+
+
+def conv2d_fwd(pc: PackedConv, ins: Sequence, in_c: Sequence[int], batch: int, h: int, w: int, *,
+               imgs_per_group: Optional[int] = None, act: int = ACT_NONE, slope: float = 0.1, epilogue: int = EPI_NHWC,
+               out=None, out_c: int = 0, out_img_stride: int = 0, out_group_stride: int = 0, residual=None, res_c: int = 0,
+               f32_io=None, f32_in=None, aux_hw: Tuple[int, int] = (0, 0), max_ctas: int = 0) -> None:
+    """Enqueue one fused convolution.  `ins`, `out`, `residual`, `f32_io`, `f32_in` are tensors
+    (or raw int device addresses) that the caller keeps alive."""
+    a = L.ConvArgs()
+    a.geom = pc.geom
+    for i, t in enumerate(ins):
+        a.inp[i] = t if isinstance(t, int) else t.data_ptr()
+        a.in_c[i] = in_c[i]
+    a.batch, a.h, a.w = batch, h, w
+    a.imgs_per_group = imgs_per_group if imgs_per_group is not None else batch // pc.geom.groups
+    a.packed = pc.buf.data_ptr()
+    a.act, a.slope, a.epilogue = act, slope, epilogue
+    a.out = _p(out)
+    a.out_c = out_c
+    a.out_img_stride, a.out_group_stride = out_img_stride, out_group_stride
+    a.residual = _p(residual)
+    a.res_c = res_c
+    a.f32_io = _p(f32_io)
+    a.f32_in = _p(f32_in)
+    a.aux_h, a.aux_w = aux_hw
+    a.max_ctas = max_ctas
+    L.check(L.load().vsrb_conv2d_fwd(C.byref(a), _stream()), "vsrb_conv2d_fwd")
+
+
+def flow_warp(x, flow, out, n: int, h: int, w: int, c: int, dtype: int, padding: int = PAD_ZEROS,
+              x_img_stride: int = 0, flow_img_stride: int = 0) -> None:
+    L.check(L.load().vsrb_flow_warp(_p(x), x_img_stride, _p(flow), flow_img_stride, _p(out), n, h, w, c, dtype, padding,
+                                    _stream()), "vsrb_flow_warp")
+
+
+def nchw_to_nhwc(src: torch.Tensor, dst: torch.Tensor, n: int, c: int, h: int, w: int, c_dst: int, dtype: int) -> None:
+    L.check(L.load().vsrb_nchw_to_nhwc(_p(src), _p(dst), n, c, h, w, c_dst, dtype, _stream()), "vsrb_nchw_to_nhwc")
+
+
+def nhwc_to_nchw(src: torch.Tensor, dst: torch.Tensor, n: int, c: int, h: int, w: int, c_src: int, dtype: int) -> None:
+    L.check(L.load().vsrb_nhwc_to_nchw(_p(src), _p(dst), n, c, h, w, c_src, dtype, _stream()), "vsrb_nhwc_to_nchw")
+
+
+def spynet_pyramid_base(frames, lvl, F: int, h: int, w: int, Hp: int, Wp: int, mean, std) -> None:
+    m = (C.c_float * 3)(*mean)
+    s = (C.c_float * 3)(*std)
+    L.check(L.load().vsrb_spynet_pyramid_base(_p(frames), _p(lvl), F, h, w, Hp, Wp, m, s, _stream()), "vsrb_spynet_pyramid_base")
+
+
+def avgpool2_c4(src, dst, F: int, H: int, W: int) -> None:
+    L.check(L.load().vsrb_avgpool2_c4(_p(src), _p(dst), F, H, W, _stream()), "vsrb_avgpool2_c4")
+
+
+def spynet_level_input(lvl, ref_idx, supp_idx, flow_prev, flow_up, conv_in, P: int, Hl: int, Wl: int, c_in: int, dtype: int) -> None:
+    L.check(L.load().vsrb_spynet_level_input(_p(lvl), _p(ref_idx), _p(supp_idx), _p(flow_prev), _p(flow_up), _p(conv_in),
+                                             P, Hl, Wl, c_in, dtype, _stream()), "vsrb_spynet_level_input")
+
+
+def flow_resize(fin, fout, P: int, Hp: int, Wp: int, h: int, w: int) -> None:
+    L.check(L.load().vsrb_flow_resize(_p(fin), _p(fout), P, Hp, Wp, h, w, _stream()), "vsrb_flow_resize")
+
+
+def launch_count() -> int:
+    return int(L.load().vsrb_launch_count())
+
+
+def debug_status() -> int:
+    return int(L.load().vsrb_debug_status(_stream()))
+
+
+def device_info() -> Tuple[int, int, int]:
+    a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
+    L.check(L.load().vsrb_device_info(C.byref(a), C.byref(b), C.byref(c)), "vsrb_device_info")
+    return a.value, b.value, c.value
