@@ -1,0 +1,264 @@
+"""Benchmark of the Real-BasicVSR x4 hot path (BASELINE.json: output frames/s, 720p out).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one `model(lr)` pass of the drop-in `vsrlab...RealBasicVSR` over `--clips`
+synthetic 30-frame 180x320 clips per GPU (cfg3 of BASELINE.json, experiment=basic 5/5 blocks
+unless --blocks is given), bf16 mode.  Prints ONE JSON line (rank 0).
+
+* value        frames/s, all ranks, inputs already resident in HBM (CUDA events, max over ranks)
+* e2e          same metric through the public nn.Module call with pinned HOST buffers: H2D of the
+               clip and D2H of sr/lq inside the timed region
+* roofline     the dominant kernel (tcgen05 implicit-GEMM conv): algorithmic conv FLOPs / CUDA-event
+               time of those launches, against MEASURED_PEAKS.json
+* cpu_baseline the CPU oracle (restatement of the reference's PyTorch path, oracle/) timed on this
+               box's host cores on a bounded sample
+* --impl reference: the reference's CPU path (oracle port; /root/reference cannot travel to the
+               GPU box) on all host cores, bounded sample per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "realbasicvsr_x4_output_frames_per_sec_720p"
+UNIT = "frames/s"
+T_FRAMES, LR_H, LR_W = 30, 180, 320
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sust": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "src": "measured"}
+    return {"hbm": 6650.0, "tf_burst": 1590.0, "tf_sust": 1400.0, "src": "fallback"}
+
+
+def build_model(blocks: int, device):
+    from vsrlab.vsr.models.RealBasicVSR.realbasicvsr import RealBasicVSR
+    torch.manual_seed(0)
+    m = RealBasicVSR(cleaning_blocks=blocks, mid_channels=64, upscale=4, res_blocks=blocks, pretrained_flow=False,
+                     train_flow=False)
+    return m.to(device).eval()
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi-equivalent (NVML) clocks and throttle reasons during the timed region."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.max_mhz = index, False, [], set(), None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+                     0x80: "hw_power_brake_slowdown"}
+            while not self.stop_flag:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+                time.sleep(0.05)
+        except Exception as e:  # noqa: BLE001
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def summary(self):
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def oracle_sample(blocks: int, frames: int, threads: int):
+    """CPU restatement of the reference path on `frames` frames of one 180x320 clip."""
+    from oracle import vsr_oracle as O
+    torch.set_num_threads(threads)
+    sd = {k: v.detach().cpu() for k, v in build_model(blocks, "cpu").state_dict().items()}
+    x = torch.rand(1, frames, 3, LR_H, LR_W, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        O.realbasicvsr(x, sd)
+        dt = time.perf_counter() - t0
+    return frames / dt, dt
+
+
+def run_reference(a):
+    """--impl reference: the reference's CPU implementation (oracle port) on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    frames = 3
+    for _ in range(a.warmup):
+        oracle_sample(a.blocks, 2, cores)
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        oracle_sample(a.blocks, frames, cores)
+    dt = time.perf_counter() - t0
+    v = a.steps * frames / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(a, 1),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{frames} frames of one 180x320 clip per step, full Real-BasicVSR forward (oracle/vsr_oracle.py)"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(a, clips):
+    return {"workload": f"cfg3: Real-BasicVSR x4 inference, {T_FRAMES}-frame {LR_H}x{LR_W}->{4*LR_H}x{4*LR_W} clips, "
+                        f"{a.blocks}/{a.blocks} blocks", "clips_per_gpu_per_step": clips, "frames_per_clip": T_FRAMES,
+            "precision": "bf16 activations, fp32 accumulate", "parallelism": f"clips sharded over {a.gpus} GPU(s), no collective",
+            "l2": "per-step working set (GBs of activations) exceeds the 126 MB L2; no explicit flush"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--blocks", type=int, default=5)
+    ap.add_argument("--clips", type=int, default=2, help="clips per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl != "reference" else a.warmup
+    if a.impl == "reference":
+        return run_reference(a)
+
+    import torch.distributed as dist
+    from vsrlab_b200 import functional as VF
+    from vsrlab_b200 import ops
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    VF.set_precision("bf16")
+    model = build_model(a.blocks, dev)
+    clips = a.clips
+    gen = torch.Generator().manual_seed(1000 + rank)
+    host_lr = torch.rand(clips, T_FRAMES, 3, LR_H, LR_W, generator=gen).pin_memory()
+    lr_dev = host_lr.to(dev)
+    work = torch.empty_like(lr_dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        work.copy_(lr_dev)                       # the model refines its input in place (reference contract)
+        with torch.no_grad():
+            return model(work)
+
+    for _ in range(a.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(a.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ops.launch_count() - l0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    # ---- end to end: pinned host -> device -> model -> pinned host --------------------------
+    host_sr = torch.empty(clips, T_FRAMES, 3, 4 * LR_H, 4 * LR_W).pin_memory()
+    host_lq = torch.empty_like(host_lr)
+
+    def e2e_step():
+        x = host_lr.to(dev, non_blocking=True)
+        with torch.no_grad():
+            sr, lq = model(x)
+        host_sr.copy_(sr, non_blocking=True)
+        host_lq.copy_(lq, non_blocking=True)
+
+    e2e_step()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(a.steps):
+        e2e_step()
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+
+    # ---- per-kernel roofline: CUDA events around every launch of one more step --------------
+    ops.PROFILE = []
+    step()
+    torch.cuda.synchronize()
+    prof, ops.PROFILE = ops.PROFILE, None
+    fam = {}
+    for kind, ev0, ev1, work_units in prof:
+        d = fam.setdefault(kind, [0.0, 0.0, 0])
+        d[0] += ev0.elapsed_time(ev1) * 1e-3
+        d[1] += work_units
+        d[2] += 1
+    step_s_prof = sum(d[0] for d in fam.values())
+
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+    frames_step = world * clips * T_FRAMES
+    value = frames_step * a.steps / (ms * 1e-3)
+    e2e = frames_step * a.steps / (ms_e2e * 1e-3)
+    if rank == 0:
+        pk = peaks()
+        conv = fam.get("conv_tc", [1e-9, 0.0, 0])
+        warp = fam.get("flow_warp", [1e-9, 0.0, 0])
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic", "config": workload_config(a, clips),
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": host_lr.numel() * 4,
+                    "d2h_bytes_per_step": (host_sr.numel() + host_lq.numel()) * 4},
+            "gpu_launches": launches,
+            "clocks": sampler.summary(),
+            "roofline": {"kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, all launches of a step)", "bound": "tensor",
+                         "achieved": conv[1] / conv[0] / 1e12, "peak": pk["tf_sust"], "unit": "TFLOP/s",
+                         "frac": conv[1] / conv[0] / 1e12 / pk["tf_sust"], "traffic": None, "peak_source": pk["src"] + " (sustained)",
+                         "launches_per_step": conv[2], "share_of_step": conv[0] / max(step_s_prof, 1e-9)},
+            "roofline_warp": {"kernel": "flow_warp_kernel", "bound": "hbm", "achieved": warp[1] / warp[0] / 1e9, "peak": pk["hbm"],
+                              "unit": "GB/s", "frac": warp[1] / warp[0] / 1e9 / pk["hbm"], "traffic": None,
+                              "launches_per_step": warp[2], "share_of_step": warp[0] / max(step_s_prof, 1e-9)},
+            "kernel_time_share": {k: round(v[0] / max(step_s_prof, 1e-9), 4) for k, v in fam.items()},
+        }
+        if world == 1 and not a.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            v, dtc = oracle_sample(a.blocks, 3, cores)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"3 frames of one 180x320 clip ({dtc:.1f} s), full forward, oracle/vsr_oracle.py"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -15,6 +15,29 @@ TORCH_DT = {BF16: torch.bfloat16, F32: torch.float32}
 ESIZE = {BF16: 2, F32: 4}
 
 
+# bench.py sets this to a list to time every launch with CUDA events on the launching stream:
+# entries are (kind, start_event, end_event, algorithmic work: FLOPs for convs, bytes otherwise)
+PROFILE = None
+
+
+class _Timed:
+    def __init__(self, kind: str, work: float):
+        self.kind, self.work = kind, work
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.e1.record()
+            PROFILE.append((self.kind, self.e0, self.e1, self.work))
+        return False
+
+
 def _stream() -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -90,13 +113,17 @@ def conv2d_fwd(pc: PackedConv, ins: Sequence, in_c: Sequence[int], batch: int, h
     a.f32_in = _p(f32_in)
     a.aux_h, a.aux_w = aux_hw
     a.max_ctas = max_ctas
-    L.check(L.load().vsrb_conv2d_fwd(C.byref(a), _stream()), "vsrb_conv2d_fwd")
+    g = pc.geom
+    flops = 2.0 * batch * h * w * pc.cout * (g.seg_c[0] + (g.seg_c[1] if g.n_seg == 2 else 0)) * pc.kh * pc.kw
+    with _Timed("conv_tc" if pc.dtype == BF16 else "conv_f32", flops):
+        L.check(L.load().vsrb_conv2d_fwd(C.byref(a), _stream()), "vsrb_conv2d_fwd")
 
 
 def flow_warp(x, flow, out, n: int, h: int, w: int, c: int, dtype: int, padding: int = PAD_ZEROS,
               x_img_stride: int = 0, flow_img_stride: int = 0) -> None:
-    L.check(L.load().vsrb_flow_warp(_p(x), x_img_stride, _p(flow), flow_img_stride, _p(out), n, h, w, c, dtype, padding,
-                                    _stream()), "vsrb_flow_warp")
+    with _Timed("flow_warp", float(n) * h * w * (2 * c * ESIZE[dtype] + 8)):
+        L.check(L.load().vsrb_flow_warp(_p(x), x_img_stride, _p(flow), flow_img_stride, _p(out), n, h, w, c, dtype, padding,
+                                        _stream()), "vsrb_flow_warp")
 
 
 def nchw_to_nhwc(src: torch.Tensor, dst: torch.Tensor, n: int, c: int, h: int, w: int, c_dst: int, dtype: int) -> None:
@@ -118,8 +145,9 @@ def avgpool2_c4(src, dst, F: int, H: int, W: int) -> None:
 
 
 def spynet_level_input(lvl, ref_idx, supp_idx, flow_prev, flow_up, conv_in, P: int, Hl: int, Wl: int, c_in: int, dtype: int) -> None:
-    L.check(L.load().vsrb_spynet_level_input(_p(lvl), _p(ref_idx), _p(supp_idx), _p(flow_prev), _p(flow_up), _p(conv_in),
-                                             P, Hl, Wl, c_in, dtype, _stream()), "vsrb_spynet_level_input")
+    with _Timed("spynet_glue", float(P) * Hl * Wl * (16 + 4 * 16 + 8 + 8 + c_in * ESIZE[dtype])):
+        L.check(L.load().vsrb_spynet_level_input(_p(lvl), _p(ref_idx), _p(supp_idx), _p(flow_prev), _p(flow_up), _p(conv_in),
+                                                 P, Hl, Wl, c_in, dtype, _stream()), "vsrb_spynet_level_input")
 
 
 def flow_resize(fin, fout, P: int, Hp: int, Wp: int, h: int, w: int) -> None:
