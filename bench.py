@@ -214,12 +214,18 @@ def main():
     step()
     torch.cuda.synchronize()
     prof, ops.PROFILE = ops.PROFILE, None
-    fam = {}
-    for kind, ev0, ev1, work_units in prof:
+    fam, parts = {}, {}
+    for kind, ev0, ev1, work_units, tag in prof:
+        sec = ev0.elapsed_time(ev1) * 1e-3
         d = fam.setdefault(kind, [0.0, 0.0, 0])
-        d[0] += ev0.elapsed_time(ev1) * 1e-3
+        d[0] += sec
         d[1] += work_units
         d[2] += 1
+        if kind == "conv_tc":
+            q = parts.setdefault(tag, [0.0, 0.0, 0])
+            q[0] += sec
+            q[1] += work_units
+            q[2] += 1
     step_s_prof = sum(d[0] for d in fam.values())
 
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
@@ -249,6 +255,8 @@ def main():
                               "unit": "GB/s", "frac": warp[1] / warp[0] / 1e9 / pk["hbm"], "traffic": None,
                               "launches_per_step": warp[2], "share_of_step": warp[0] / max(step_s_prof, 1e-9)},
             "kernel_time_share": {k: round(v[0] / max(step_s_prof, 1e-9), 4) for k, v in fam.items()},
+            "conv_by_part": {k: {"ms": round(v[0] * 1e3, 3), "tflops": round(v[1] / v[0] / 1e12, 1), "launches": v[2]}
+                             for k, v in parts.items()},
         }
         if world == 1 and not a.no_cpu_baseline:
             cores = os.cpu_count() or 1

@@ -1,0 +1,248 @@
+"""Parity of the CUDA path (through the C-ABI) against the CPU oracle and the golden fixtures.
+
+Tolerances (north_star): fp32 mode max-abs <= 1e-4 on sr; flows <= 1e-2 px; bf16 mode PSNR
+within 0.05 dB on [0,1] frames.  Kernel-level bf16 checks compare against the oracle run on
+bf16-rounded operands: the only differences left are fp32 summation order and the final bf16
+rounding of the stored activation (half an ulp: 2^-9 relative)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import build_state_dict
+from oracle import vsr_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    from vsrlab_b200 import load
+    load()
+    return torch.device("cuda:0")
+
+
+def bf16r(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+CONV_CASES = [
+    # segs (OIHW offset, channels), cout, k, h, w, n, act, groups, pixshuf, residual
+    ([(0, 64)], 64, 3, 16, 16, 1, "none", 1, 0, False),
+    ([(0, 64)], 64, 1, 16, 16, 1, "none", 1, 0, False),
+    ([(0, 64)], 64, 3, 37, 52, 3, "none", 1, 0, True),
+    ([(0, 3)], 64, 3, 24, 33, 2, "lrelu", 1, 0, False),
+    ([(3, 64), (0, 3)], 64, 3, 24, 40, 2, "lrelu", 2, 0, False),
+    ([(0, 64), (64, 64)], 64, 1, 24, 40, 2, "lrelu", 1, 0, False),
+    ([(0, 64)], 256, 3, 24, 40, 1, "none", 1, 2, False),
+    ([(0, 64)], 3, 3, 24, 40, 2, "none", 1, 0, False),
+    ([(0, 8)], 32, 7, 24, 40, 2, "relu", 1, 0, False),
+    ([(0, 32)], 64, 7, 24, 40, 2, "relu", 1, 0, False),
+    ([(0, 64)], 32, 7, 12, 20, 2, "relu", 1, 0, False),
+    ([(0, 32)], 16, 7, 6, 10, 2, "relu", 1, 0, False),
+    ([(0, 16)], 2, 7, 2, 2, 3, "relu", 1, 0, False),
+    ([(0, 64)], 64, 3, 180, 320, 2, "relu", 1, 0, True),
+]
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: f"k{c[2]}_{c[0]}_{c[1]}_{c[3]}x{c[4]}")
+def test_conv_kernels(dev, mode, case):
+    from vsrlab_b200 import functional as VF, ops
+    from vsrlab_b200._lib import ACT_LRELU, ACT_NONE, ACT_RELU, BF16, F32
+    segs, cout, k, h, w, n, act, groups, pixshuf, residual = case
+    dt = BF16 if mode == "bf16" else F32
+    g = torch.Generator().manual_seed(hash((k, cout, h, w)) % 1000)
+    cin = sum(c for _, c in segs)
+    convs = []
+    for _ in range(groups):
+        cv = torch.nn.Conv2d(cin, cout, k, 1, k // 2)
+        with torch.no_grad():
+            cv.weight.copy_(torch.randn(cv.weight.shape, generator=g) / (cin * k * k) ** 0.5)
+            cv.bias.copy_(torch.randn(cv.bias.shape, generator=g) * 0.1)
+        convs.append(cv)
+    B = n * groups
+    x = torch.randn(B, cin, h, w, generator=g)
+    res = torch.randn(B, cout, h, w, generator=g) if residual else None
+    ys = []
+    for gi in range(groups):
+        xs, wg = x[gi * n:(gi + 1) * n], convs[gi].weight.detach()
+        if dt == BF16:
+            xs, wg = bf16r(xs), bf16r(wg)
+        ys.append(F.conv2d(xs, wg, convs[gi].bias.detach(), padding=k // 2))
+    y = torch.cat(ys)
+    y = {"none": lambda v: v, "relu": O.relu, "lrelu": O.lrelu}[act](y)
+    if residual:
+        y = y + (bf16r(res) if dt == BF16 else res)
+    if pixshuf:
+        y = O.pixel_shuffle(y, 2)
+
+    tdt = ops.TORCH_DT[dt]
+    pc = ops.PackedConv([c.to(dev) for c in convs], segs, dt, pixshuf)
+    ins, in_c = [], []
+    for off, c in segs:
+        ca = VF._act_c(c, dt)
+        t = torch.zeros(B, h, w, ca, dtype=tdt, device=dev)
+        t[..., :c] = x[:, off:off + c].permute(0, 2, 3, 1).to(dev).to(tdt)
+        ins.append(t)
+        in_c.append(ca)
+    r = pixshuf or 1
+    co = cout // (r * r)
+    oc = VF._act_c(co, dt) if r > 1 else pc.cout_pad
+    out = torch.full((B, h * r, w * r, oc), 7.0, dtype=tdt, device=dev)
+    rt, rc = None, 0
+    if residual:
+        rc = VF._act_c(cout, dt)
+        rt = torch.zeros(B, h, w, rc, dtype=tdt, device=dev)
+        rt[..., :cout] = res.permute(0, 2, 3, 1).to(dev).to(tdt)
+    ops.conv2d_fwd(pc, ins, in_c, B, h, w, act={"none": ACT_NONE, "relu": ACT_RELU, "lrelu": ACT_LRELU}[act], slope=0.1,
+                   out=out, out_c=oc, residual=rt, res_c=rc)
+    torch.cuda.synchronize()
+    assert ops.debug_status() == 0
+    got = out[..., :co].float().permute(0, 3, 1, 2).cpu()
+    scale = max(y.abs().max().item(), 1.0)
+    tol = (2.0 ** -8 if dt == BF16 else 2e-5) * scale        # bf16: half-ulp of the stored value (2^-9) + slack
+    assert (got - y).abs().max().item() <= tol
+    if oc > co and not pixshuf:                              # padded channels must come out as act(0) = 0
+        assert out[..., co:].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("pad", ["zeros", "border"])
+def test_flow_warp_golden_and_adversarial(dev, golden, mode, pad):
+    from vsrlab.vsr.models.RealBasicVSR.modules.spynet import flow_warp
+    from vsrlab_b200 import functional as VF
+    g = golden("ops")
+    x, fl = T(g["warp_x"]), T(g["warp_flow"])
+    tol = 2e-5 if mode == "fp32" else 2.0 ** -7
+    with VF.precision(mode):
+        got = flow_warp(x.to(dev), fl.to(dev), padding_mode=pad).cpu()
+    assert (got - T(g[f"warp_{pad}"])).abs().max().item() <= tol
+    # adversarial: integer, half-pixel, far out-of-bounds flows on a 64-channel map
+    gen = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 64, 19, 27, generator=gen)
+    fl = (torch.rand(2, 19, 27, 2, generator=gen) - 0.5) * 40
+    fl[0, 0, :3] = torch.tensor([[0.0, 0.0], [1.0, 1.0], [0.5, 0.5]])
+    fl[1, 3, 3] = torch.tensor([500.0, -500.0])
+    fl[1, 18, 26] = torch.tensor([1e-4, 1e-4])
+    ref = O.flow_warp(bf16r(x) if mode == "bf16" else x, fl, pad)
+    with VF.precision(mode):
+        got = flow_warp(x.to(dev), fl.to(dev), padding_mode=pad).cpu()
+    assert (got - ref).abs().max().item() <= (2e-5 if mode == "fp32" else 2.0 ** -6)
+
+
+def test_flow_warp_empty_and_bad_args(dev):
+    from vsrlab_b200 import VsrbError, ops
+    from vsrlab_b200._lib import BF16
+    x = torch.zeros(1, 4, 4, 12, dtype=torch.bfloat16, device=dev)
+    with pytest.raises(VsrbError):                            # 12 channels is not a multiple of 8
+        ops.flow_warp(x, torch.zeros(1, 4, 4, 2, device=dev), torch.empty_like(x), 1, 4, 4, 12, BF16)
+
+
+@pytest.mark.parametrize("tag,kind", [("a", "spynet"), ("b", "spynet"), ("c", "spynet_amp")])
+def test_spynet_flows(dev, golden, tag, kind):
+    """Flow fields within 1e-2 px of the reference in fp32 mode (and in bf16 mode at the
+    reference's own flow magnitudes; the amplified case is reported, with a relative bound)."""
+    from vsrlab_b200 import functional as VF
+    g = golden("spynet")
+    sp = build_state_dict(kind).to(dev).eval()
+    ref, supp, want = T(g[f"{tag}_ref"]).to(dev), T(g[f"{tag}_supp"]).to(dev), T(g[f"{tag}_flow"])
+    with torch.no_grad(), VF.precision("fp32"):
+        fl = sp(ref, supp).cpu()
+    assert fl.shape == want.shape
+    assert (fl - want).abs().max().item() <= 1e-3
+    with torch.no_grad(), VF.precision("bf16"):
+        fl = sp(ref, supp).cpu()
+    err = (fl - want).abs().max().item()
+    assert err <= (1e-2 if kind == "spynet" else 0.03 * want.abs().max().item())
+
+
+@pytest.mark.parametrize("name", ["cfg1", "ragged"])
+def test_realbasicvsr_end_to_end(dev, golden, name):
+    from vsrlab_b200 import functional as VF, ops
+    g = golden(name)
+    net = build_state_dict(name).to(dev).eval()
+    sr_ref, lq_ref = T(g["sr"]), T(g["lq"])
+    lr = T(g["lr"]).to(dev)
+    with torch.no_grad(), VF.precision("fp32"):
+        sr, lq = net(lr)
+    torch.cuda.synchronize()
+    assert lq.data_ptr() == lr.data_ptr()                     # in-place / aliasing contract (realbasicvsr.py:26-29)
+    assert (sr.cpu() - sr_ref).abs().max().item() <= 1e-4     # north_star fp32 gate
+    assert (lq.cpu() - lq_ref).abs().max().item() <= 1e-4
+    lr = T(g["lr"]).to(dev)
+    with torch.no_grad(), VF.precision("bf16"):
+        sr16, _ = net(lr)
+    hr = torch.rand(sr_ref.shape, generator=torch.Generator().manual_seed(9))
+    assert abs(O.psnr(sr16.cpu(), hr) - O.psnr(sr_ref, hr)) <= 0.05    # north_star bf16 gate
+    assert O.psnr(sr16.cpu(), sr_ref) > 40.0
+    assert ops.debug_status() == 0
+
+
+def test_flows_and_basicvsr_alone(dev, golden):
+    from vsrlab_b200 import functional as VF
+    g = golden("ragged")
+    net = build_state_dict("ragged").to(dev).eval()
+    lr = T(g["lr"]).to(dev)
+    with torch.no_grad(), VF.precision("fp32"):
+        ff, fb = net.basicvsr.compute_flow(lr)
+        sr = net.basicvsr(lr)
+    assert (ff.cpu() - T(g["basicvsr_flow_forward"])).abs().max().item() <= 1e-2
+    assert (fb.cpu() - T(g["basicvsr_flow_backward"])).abs().max().item() <= 1e-2
+    assert (sr.cpu() - T(g["basicvsr_sr"])).abs().max().item() <= 1e-4
+
+
+def test_small_modules_match_golden(dev, golden):
+    from vsrlab.core.modules.conv import ResidualBlock
+    from vsrlab.core.modules.upsampling import PixelShufflePack
+    from vsrlab.vsr.models.RealBasicVSR.realbasicvsr import IterativeRefinement
+    from vsrlab_b200 import functional as VF
+    g = golden("ops")
+
+    def sub(prefix):
+        return {k[len(prefix):]: T(g[k]) for k in g.files if k.startswith(prefix)}
+    with torch.no_grad(), VF.precision("fp32"):
+        rb = ResidualBlock(3, 16, 2)
+        rb.load_state_dict(sub("rb_sd."))
+        assert (rb.to(dev)(T(g["rb_x"]).to(dev)).cpu() - T(g["rb_y"])).abs().max().item() <= 1e-5
+        ps = PixelShufflePack(16, 16, 2)
+        ps.load_state_dict(sub("ps_sd."))
+        assert (ps.to(dev)(T(g["ps_x"]).to(dev)).cpu() - T(g["ps_y"])).abs().max().item() <= 1e-5
+        ir = IterativeRefinement(16, 1)
+        ir.load_state_dict(sub("ir_sd."))
+        x = T(g["ir_x"]).to(dev)
+        y = ir.to(dev)(x)
+        assert y.data_ptr() == x.data_ptr()
+        assert (y.cpu() - T(g["ir_y"])).abs().max().item() <= 1e-5
+
+
+def test_full_size_properties(dev):
+    """BASELINE cfg3 size (one 180x320 frame pair): size-independent properties instead of an
+    oracle run - a zero flow warps to the identity, and the conv is linear in its input."""
+    from vsrlab_b200 import functional as VF, ops
+    from vsrlab_b200._lib import ACT_NONE, BF16
+    gen = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 180, 320, 64, generator=gen).to(dev).to(torch.bfloat16)
+    out = torch.empty_like(x)
+    ops.flow_warp(x, torch.zeros(2, 180, 320, 2, device=dev), out, 2, 180, 320, 64, BF16)
+    # zero flow is the identity up to the reference's normalise/de-normalise round trip (spynet.py:101-105),
+    # which moves the sample point by ~1e-6 * w pixels
+    assert (out.float() - x.float()).abs().max().item() <= 2e-3
+    from vsrlab_b200._lib import PAD_BORDER
+    const = torch.arange(64, device=dev).to(torch.bfloat16).expand(2, 180, 320, 64).contiguous()
+    fl = (torch.rand(2, 180, 320, 2, generator=gen).to(dev) - 0.5) * 100
+    ops.flow_warp(const, fl, out, 2, 180, 320, 64, BF16, PAD_BORDER)
+    assert (out.float() - const.float()).abs().max().item() <= 0.5       # bilinear weights sum to one (1 bf16 ulp at 63)
+    cv = torch.nn.Conv2d(64, 64, 3, 1, 1, bias=False).to(dev)
+    pc = ops.PackedConv([cv], [(0, 64)], BF16)
+    ya, yb = torch.empty_like(x), torch.empty_like(x)
+    ops.conv2d_fwd(pc, [x], [64], 2, 180, 320, act=ACT_NONE, out=ya, out_c=64)
+    ops.conv2d_fwd(pc, [x * 2], [64], 2, 180, 320, act=ACT_NONE, out=yb, out_c=64)
+    torch.cuda.synchronize()
+    assert torch.equal(ya.float() * 2, yb.float())            # exact: scaling by 2 commutes with every rounding
+    assert ops.debug_status() == 0

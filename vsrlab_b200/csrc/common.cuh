@@ -171,16 +171,17 @@ __device__ __forceinline__ void up_tap(int dst, float scale, int in_size, int& i
     l1 = src - (float)i0;
 }
 
-// One pixel (b,y,x), 16 consecutive packed output channels starting at n0 (multiple of 16),
-// v = raw accumulators.  `g` = weight group of image b.
-template <typename T>
-__device__ __forceinline__ void epi_store16(const EpiParams& e, int g, int b, int y, int x, int n0, float (&v)[16]) {
+// bias of 16 consecutive packed channels (global memory copy of the packed bias)
+__device__ __forceinline__ void epi_bias16(const EpiParams& e, int g, int n0, float (&v)[16]) {
     const float4* bp = reinterpret_cast<const float4*>(e.bias + (size_t)g * e.cout_pad + n0);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         float4 f = __ldg(bp + i);
         v[4 * i] += f.x; v[4 * i + 1] += f.y; v[4 * i + 2] += f.z; v[4 * i + 3] += f.w;
     }
+}
+
+__device__ __forceinline__ void epi_act16(const EpiParams& e, float (&v)[16]) {
     if (e.act == VSRB_ACT_RELU) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
@@ -188,6 +189,13 @@ __device__ __forceinline__ void epi_store16(const EpiParams& e, int g, int b, in
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = v[i] >= 0.f ? v[i] : v[i] * e.slope;
     }
+}
+
+// One pixel (b,y,x), 16 consecutive packed output channels starting at n0 (multiple of 16);
+// v = act(acc + bias) already applied by the caller.  `g` = weight group of image b.
+// kResDone: the caller has already added the residual.
+template <typename T, bool kResDone = false>
+__device__ __forceinline__ void epi_store16(const EpiParams& e, int g, int b, int y, int x, int n0, float (&v)[16]) {
     if (e.mode == VSRB_EPI_NHWC) {
         int Y = y, X = x, OH = e.H, OW = e.W, c0 = n0;
         if (e.pixshuf) {
@@ -198,7 +206,7 @@ __device__ __forceinline__ void epi_store16(const EpiParams& e, int g, int b, in
             OH = 2 * e.H;
             OW = 2 * e.W;
         }
-        if (e.res) {
+        if (!kResDone && e.res) {
             float r[16];
             size_t pix = ((size_t)b * OH + Y) * OW + X;
             Act<T>::load16(reinterpret_cast<const T*>(e.res) + pix * e.res_c + c0, r);

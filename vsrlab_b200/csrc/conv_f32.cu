@@ -109,6 +109,8 @@ __global__ void __launch_bounds__(128) conv_f32_kernel(F32Params P) {
                 float v[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = half ? acc1[c0 + i] : acc0[c0 + i];
+                epi_bias16(P.epi, g, n0 + c0, v);
+                epi_act16(P.epi, v);
                 epi_store16<float>(P.epi, g, img, y, x, n0 + c0, v);
             }
         }

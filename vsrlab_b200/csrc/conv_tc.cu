@@ -12,13 +12,21 @@
 // * W is pre-packed by vsrb_pack_conv_weight into the exact swizzled K-major shared-memory image
 //   of each stage and copied with cp.async.bulk; when one (group, n_block) worth of weights fits,
 //   it is loaded once per persistent CTA and stays resident.
+// * A residual input (`x + conv(...)`, act none) is folded into the accumulation as one more K=64
+//   stage: the residual tile is the A operand and a 64x64 identity matrix the B operand, so the
+//   tensor core adds it exactly (bf16 * 1.0 into the fp32 accumulator) and the epilogue never
+//   touches it.
 // * One CTA per SM, persistent over output tiles.  Warp 0 = TMA producer, warp 1 = MMA issuer
 //   (one elected lane issues tcgen05.mma, accumulators live in TMEM, double buffered), warp 2 =
-//   TMEM allocator, warps 4..7 = epilogue (tcgen05.ld -> bias/act/residual/pixel-shuffle/skip ->
-//   global).  smem full/empty and TMEM full/empty mbarrier rings connect the roles.
+//   TMEM allocator, warp 3 = bias loader, warps 4..7 = epilogue: tcgen05.ld -> bias/act -> bf16 ->
+//   swizzled shared-memory staging -> one TMA store per warp (full 128-byte lines, asynchronous,
+//   clipped at the image border by the tensor map; the PixelShuffle(2) store is just a strided
+//   tensor map per sub-pixel).  Special epilogues (3-channel fp32 outputs) store directly.
 //
 // Replaces: F.conv2d behind nn.Conv2d at reference conv.py:89-92,101-103; upsampling.py:10-12;
 // basicvsr.py:75-82; realbasicvsr.py:28-29; spynet.py:16-21 (see include/vsrb200.h).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace vsrb {
@@ -27,10 +35,14 @@ static constexpr int kMaxSlots = 8;
 static constexpr int kThreads = 256;
 static constexpr int kSmemMax = 232448;   // 227 KiB opt-in maximum per CTA on sm_100
 static constexpr int kCtrlBytes = 1024;
+static constexpr int kIdentBytes = 8192;  // 64 x 64 bf16 identity, swizzle-128B K-major image
 
 struct TcParams {
     CUtensorMap tmap[2];
-    const uint8_t* w;     // packed weights (after the bias header)
+    CUtensorMap rmap;      // residual (MMA-identity path)
+    CUtensorMap smap[4];   // output maps for the staged TMA store (one per pixel-shuffle sub-position)
+    const uint8_t* w;      // packed weights (after the bias header)
+    const uint8_t* ident;  // identity image in global memory
     EpiParams epi;
     int n_seg;
     int seg_chunks[2], seg_ck[2], seg_rowbytes[2], seg_layout[2], seg_bstage[2], seg_abytes[2], seg_stages[2];
@@ -40,12 +52,16 @@ struct TcParams {
     int tiles_x, tiles_per_img;
     int imgs_per_group, groups;
     int n_tile, n_blocks;
-    int stages_per_tile;
     int num_slots, slot_bytes;
     int resident;
     uint32_t wblock_bytes, wres_bytes;
     int acc_cols;
+    int res_mma;           // 1: residual added by the tensor core (identity stage)
+    uint32_t res_abytes;
+    int n_store;           // channels per store block (<= 64)
+    int stg_bytes;         // bytes of one staging buffer (two are allocated)
     int* dbg;
+    int debug;             // VSRB_TC_DEBUG bits (timing experiments only): 1 = no loads, 2 = no stores, 4 = no MMA
 };
 
 // ---------------------------------------------------------------------------------------
@@ -75,21 +91,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 // Bounded wait: a mis-programmed pipeline raises the debug flag and lets the kernel run to
 // completion with garbage instead of hanging the GPU.  `dead` is sticky per thread.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* dbg, int code, bool& dead) {
-    if (dead) return;
-    long long t0 = 0;
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, int* dbg, int code, bool& dead) {
+    long long t0 = clock64();
     for (uint32_t it = 0;; ++it) {
         if (mbar_try_wait(bar, parity)) return;
-        if ((it & 1023u) == 1023u) {
-            long long now = clock64();
-            if (t0 == 0) t0 = now;
-            if (now - t0 > 4000000000LL || *reinterpret_cast<volatile int*>(dbg) != 0) {
+        if ((it & 255u) == 255u) {
+            if (clock64() - t0 > 4000000000LL || *reinterpret_cast<volatile int*>(dbg) != 0) {
                 atomicCAS(dbg, 0, code);
                 dead = true;
                 return;
             }
         }
     }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* dbg, int code, bool& dead) {
+    if (dead) return;
+    if (mbar_try_wait(bar, parity)) return;
+    mbar_wait_slow(bar, parity, dbg, code, dead);
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -107,6 +125,19 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
@@ -126,39 +157,84 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
+// 32 lanes x 16 consecutive fp32 columns; the caller waits with tmem_ld_wait()
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 
 // K-major, swizzled shared-memory operand descriptor (sm_100 "version 1"):
 //  [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major, 1) | [32,46) SBO>>4 = 8 rows |
 //  [46,48) version=1 | [61,64) layout type (2 = 128B, 4 = 64B, 6 = 32B swizzle)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t rowbytes, uint32_t layout) {
-    uint32_t lo = ((saddr >> 4) & 0x3FFFu) | (1u << 16);
-    uint32_t hi = ((rowbytes * 8u) >> 4) | (1u << 14) | (layout << 29);
-    return ((uint64_t)hi << 32) | lo;
+// All MMAs of one pipeline stage: MT sub-tiles x KH filter rows x ksteps K=16 steps.  Descriptors
+// differ only in their 14-bit start-address field, so each MMA costs one add per operand.
+template <int KH>
+__device__ __forceinline__ void issue_stage(uint32_t d0, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                            int MT, int n_tile, uint32_t a_m, uint32_t a_ky, uint32_t b_ky, int ksteps,
+                                            bool first) {
+    for (int m = 0; m < MT; ++m) {
+#pragma unroll
+        for (int ky = 0; ky < KH; ++ky) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (k < ksteps) {
+                    const uint64_t ad = ((uint64_t)desc_hi << 32) | (a_lo + m * a_m + ky * a_ky + k * 2);
+                    const uint64_t bd = ((uint64_t)desc_hi << 32) | (b_lo + ky * b_ky + k * 2);
+                    umma_bf16(d0 + m * n_tile, ad, bd, idesc, (first && ky == 0 && k == 0) ? 0u : 1u);
+                }
+            }
+        }
+    }
+}
+
+// bias + activation + bf16 pack of 16 accumulator columns into one swizzled staging row
+__device__ __forceinline__ void stage_chunk(const EpiParams& e, const uint32_t (&r)[16], const float* bias16, uint32_t row_base,
+                                            uint32_t col_bytes, uint32_t msk) {
+    float v[16];
+    const float4* bp = reinterpret_cast<const float4*>(bias16);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float4 f = bp[i];
+        v[4 * i] = __uint_as_float(r[4 * i]) + f.x;
+        v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + f.y;
+        v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + f.z;
+        v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + f.w;
+    }
+    epi_act16(e, v);
+    uint32_t o0 = row_base + col_bytes, o1 = o0 + 16u;      // the XOR only touches address bits 4..6
+    o0 ^= ((o0 >> 7) & msk) << 4;
+    o1 ^= ((o1 >> 7) & msk) << 4;
+    st_shared_v4(o0, pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    st_shared_v4(o1, pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
 }
 
 // ---------------------------------------------------------------------------------------
+// kStaged = true : EPI_NHWC through swizzled staging + per-warp TMA stores (the hot path)
+// kStaged = false: every other epilogue, direct per-thread stores (3-channel fp32 outputs etc.)
+template <bool kStaged>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ TcParams P) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;                // swizzle atoms need 1 KiB alignment
     uint8_t* base_ptr = smem_raw + (base - raw);
-    // control block
+    // control block: barriers, TMEM base, bias of this (group, n_block)
     const uint32_t full0 = base, empty0 = base + 8 * kMaxSlots, tfull0 = base + 16 * kMaxSlots,
                    tempty0 = tfull0 + 16, wbar = tempty0 + 16;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + 16 * kMaxSlots + 48);
+    float* bias_s = reinterpret_cast<float*>(base_ptr + 256);   // up to 128 floats
     const uint32_t wres = base + kCtrlBytes;
-    const uint32_t slots0 = wres + P.wres_bytes;
+    const uint32_t wid = wres + P.wres_bytes;                    // identity image (residual path)
+    const uint32_t slots0 = wid + (P.res_mma ? kIdentBytes : 0);
+    const uint32_t stg0 = slots0 + P.num_slots * P.slot_bytes;   // two staging buffers for the TMA store
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = blockIdx.y / P.n_blocks, qb = blockIdx.y - g * P.n_blocks;
@@ -178,6 +254,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(smem_u32(tmem_slot), 512);
+    if (warp == 3)
+        for (int i = lane; i < P.n_tile; i += 32) bias_s[i] = __ldg(P.epi.bias + (size_t)g * P.epi.cout_pad + qb * P.n_tile + i);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -187,9 +265,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
     if (warp == 0) {
         // =============================== TMA producer ===============================
-        if (lane == 0) {
+        // the warp stays converged; one elected lane arms the barrier and issues the copies
+        if ((P.resident || P.res_mma) && elect_one()) {
+            mbar_expect_tx(wbar, (P.resident ? P.wblock_bytes : 0u) + (P.res_mma ? (uint32_t)kIdentBytes : 0u));
             if (P.resident) {
-                mbar_expect_tx(wbar, P.wblock_bytes);
                 uint32_t off = 0;
                 for (int s = 0; s < P.n_seg; ++s)
                     for (int i = 0; i < P.seg_stages[s]; ++i) {
@@ -197,94 +276,170 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                         off += P.seg_bstage[s];
                     }
             }
-            int slot = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < tiles_g; tile += gridDim.x) {
-                const int li = tile / P.tiles_per_img;
-                const int t = tile - li * P.tiles_per_img;
-                const int img = g * P.imgs_per_group + li;
-                const int ty = t / P.tiles_x, tx = t - ty * P.tiles_x;
-                const int y0 = ty * rows_tile - P.kh / 2, x0 = tx * P.TW - P.kw / 2;
-                uint32_t boff = 0;
-                for (int s = 0; s < P.n_seg; ++s) {
-                    for (int local = 0; local < P.seg_stages[s]; ++local) {
-                        const int chunk = local / P.kw, kx = local - chunk * P.kw;
-                        const uint32_t sa = slots0 + slot * P.slot_bytes;
-                        mbar_wait(empty0 + 8 * slot, phase ^ 1, P.dbg, 1, dead);
-                        mbar_expect_tx(full0 + 8 * slot, P.seg_abytes[s] + (P.resident ? 0 : P.seg_bstage[s]));
-                        tma_load_4d(&P.tmap[s], full0 + 8 * slot, sa, chunk * P.seg_ck[s], x0 + kx, y0, img);
-                        if (!P.resident) bulk_load(sa + P.seg_abytes[s], wsrc + boff, P.seg_bstage[s], full0 + 8 * slot);
-                        boff += P.seg_bstage[s];
-                        if (++slot == P.num_slots) { slot = 0; phase ^= 1; }
+            if (P.res_mma) bulk_load(wid, P.ident, kIdentBytes, wbar);
+        }
+        __syncwarp();
+        int slot = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < tiles_g; tile += gridDim.x) {
+            const int li = tile / P.tiles_per_img;
+            const int t = tile - li * P.tiles_per_img;
+            const int img = g * P.imgs_per_group + li;
+            const int ty = t / P.tiles_x, tx = t - ty * P.tiles_x;
+            const int y0 = ty * rows_tile - P.kh / 2, x0 = tx * P.TW - P.kw / 2;
+            uint32_t boff = 0;
+            for (int s = 0; s < P.n_seg; ++s) {
+                const uint32_t abytes = P.seg_abytes[s], bbytes = P.seg_bstage[s];
+                int chunk = 0, kx = 0;
+                for (int local = 0; local < P.seg_stages[s]; ++local) {
+                    const uint32_t sa = slots0 + slot * P.slot_bytes;
+                    mbar_wait(empty0 + 8 * slot, phase ^ 1, P.dbg, 1, dead);
+                    if (elect_one()) {
+                        if (P.debug & 1) {
+                            mbar_arrive(full0 + 8 * slot);
+                        } else {
+                            mbar_expect_tx(full0 + 8 * slot, abytes + (P.resident ? 0 : bbytes));
+                            tma_load_4d(&P.tmap[s], full0 + 8 * slot, sa, chunk * P.seg_ck[s], x0 + kx, y0, img);
+                            if (!P.resident) bulk_load(sa + abytes, wsrc + boff, bbytes, full0 + 8 * slot);
+                        }
+                    }
+                    __syncwarp();
+                    boff += bbytes;
+                    if (++kx == P.kw) { kx = 0; ++chunk; }
+                    if (++slot == P.num_slots) { slot = 0; phase ^= 1; }
+                }
+            }
+            if (P.res_mma) {                                   // residual tile: A operand of the identity stage
+                const uint32_t sa = slots0 + slot * P.slot_bytes;
+                mbar_wait(empty0 + 8 * slot, phase ^ 1, P.dbg, 6, dead);
+                if (elect_one()) {
+                    if (P.debug & 1) {
+                        mbar_arrive(full0 + 8 * slot);
+                    } else {
+                        mbar_expect_tx(full0 + 8 * slot, P.res_abytes);
+                        tma_load_4d(&P.rmap, full0 + 8 * slot, sa, qb * P.n_tile, tx * P.TW, ty * rows_tile, img);
                     }
                 }
+                __syncwarp();
+                if (++slot == P.num_slots) { slot = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
         // =============================== MMA issuer =================================
-        if (lane == 0) {
-            // instruction descriptor: D=f32, A=B=bf16, K-major both, N>>3 @17, M>>4 @24
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.n_tile >> 3) << 17) | (8u << 24);
-            if (P.resident) mbar_wait(wbar, 0, P.dbg, 2, dead);
-            int slot = 0, acc = 0;
-            uint32_t phase = 0, acc_phase = 0;
-            for (int tile = blockIdx.x; tile < tiles_g; tile += gridDim.x) {
-                mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1, P.dbg, 3, dead);
-                tc_fence_after();
-                const uint32_t d0 = tmem_base + acc * P.acc_cols;
-                uint32_t boff = 0;
-                bool first = true;
-                for (int s = 0; s < P.n_seg; ++s) {
-                    const uint32_t rb = P.seg_rowbytes[s], lay = P.seg_layout[s];
-                    const int ksteps = P.seg_ck[s] >> 4;
-                    for (int local = 0; local < P.seg_stages[s]; ++local) {
-                        const uint32_t sa = slots0 + slot * P.slot_bytes;
-                        const uint32_t sb = P.resident ? (wres + boff) : (sa + P.seg_abytes[s]);
-                        mbar_wait(full0 + 8 * slot, phase, P.dbg, 4, dead);
-                        tc_fence_after();
-                        for (int m = 0; m < P.MT; ++m) {
-                            for (int ky = 0; ky < P.kh; ++ky) {
-                                const uint32_t arow = sa + (uint32_t)((m * P.rows_sub + ky) * P.TW) * rb;
-                                const uint32_t brow = sb + (uint32_t)(ky * P.n_tile) * rb;
-                                for (int k = 0; k < ksteps; ++k) {
-                                    const uint32_t accum = (first && ky == 0 && k == 0) ? 0u : 1u;
-                                    umma_bf16(d0 + m * P.n_tile, make_desc(arow + k * 32, rb, lay),
-                                              make_desc(brow + k * 32, rb, lay), idesc, accum);
-                                }
-                            }
-                        }
+        // instruction descriptor: D=f32, A=B=bf16, K-major both, N>>3 @17, M>>4 @24
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.n_tile >> 3) << 17) | (8u << 24);
+        if (P.resident || P.res_mma) mbar_wait(wbar, 0, P.dbg, 2, dead);
+        int slot = 0, acc = 0;
+        uint32_t phase = 0, acc_phase = 0;
+        for (int tile = blockIdx.x; tile < tiles_g; tile += gridDim.x) {
+            mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1, P.dbg, 3, dead);
+            tc_fence_after();
+            const uint32_t d0 = tmem_base + acc * P.acc_cols;
+            uint32_t boff = 0;
+            bool first = true;
+            for (int s = 0; s < P.n_seg; ++s) {
+                const uint32_t rb = P.seg_rowbytes[s];
+                const uint32_t desc_hi = ((rb * 8u) >> 4) | (1u << 14) | ((uint32_t)P.seg_layout[s] << 29);
+                const uint32_t a_ky = (P.TW * rb) >> 4, b_ky = (P.n_tile * rb) >> 4, a_m = (P.rows_sub * P.TW * rb) >> 4;
+                const int ksteps = P.seg_ck[s] >> 4;
+                for (int local = 0; local < P.seg_stages[s]; ++local) {
+                    const uint32_t sa = slots0 + slot * P.slot_bytes;
+                    const uint32_t sb = P.resident ? (wres + boff) : (sa + P.seg_abytes[s]);
+                    mbar_wait(full0 + 8 * slot, phase, P.dbg, 4, dead);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t a_lo = ((sa >> 4) & 0x3FFFu) | (1u << 16), b_lo = ((sb >> 4) & 0x3FFFu) | (1u << 16);
+                        if (P.debug & 4) {
+                        } else if (P.kh == 3) issue_stage<3>(d0, a_lo, b_lo, desc_hi, idesc, P.MT, P.n_tile, a_m, a_ky, b_ky, ksteps, first);
+                        else if (P.kh == 7) issue_stage<7>(d0, a_lo, b_lo, desc_hi, idesc, P.MT, P.n_tile, a_m, a_ky, b_ky, ksteps, first);
+                        else if (P.kh == 1) issue_stage<1>(d0, a_lo, b_lo, desc_hi, idesc, P.MT, P.n_tile, a_m, a_ky, b_ky, ksteps, first);
+                        else issue_stage<5>(d0, a_lo, b_lo, desc_hi, idesc, P.MT, P.n_tile, a_m, a_ky, b_ky, ksteps, first);
                         umma_commit(empty0 + 8 * slot);   // frees the slot when these MMAs retire
-                        first = false;
-                        boff += P.seg_bstage[s];
-                        if (++slot == P.num_slots) { slot = 0; phase ^= 1; }
                     }
+                    __syncwarp();
+                    first = false;
+                    boff += P.seg_bstage[s];
+                    if (++slot == P.num_slots) { slot = 0; phase ^= 1; }
                 }
-                umma_commit(tfull0 + 8 * acc);            // accumulator complete -> epilogue
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
+            if (P.res_mma) {                                   // D += residual * I
+                const uint32_t sa = slots0 + slot * P.slot_bytes;
+                mbar_wait(full0 + 8 * slot, phase, P.dbg, 7, dead);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t a_lo = ((sa >> 4) & 0x3FFFu) | (1u << 16), b_lo = ((wid >> 4) & 0x3FFFu) | (1u << 16);
+                    const uint32_t desc_hi = ((128u * 8u) >> 4) | (1u << 14) | (2u << 29);
+                    if (!(P.debug & 4))
+                        issue_stage<1>(d0, a_lo, b_lo, desc_hi, idesc, P.MT, P.n_tile, (P.rows_sub * P.TW * 128u) >> 4, 0, 0, 4, false);
+                    umma_commit(empty0 + 8 * slot);
+                }
+                __syncwarp();
+                if (++slot == P.num_slots) { slot = 0; phase ^= 1; }
+            }
+            if (elect_one()) umma_commit(tfull0 + 8 * acc);   // accumulator complete -> epilogue
+            __syncwarp();
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= 4) {
         // =============================== epilogue ===================================
         const int wq = warp - 4;                          // == warp % 4: the TMEM lane quarter this warp may read
         const int p = wq * 32 + lane;
         const int py = p / P.TW, px = p - py * P.TW;
-        int acc = 0;
+        int acc = 0, sbuf = 0;
         uint32_t acc_phase = 0;
+        // staged path: this warp owns rows [32*wq, 32*wq+32) of each staging buffer (a 1 KiB-aligned
+        // region of whole swizzle atoms) and stores them with its own TMA store - no cross-warp barrier
+        const uint32_t rowb = (uint32_t)P.n_store * 2u;
+        const uint32_t msk = rowb == 128u ? 7u : (rowb == 64u ? 3u : 1u);
+        const int rows_warp = 32 / P.TW;                  // image rows covered by one warp's 32 pixels
         for (int tile = blockIdx.x; tile < tiles_g; tile += gridDim.x) {
             const int li = tile / P.tiles_per_img;
             const int t = tile - li * P.tiles_per_img;
             const int img = g * P.imgs_per_group + li;
             const int ty = t / P.tiles_x, tx = t - ty * P.tiles_x;
+            const int x = tx * P.TW + px;
             mbar_wait(tfull0 + 8 * acc, acc_phase, P.dbg, 5, dead);
             tc_fence_after();
             for (int m = 0; m < P.MT; ++m) {
-                const int y = ty * rows_tile + m * P.rows_sub + py, x = tx * P.TW + px;
-                const bool valid = (y < P.H) && (x < P.W);
                 const uint32_t t0 = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * P.acc_cols + m * P.n_tile;
-                for (int c0 = 0; c0 < P.n_tile; c0 += 16) {
-                    float v[16];
-                    tmem_ld16(t0 + c0, v);
-                    if (valid) epi_store16<__nv_bfloat16>(P.epi, g, img, y, x, qb * P.n_tile + c0, v);
+                if (kStaged) {
+                    for (int b0 = 0; b0 < P.n_tile; b0 += P.n_store) {
+                        uint32_t r[4][16];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (j * 16 < P.n_store) tmem_ld16_nowait(t0 + b0 + j * 16, r[j]);
+                        if (lane == 0) bulk_wait_read<1>();      // the buffer used two stores ago is free again
+                        __syncwarp();
+                        tmem_ld_wait();
+                        const uint32_t row_base = stg0 + sbuf * P.stg_bytes + (uint32_t)p * rowb;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (j * 16 < P.n_store) stage_chunk(P.epi, r[j], bias_s + b0 + j * 16, row_base, j * 32u, msk);
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0 && !(P.debug & 2)) {
+                            const int n0 = qb * P.n_tile + b0;
+                            const int q = P.epi.pixshuf ? n0 / P.epi.cq : 0;
+                            const int ch = P.epi.pixshuf ? n0 - q * P.epi.cq : n0;
+                            tma_store_5d(&P.smap[q], stg0 + sbuf * P.stg_bytes + (uint32_t)(wq * 32) * rowb, ch, tx * P.TW,
+                                         ty * rows_tile + m * P.rows_sub + wq * rows_warp, li, g);
+                            bulk_commit();
+                        }
+                        sbuf ^= 1;
+                    }
+                } else {
+                    const int y = ty * rows_tile + m * P.rows_sub + py;
+                    const bool valid = (y < P.H) && (x < P.W) && !(P.debug & 2);
+                    for (int c0 = 0; c0 < P.n_tile; c0 += 16) {
+                        uint32_t r[16];
+                        tmem_ld16_nowait(t0 + c0, r);
+                        tmem_ld_wait();
+                        float v[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + bias_s[c0 + i];
+                        epi_act16(P.epi, v);
+                        if (valid) epi_store16<__nv_bfloat16, false>(P.epi, g, img, y, x, qb * P.n_tile + c0, v);
+                    }
                 }
             }
             tc_fence_before();
@@ -292,6 +447,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (kStaged && lane == 0) bulk_wait_all();   // staged tiles must be read out before shared memory goes away
     }
 
     tc_fence_before();
@@ -300,6 +456,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
+}
+
+// 64 x 64 bf16 identity in the swizzle-128B K-major layout (row n, 16-byte chunk j at j ^ (n & 7))
+__device__ __align__(1024) uint8_t g_identity[kIdentBytes];
+__global__ void fill_identity_kernel() {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // element index, 64 x 64
+    if (i >= 64 * 64) return;
+    const int n = i >> 6, k = i & 63;
+    uint32_t off = (uint32_t)n * 128u + (uint32_t)k * 2u;
+    off ^= ((off >> 7) & 7u) << 4;
+    *reinterpret_cast<__nv_bfloat16*>(g_identity + off) = __float2bfloat16_rn(n == k ? 1.f : 0.f);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -323,8 +490,13 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-static int g_sm_count = 0;
-static bool g_attr_set = false;
+static int g_sm_count[64] = {0};
+static bool g_dev_ready[64] = {false};
+static const uint8_t* g_ident_ptr[64] = {nullptr};
+
+static CUtensorMapSwizzle swizzle_for(int channels) {
+    return channels == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (channels == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
 
 int launch_conv_tc(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t stream) {
     EncodeTiledFn encode = get_encode();
@@ -332,30 +504,61 @@ int launch_conv_tc(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t stre
         set_error("cuTensorMapEncodeTiled not available from the driver");
         return VSRB_E_NODEVICE;
     }
-    if (!g_sm_count) {
-        int dev = 0;
-        VSRB_CUDA(cudaGetDevice(&dev));
-        VSRB_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
-    }
-    if (!g_attr_set) {
-        VSRB_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
-        g_attr_set = true;
+    int dev = 0;
+    VSRB_CUDA(cudaGetDevice(&dev));
+    VSRB_CHECK_ARG(dev >= 0 && dev < 64, "device ordinal %d out of range", dev);
+    if (!g_dev_ready[dev]) {
+        VSRB_CUDA(cudaDeviceGetAttribute(&g_sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
+        VSRB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+        VSRB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+        void* ip = nullptr;
+        VSRB_CUDA(cudaGetSymbolAddress(&ip, g_identity));
+        g_ident_ptr[dev] = reinterpret_cast<const uint8_t*>(ip);
+        // legacy default stream: ordered before every later launch of this process on this device
+        fill_identity_kernel<<<16, 256, 0, stream>>>();
+        VSRB_LAUNCH_CHECK();
+        g_dev_ready[dev] = true;
     }
     TcParams P;
     memset(&P, 0, sizeof(P));
     P.n_seg = p.n_seg; P.kh = p.kh; P.kw = p.kw; P.H = a->h; P.W = a->w;
     P.groups = p.groups; P.imgs_per_group = a->imgs_per_group;
-    P.n_tile = p.n_tile; P.n_blocks = p.n_blocks; P.stages_per_tile = p.stages_per_tile;
+    P.n_tile = p.n_tile; P.n_blocks = p.n_blocks;
     P.wblock_bytes = (uint32_t)p.wblock_bytes;
     P.w = reinterpret_cast<const uint8_t*>(a->packed) + p.bias_bytes;
+    P.ident = g_ident_ptr[dev];
     P.dbg = debug_flag();
+    {
+        const char* e = getenv("VSRB_TC_DEBUG");
+        P.debug = e ? atoi(e) : 0;
+    }
     fill_epi(a, p, &P.epi);
 
     P.TW = a->w <= 8 ? 8 : 16;
     P.rows_sub = 128 / P.TW;
     const int units = p.groups * p.n_blocks;
-    const int ctas_budget = (a->max_ctas > 0 ? a->max_ctas : g_sm_count);
-    const int avail = kSmemMax - kCtrlBytes - 1024;   // control block + alignment slack
+    const int ctas_budget = (a->max_ctas > 0 ? a->max_ctas : g_sm_count[dev]);
+
+    // EPI_NHWC tiles leave through two swizzled staging buffers and TMA stores (full-line, asynchronous
+    // writes); needs positive 16-byte-multiple strides.  VSRB_TC_DIRECT_STORE=1 forces per-thread stores.
+    const long long oimg = P.epi.out_img_stride, ogrp = P.epi.out_group_stride;
+    bool staged = a->epilogue == VSRB_EPI_NHWC && oimg > 0 && ogrp > 0 && oimg % 8 == 0 && ogrp % 8 == 0 &&
+                  (reinterpret_cast<uintptr_t>(a->out) & 15) == 0 && !getenv("VSRB_TC_DIRECT_STORE");
+    P.n_store = p.n_tile < 64 ? p.n_tile : 64;
+    if (p.pixshuf && p.cout / 4 < P.n_store) P.n_store = p.cout / 4;
+    if (P.n_store != 16 && P.n_store != 32 && P.n_store != 64) staged = false;
+    P.stg_bytes = (int)round_up((size_t)128 * P.n_store * 2, 4096);
+    const int stg_total = staged ? 2 * P.stg_bytes : 0;
+
+    // residual: folded into the accumulation by an identity-matrix MMA stage when it has the plain
+    // resblock shape; otherwise the direct-store epilogue adds it
+    P.res_mma = staged && a->residual && a->act == VSRB_ACT_NONE && p.n_tile == 64 && p.n_blocks == 1 && a->res_c % 8 == 0 &&
+                (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0;
+    if (a->residual && !P.res_mma) staged = false;
+    if (P.res_mma) P.epi.res = nullptr;
+    const int ident_total = P.res_mma ? kIdentBytes : 0;
+
+    const int avail = kSmemMax - kCtrlBytes - 1024 - (staged ? stg_total : 0) - ident_total;
     int MT = (2 * 2 * p.n_tile <= 512) ? 2 : 1;
     if (MT == 2) {
         long tiles2 = (long)a->imgs_per_group * ceil_div(a->h, 2 * P.rows_sub) * ceil_div(a->w, P.TW) * units;
@@ -370,6 +573,11 @@ int launch_conv_tc(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t stre
             amax = amax > P.seg_abytes[s] ? amax : P.seg_abytes[s];
             int ab = P.seg_abytes[s] + p.b_stage_bytes[s];
             abmax = abmax > ab ? abmax : ab;
+        }
+        P.res_abytes = (uint32_t)(P.rows_sub * MT * P.TW * 128);
+        if (P.res_mma) {
+            amax = amax > (int)P.res_abytes ? amax : (int)P.res_abytes;
+            abmax = abmax > (int)P.res_abytes ? abmax : (int)P.res_abytes;
         }
         const int slot_res = (int)round_up(amax, 1024), slot_str = (int)round_up(abmax, 1024);
         const int wres = (int)round_up(p.wblock_bytes, 1024);
@@ -390,6 +598,7 @@ int launch_conv_tc(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t stre
     P.acc_cols = P.MT * p.n_tile;
     P.tiles_x = ceil_div(a->w, P.TW);
     P.tiles_per_img = P.tiles_x * ceil_div(a->h, P.rows_sub * P.MT);
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     for (int s = 0; s < p.n_seg; ++s) {
         const SegPlan& sp = p.seg[s];
         P.seg_chunks[s] = sp.chunks; P.seg_ck[s] = sp.ck; P.seg_rowbytes[s] = sp.rowbytes;
@@ -398,13 +607,10 @@ int launch_conv_tc(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t stre
         cuuint64_t strides[3] = {(cuuint64_t)a->in_c[s] * 2, (cuuint64_t)a->w * a->in_c[s] * 2,
                                  (cuuint64_t)a->h * a->w * a->in_c[s] * 2};
         cuuint32_t box[4] = {(cuuint32_t)sp.ck, (cuuint32_t)P.TW, (cuuint32_t)P.box_rows, 1};
-        cuuint32_t estr[4] = {1, 1, 1, 1};
-        CUtensorMapSwizzle sw = sp.ck == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
-                                            : (sp.ck == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
         VSRB_CHECK_ARG(a->in_c[s] % 8 == 0, "segment %d: channel stride %d must be a multiple of 8", s, a->in_c[s]);
         VSRB_CHECK_ARG((reinterpret_cast<uintptr_t>(a->in[s]) & 15) == 0, "segment %d: pointer not 16-byte aligned", s);
         CUresult r = encode(&P.tmap[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a->in[s]), dims, strides, box,
-                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(sp.ck), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             set_error("cuTensorMapEncodeTiled failed with %d (seg %d, c=%d w=%d h=%d b=%d box=%d,%d,%d)", (int)r, s,
@@ -412,13 +618,46 @@ int launch_conv_tc(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t stre
             return VSRB_E_CUDA;
         }
     }
+    if (P.res_mma) {
+        cuuint64_t dims[4] = {(cuuint64_t)a->res_c, (cuuint64_t)a->w, (cuuint64_t)a->h, (cuuint64_t)a->batch};
+        cuuint64_t strides[3] = {(cuuint64_t)a->res_c * 2, (cuuint64_t)a->w * a->res_c * 2, (cuuint64_t)a->h * a->w * a->res_c * 2};
+        cuuint32_t box[4] = {64, (cuuint32_t)P.TW, (cuuint32_t)(P.rows_sub * P.MT), 1};
+        CUresult r = encode(&P.rmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a->residual), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("cuTensorMapEncodeTiled (residual) failed with %d", (int)r);
+            return VSRB_E_CUDA;
+        }
+    }
+    if (staged) {
+        const int nq = p.pixshuf ? 4 : 1, sx = p.pixshuf ? 2 : 1;
+        const long long OW = (long long)sx * a->w;
+        for (int q = 0; q < nq; ++q) {
+            char* obase = reinterpret_cast<char*>(a->out) + (((long long)(q >> 1) * OW + (q & 1)) * a->out_c) * 2;
+            cuuint64_t dims[5] = {(cuuint64_t)a->out_c, (cuuint64_t)a->w, (cuuint64_t)a->h, (cuuint64_t)a->imgs_per_group,
+                                  (cuuint64_t)p.groups};
+            cuuint64_t strides[4] = {(cuuint64_t)sx * a->out_c * 2, (cuuint64_t)sx * OW * a->out_c * 2, (cuuint64_t)oimg * 2,
+                                     (cuuint64_t)ogrp * 2};
+            cuuint32_t box[5] = {(cuuint32_t)P.n_store, (cuuint32_t)P.TW, (cuuint32_t)(32 / P.TW), 1, 1};
+            CUresult r = encode(&P.smap[q], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, obase, dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(P.n_store), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) {
+                set_error("cuTensorMapEncodeTiled (store) failed with %d (c=%d w=%d h=%d imgs=%d groups=%d, strides %lld %lld)",
+                          (int)r, a->out_c, a->w, a->h, a->imgs_per_group, p.groups, oimg, ogrp);
+                return VSRB_E_CUDA;
+            }
+        }
+    }
     const int tiles_g = a->imgs_per_group * P.tiles_per_img;
     int ctas_x = ctas_budget / units;
     if (ctas_x < 1) ctas_x = 1;
     if (ctas_x > tiles_g) ctas_x = tiles_g;
-    const int smem = kCtrlBytes + 1024 + (int)P.wres_bytes + P.num_slots * P.slot_bytes;
+    const int smem = kCtrlBytes + 1024 + (int)P.wres_bytes + ident_total + P.num_slots * P.slot_bytes + (staged ? stg_total : 0);
     dim3 grid(ctas_x, units);
-    conv_tc_kernel<<<grid, kThreads, smem, stream>>>(P);
+    if (staged) conv_tc_kernel<true><<<grid, kThreads, smem, stream>>>(P);
+    else conv_tc_kernel<false><<<grid, kThreads, smem, stream>>>(P);
     VSRB_LAUNCH_CHECK();
     return VSRB_OK;
 }

@@ -243,6 +243,7 @@ def _spynet_run(sp, frames: torch.Tensor, ref_idx: torch.Tensor, supp_idx: torch
     Returns flows [P,h,w,2] fp32 (channels-last, the layout flow_warp consumes)."""
     F_, _, h, w = frames.shape
     dev = frames.device
+    ops.TAG = "spynet"
     if resize:
         Hp, Wp = (h + 31) // 32 * 32, (w + 31) // 32 * 32
     else:
@@ -331,6 +332,7 @@ def _cleaner_run(cl, x: torch.Tensor, dt: int) -> torch.Tensor:
     Returns the NHWC copy of the refined frames (input of the propagation stems)."""
     B, c, h, w = x.shape
     dev = x.device
+    ops.TAG = "cleaner"
     tdt = ops.TORCH_DT[dt]
     mid = cl.resblock.conv[0].out_channels
     mid_c = _act_c(mid, dt)
@@ -382,6 +384,7 @@ def _basicvsr_run(bv, lrs: torch.Tensor, dt: int, x_nhwc: Optional[torch.Tensor]
         flows_b, flows_f = flows[:m], flows[m:]
 
     # ---- bidirectional propagation: both directions run as two weight groups ------------
+    ops.TAG = "propagation"
     x5 = x_nhwc.view(n, t, h, w, clr)
     pairs = ws("lr_pairs", (t, 2 * n, h, w, clr), tdt, dev)
     pairs.copy_(torch.cat([x5.flip(1), x5], 0).transpose(0, 1))      # step s: [frame t-1-s | frame s]
@@ -407,6 +410,7 @@ def _basicvsr_run(bv, lrs: torch.Tensor, dt: int, x_nhwc: Optional[torch.Tensor]
                        final_strides=(t * frame_el, (o_f - o_b) // es), extra_in=pairs[s], extra_c=clr, groups=2)
 
     # ---- fusion + upsampling + reconstruction, batched over frames (basicvsr.py:75-83) --
+    ops.TAG = "tail"
     n_up = len(bv.upsample)
     scale = 2 ** n_up
     H, W = h * scale, w * scale

@@ -18,6 +18,7 @@ ESIZE = {BF16: 2, F32: 4}
 # bench.py sets this to a list to time every launch with CUDA events on the launching stream:
 # entries are (kind, start_event, end_event, algorithmic work: FLOPs for convs, bytes otherwise)
 PROFILE = None
+TAG = ""          # set by the scheduler so profile entries can be grouped by network part
 
 
 class _Timed:
@@ -34,7 +35,7 @@ class _Timed:
     def __exit__(self, *exc):
         if PROFILE is not None:
             self.e1.record()
-            PROFILE.append((self.kind, self.e0, self.e1, self.work))
+            PROFILE.append((self.kind, self.e0, self.e1, self.work, TAG))
         return False
 
 
