@@ -1,5 +1,6 @@
 // C-ABI plumbing: errors, device info, conv geometry, weight packing, conv dispatch.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -46,6 +47,31 @@ int make_plan(const vsrb_conv_geom* g, ConvPlan* p) {
     else if (p->cout_pad % 128 == 0) { p->n_tile = 128; p->n_blocks = p->cout_pad / 128; }
     else if (p->cout_pad % 64 == 0) { p->n_tile = 64; p->n_blocks = p->cout_pad / 64; }
     else { p->n_tile = 16; p->n_blocks = p->cout_pad / 16; }
+    // "stacked" tensor-core layout: the kw filter columns sit side by side along the MMA N dimension
+    // (N = kw * n_tile <= 256), so one un-shifted activation tile feeds all of them and the x-shift
+    // is undone in the epilogue.  Cuts the A-operand shared-memory traffic per FLOP by kw.
+    p->stacked = 0;
+    p->ns = p->n_tile;
+    if (p->dtype == VSRB_BF16 && !p->pixshuf && (p->kw == 3 || p->kw == 7) && !getenv("VSRB_TC_NO_STACK")) {
+        // widest row any segment will use (same rule as below) bounds one stage's weight tile
+        int rb_max = 0;
+        for (int s = 0; s < g->n_seg; ++s) {
+            const int cpad = (int)round_up(g->seg_c[s], 16);
+            const int rb = 2 * ((cpad % 64 == 0) ? 64 : (cpad % 32 == 0 ? 32 : 16));
+            rb_max = rb > rb_max ? rb : rb_max;
+        }
+        const int cands[3] = {64, 32, 16};
+        for (int i = 0; i < 3; ++i)
+            if (p->cout_pad % cands[i] == 0 && p->kw * cands[i] <= 256 && p->kh * p->kw * cands[i] * rb_max <= 76 * 1024) {
+                p->stacked = 1;
+                p->n_tile = cands[i];
+                p->n_blocks = p->cout_pad / cands[i];
+                p->ns = p->kw * cands[i];
+                break;
+            }
+    }
+    const int kx_stages = p->stacked ? 1 : p->kw;      // pipeline stages per channel chunk
+    const int kx_rows = p->stacked ? p->kw : 1;        // filter columns inside one stage's B tile
     p->stages_per_tile = 0;
     p->wblock_bytes = 0;
     for (int s = 0; s < g->n_seg; ++s) {
@@ -60,9 +86,9 @@ int make_plan(const vsrb_conv_geom* g, ConvPlan* p) {
         sp.swz_mask = sp.ck == 64 ? 7 : (sp.ck == 32 ? 3 : 1);
         sp.layout = sp.ck == 64 ? 2 : (sp.ck == 32 ? 4 : 6);
         p->cin_packed += sp.c;
-        p->b_stage_bytes[s] = p->kh * p->n_tile * sp.rowbytes;
-        p->stages_per_tile += sp.chunks * p->kw;
-        p->wblock_bytes += (size_t)sp.chunks * p->kw * p->b_stage_bytes[s];
+        p->b_stage_bytes[s] = p->kh * kx_rows * p->n_tile * sp.rowbytes;
+        p->stages_per_tile += sp.chunks * kx_stages;
+        p->wblock_bytes += (size_t)sp.chunks * kx_stages * p->b_stage_bytes[s];
     }
     p->bias_bytes = round_up((size_t)p->groups * p->cout_pad * sizeof(float), 1024);
     if (p->dtype == VSRB_BF16)
@@ -84,7 +110,7 @@ __host__ __device__ static inline int orig_cout(int np, int cout, int pixshuf) {
 struct PackParams {
     int kh, kw, n_seg, groups, pixshuf;
     int seg_c[2], seg_off[2], seg_ck[2], seg_chunks[2], seg_rowbytes[2], seg_mask[2], seg_bstage[2];
-    int cin_total, cin_packed, cout, cout_pad, n_tile, n_blocks;
+    int cin_total, cin_packed, cout, cout_pad, n_tile, n_blocks, stacked;
     size_t wblock_bytes, bias_bytes;
 };
 
@@ -98,8 +124,9 @@ __global__ void pack_bias_kernel(PackParams pp, const float* __restrict__ bias, 
     out[i] = v;
 }
 
-// Tensor-core image: [group][n_block][stage (seg, chunk, kx)][ky][n][ck] bf16, each stage
-// region stored exactly as it must sit in shared memory (swizzled K-major rows).
+// Tensor-core image: [group][n_block][stage (seg, chunk, kx)][ky][n][ck] bf16 (classic) or
+// [group][n_block][stage (seg, chunk)][ky][kx][n][ck] (stacked), each stage region stored exactly as
+// it must sit in shared memory (swizzled K-major rows).
 __global__ void pack_tc_kernel(PackParams pp, const float* __restrict__ w, uint8_t* __restrict__ out) {
     size_t elems_per_block = pp.wblock_bytes / 2;
     size_t total = (size_t)pp.groups * pp.n_blocks * elems_per_block;
@@ -109,16 +136,26 @@ __global__ void pack_tc_kernel(PackParams pp, const float* __restrict__ w, uint8
         int g = (int)(blk / pp.n_blocks), qb = (int)(blk % pp.n_blocks);
         // locate segment / stage
         int s = 0;
-        size_t seg0_elems = (size_t)pp.seg_chunks[0] * pp.kw * pp.seg_bstage[0] / 2;
+        const int kxs = pp.stacked ? 1 : pp.kw;        // stages per channel chunk
+        size_t seg0_elems = (size_t)pp.seg_chunks[0] * kxs * pp.seg_bstage[0] / 2;
         size_t base_bytes = 0;
         if (r >= seg0_elems) { s = 1; r -= seg0_elems; base_bytes = seg0_elems * 2; }
         size_t st_elems = (size_t)pp.seg_bstage[s] / 2;
         int local = (int)(r / st_elems);
         size_t e = r - (size_t)local * st_elems;
-        int chunk = local / pp.kw, kx = local - chunk * pp.kw;
+        int chunk = local / kxs, kx = local - chunk * kxs;
         int ck = pp.seg_ck[s];
         int row = (int)(e / ck), kk = (int)(e - (size_t)row * ck);
-        int ky = row / pp.n_tile, n = row - ky * pp.n_tile;
+        int ky, n;
+        if (pp.stacked) {
+            ky = row / (pp.kw * pp.n_tile);
+            const int rem = row - ky * pp.kw * pp.n_tile;
+            kx = rem / pp.n_tile;
+            n = rem - kx * pp.n_tile;
+        } else {
+            ky = row / pp.n_tile;
+            n = row - ky * pp.n_tile;
+        }
         int np = qb * pp.n_tile + n;
         int ci = chunk * ck + kk;
         float v = 0.f;
@@ -168,7 +205,7 @@ int launch_pack(const vsrb_conv_geom* g, const ConvPlan& p, const float* w, int 
         VSRB_CHECK_ARG(p.seg[i].off + p.seg[i].c <= cin_total, "segment %d exceeds cin_total %d", i, cin_total);
     }
     pp.cin_total = cin_total; pp.cin_packed = p.cin_packed; pp.cout = p.cout; pp.cout_pad = p.cout_pad;
-    pp.n_tile = p.n_tile; pp.n_blocks = p.n_blocks; pp.wblock_bytes = p.wblock_bytes; pp.bias_bytes = p.bias_bytes;
+    pp.n_tile = p.n_tile; pp.n_blocks = p.n_blocks; pp.stacked = p.stacked; pp.wblock_bytes = p.wblock_bytes; pp.bias_bytes = p.bias_bytes;
     int nb = p.groups * p.cout_pad;
     pack_bias_kernel<<<ceil_div(nb, 256), 256, 0, s>>>(pp, bias, reinterpret_cast<float*>(packed));
     VSRB_LAUNCH_CHECK();
@@ -190,6 +227,7 @@ int launch_pack(const vsrb_conv_geom* g, const ConvPlan& p, const float* w, int 
 
 void fill_epi(const vsrb_conv_args* a, const ConvPlan& p, EpiParams* e) {
     e->mode = a->epilogue; e->act = a->act; e->slope = a->slope;
+    e->act_k = a->act == VSRB_ACT_NONE ? 1.f : (a->act == VSRB_ACT_RELU ? 0.f : a->slope);
     e->H = a->h; e->W = a->w;
     e->cout_pad = p.cout_pad; e->cq = p.pixshuf ? p.cout / 4 : 0; e->pixshuf = p.pixshuf;
     e->out = a->out; e->out_c = a->out_c; e->res = a->residual; e->res_c = a->res_c;
@@ -261,6 +299,7 @@ int vsrb_conv2d_fwd(const vsrb_conv_args* a, void* stream) {
     VSRB_CHECK_ARG(a->imgs_per_group >= 1 && a->imgs_per_group * p.groups == a->batch,
                    "batch %d != groups %d * imgs_per_group %d", a->batch, p.groups, a->imgs_per_group);
     VSRB_CHECK_ARG(a->packed, "null packed weights");
+    VSRB_CHECK_ARG(a->act != VSRB_ACT_LRELU || (a->slope >= 0.f && a->slope <= 1.f), "LeakyReLU slope must be in [0,1]");
     for (int s = 0; s < p.n_seg; ++s) {
         VSRB_CHECK_ARG(a->in[s], "null input segment %d", s);
         int need = p.dtype == VSRB_BF16 ? p.seg[s].cpad : p.seg[s].c;

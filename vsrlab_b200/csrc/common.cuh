@@ -70,6 +70,7 @@ struct ConvPlan {
     int cin_packed;        // sum of real segment channels (fp32 path K extent per tap)
     int cout, cout_pad;    // cout_pad = round_up(cout, 16)
     int n_tile, n_blocks;  // tensor-core path: output channels per CTA, CTAs along N
+    int stacked, ns;       // stacked layout: kw filter columns side by side along the MMA N (ns = kw*n_tile)
     int stages_per_tile;   // sum over segments of chunks*kw
     int b_stage_bytes[2];  // kh * n_tile * rowbytes
     size_t wblock_bytes;   // packed weights of one (group, n_block)
@@ -85,6 +86,7 @@ int make_plan(const vsrb_conv_geom* g, ConvPlan* p);   // returns VSRB_OK or err
 struct EpiParams {
     int mode, act;
     float slope;
+    float act_k;          // act(v) = max(v, v*act_k): 1 = none, 0 = ReLU, slope = LeakyReLU
     int H, W;             // conv extent
     int cout_pad, cq;     // cq = cout/4 when pixshuf
     int pixshuf;
@@ -181,14 +183,11 @@ __device__ __forceinline__ void epi_bias16(const EpiParams& e, int g, int n0, fl
     }
 }
 
+// Branch-free activation: act(v) = max(v, v * k) with k = 1 (none), 0 (ReLU), slope (LeakyReLU, slope <= 1)
 __device__ __forceinline__ void epi_act16(const EpiParams& e, float (&v)[16]) {
-    if (e.act == VSRB_ACT_RELU) {
+    const float k = e.act_k;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-    } else if (e.act == VSRB_ACT_LRELU) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = v[i] >= 0.f ? v[i] : v[i] * e.slope;
-    }
+    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], v[i] * k);
 }
 
 // One pixel (b,y,x), 16 consecutive packed output channels starting at n0 (multiple of 16);

@@ -32,7 +32,7 @@
 namespace vsrb {
 
 static constexpr int kMaxSlots = 8;
-static constexpr int kThreads = 256;
+static constexpr int kThreads = 384;   // 4 control warps + 8 epilogue warps
 static constexpr int kSmemMax = 232448;   // 227 KiB opt-in maximum per CTA on sm_100
 static constexpr int kCtrlBytes = 1024;
 static constexpr int kIdentBytes = 8192;  // 64 x 64 bf16 identity, swizzle-128B K-major image
@@ -49,6 +49,10 @@ struct TcParams {
     int kh, kw;
     int H, W;
     int TW, rows_sub, MT, box_rows;
+    int UW;                // output columns per tile: TW (classic) or TW - (kw-1) (stacked)
+    int kxs;               // pipeline stages per channel chunk: kw (classic) or 1 (stacked)
+    int ns;                // accumulator columns per sub-tile: n_tile (classic) or kw*n_tile (stacked)
+    int res_xoff;          // x offset of the residual box relative to the tile's first output column
     int tiles_x, tiles_per_img;
     int imgs_per_group, groups;
     int n_tile, n_blocks;
@@ -165,6 +169,18 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[1
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
 }
+template <int N>
+__device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t (&r)[N]);
+template <>
+__device__ __forceinline__ void tmem_ld_n<16>(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld16_nowait(taddr, r); }
+template <>
+__device__ __forceinline__ void tmem_ld_n<8>(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+// the two epilogue warps of TMEM lane quarter `wq` (64 threads) meet on named barrier 1 + wq
+__device__ __forceinline__ void pair_sync(int wq) { asm volatile("bar.sync %0, 64;" ::"r"(wq + 1) : "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
@@ -179,7 +195,7 @@ __device__ __forceinline__ bool elect_one() {
 // differ only in their 14-bit start-address field, so each MMA costs one add per operand.
 template <int KH>
 __device__ __forceinline__ void issue_stage(uint32_t d0, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
-                                            int MT, int n_tile, uint32_t a_m, uint32_t a_ky, uint32_t b_ky, int ksteps,
+                                            int MT, int d_m, uint32_t a_m, uint32_t a_ky, uint32_t b_ky, int ksteps,
                                             bool first) {
     for (int m = 0; m < MT; ++m) {
 #pragma unroll
@@ -189,7 +205,7 @@ __device__ __forceinline__ void issue_stage(uint32_t d0, uint32_t a_lo, uint32_t
                 if (k < ksteps) {
                     const uint64_t ad = ((uint64_t)desc_hi << 32) | (a_lo + m * a_m + ky * a_ky + k * 2);
                     const uint64_t bd = ((uint64_t)desc_hi << 32) | (b_lo + ky * b_ky + k * 2);
-                    umma_bf16(d0 + m * n_tile, ad, bd, idesc, (first && ky == 0 && k == 0) ? 0u : 1u);
+                    umma_bf16(d0 + m * d_m, ad, bd, idesc, (first && ky == 0 && k == 0) ? 0u : 1u);
                 }
             }
         }
@@ -220,7 +236,8 @@ __device__ __forceinline__ void stage_chunk(const EpiParams& e, const uint32_t (
 // ---------------------------------------------------------------------------------------
 // kStaged = true : EPI_NHWC through swizzled staging + per-warp TMA stores (the hot path)
 // kStaged = false: every other epilogue, direct per-thread stores (3-channel fp32 outputs etc.)
-template <bool kStaged>
+// kKW = 0: classic layout (one stage per filter column); 3 / 7: stacked layout (see api.cu make_plan)
+template <bool kStaged, int kKW>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ TcParams P) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -248,7 +265,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(tfull0 + 8 * i, 1);
-            mbar_init(tempty0 + 8 * i, 4);
+            mbar_init(tempty0 + 8 * i, 8);
         }
         mbar_init(wbar, 1);
         fence_barrier_init();
@@ -286,7 +303,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             const int t = tile - li * P.tiles_per_img;
             const int img = g * P.imgs_per_group + li;
             const int ty = t / P.tiles_x, tx = t - ty * P.tiles_x;
-            const int y0 = ty * rows_tile - P.kh / 2, x0 = tx * P.TW - P.kw / 2;
+            const int y0 = ty * rows_tile - P.kh / 2, x0 = tx * P.UW - P.kw / 2;
             uint32_t boff = 0;
             for (int s = 0; s < P.n_seg; ++s) {
                 const uint32_t abytes = P.seg_abytes[s], bbytes = P.seg_bstage[s];
@@ -305,7 +322,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                     }
                     __syncwarp();
                     boff += bbytes;
-                    if (++kx == P.kw) { kx = 0; ++chunk; }
+                    if (++kx == P.kxs) { kx = 0; ++chunk; }
                     if (++slot == P.num_slots) { slot = 0; phase ^= 1; }
                 }
             }
@@ -317,7 +334,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                         mbar_arrive(full0 + 8 * slot);
                     } else {
                         mbar_expect_tx(full0 + 8 * slot, P.res_abytes);
-                        tma_load_4d(&P.rmap, full0 + 8 * slot, sa, qb * P.n_tile, tx * P.TW, ty * rows_tile, img);
+                        tma_load_4d(&P.rmap, full0 + 8 * slot, sa, qb * P.n_tile, tx * P.UW - P.res_xoff, ty * rows_tile, img);
                     }
                 }
                 __syncwarp();
@@ -327,7 +344,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     } else if (warp == 1) {
         // =============================== MMA issuer =================================
         // instruction descriptor: D=f32, A=B=bf16, K-major both, N>>3 @17, M>>4 @24
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.n_tile >> 3) << 17) | (8u << 24);
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.ns >> 3) << 17) | (8u << 24);
+        const uint32_t idesc_res = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | (8u << 24);
         if (P.resident || P.res_mma) mbar_wait(wbar, 0, P.dbg, 2, dead);
         int slot = 0, acc = 0;
         uint32_t phase = 0, acc_phase = 0;
@@ -340,7 +358,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             for (int s = 0; s < P.n_seg; ++s) {
                 const uint32_t rb = P.seg_rowbytes[s];
                 const uint32_t desc_hi = ((rb * 8u) >> 4) | (1u << 14) | ((uint32_t)P.seg_layout[s] << 29);
-                const uint32_t a_ky = (P.TW * rb) >> 4, b_ky = (P.n_tile * rb) >> 4, a_m = (P.rows_sub * P.TW * rb) >> 4;
+                const uint32_t a_ky = (P.TW * rb) >> 4, b_ky = (P.ns * rb) >> 4, a_m = (P.rows_sub * P.TW * rb) >> 4;
                 const int ksteps = P.seg_ck[s] >> 4;
                 for (int local = 0; local < P.seg_stages[s]; ++local) {
                     const uint32_t sa = slots0 + slot * P.slot_bytes;
@@ -350,10 +368,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                     if (elect_one()) {
                         const uint32_t a_lo = ((sa >> 4) & 0x3FFFu) | (1u << 16), b_lo = ((sb >> 4) & 0x3FFFu) | (1u << 16);
                         if (P.debug & 4) {
-                        } else if (P.kh == 3) issue_stage<3>(d0, a_lo, b_lo, desc_hi, idesc, P.MT, P.n_tile, a_m, a_ky, b_ky, ksteps, first);
-                        else if (P.kh == 7) issue_stage<7>(d0, a_lo, b_lo, desc_hi, idesc, P.MT, P.n_tile, a_m, a_ky, b_ky, ksteps, first);
-                        else if (P.kh == 1) issue_stage<1>(d0, a_lo, b_lo, desc_hi, idesc, P.MT, P.n_tile, a_m, a_ky, b_ky, ksteps, first);
-                        else issue_stage<5>(d0, a_lo, b_lo, desc_hi, idesc, P.MT, P.n_tile, a_m, a_ky, b_ky, ksteps, first);
+                        } else if (P.kh == 3) issue_stage<3>(d0, a_lo, b_lo, desc_hi, idesc, P.MT, P.ns, a_m, a_ky, b_ky, ksteps, first);
+                        else if (P.kh == 7) issue_stage<7>(d0, a_lo, b_lo, desc_hi, idesc, P.MT, P.ns, a_m, a_ky, b_ky, ksteps, first);
+                        else if (P.kh == 1) issue_stage<1>(d0, a_lo, b_lo, desc_hi, idesc, P.MT, P.ns, a_m, a_ky, b_ky, ksteps, first);
+                        else issue_stage<5>(d0, a_lo, b_lo, desc_hi, idesc, P.MT, P.ns, a_m, a_ky, b_ky, ksteps, first);
                         umma_commit(empty0 + 8 * slot);   // frees the slot when these MMAs retire
                     }
                     __syncwarp();
@@ -370,7 +388,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                     const uint32_t a_lo = ((sa >> 4) & 0x3FFFu) | (1u << 16), b_lo = ((wid >> 4) & 0x3FFFu) | (1u << 16);
                     const uint32_t desc_hi = ((128u * 8u) >> 4) | (1u << 14) | (2u << 29);
                     if (!(P.debug & 4))
-                        issue_stage<1>(d0, a_lo, b_lo, desc_hi, idesc, P.MT, P.n_tile, (P.rows_sub * P.TW * 128u) >> 4, 0, 0, 4, false);
+                        issue_stage<1>(d0 + (kKW / 2) * P.n_tile, a_lo, b_lo, desc_hi, idesc_res, P.MT, P.ns, (P.rows_sub * P.TW * 128u) >> 4, 0,
+                                       0, 4, false);
                     umma_commit(empty0 + 8 * slot);
                 }
                 __syncwarp();
@@ -382,16 +401,27 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
     } else if (warp >= 4) {
         // =============================== epilogue ===================================
-        const int wq = warp - 4;                          // == warp % 4: the TMEM lane quarter this warp may read
+        // Two warps per TMEM lane quarter (hardware rule: a warp reads lanes 32*(warp%4)..+31): warp pair
+        // (wq, eh=0/1) shares the 32 pixels of quarter wq and splits their channels.
+        const int wq = (warp - 4) & 3;
+        const int eh = (warp - 4) >> 2;
         const int p = wq * 32 + lane;
         const int py = p / P.TW, px = p - py * P.TW;
         int acc = 0, sbuf = 0;
         uint32_t acc_phase = 0;
-        // staged path: this warp owns rows [32*wq, 32*wq+32) of each staging buffer (a 1 KiB-aligned
-        // region of whole swizzle atoms) and stores them with its own TMA store - no cross-warp barrier
+        // staged path: the pair owns rows [32*wq, 32*wq+32) of each staging buffer (a 1 KiB-aligned region
+        // of whole swizzle atoms) and stores them with its own TMA store - no CTA-wide barrier
         const uint32_t rowb = (uint32_t)P.n_store * 2u;
         const uint32_t msk = rowb == 128u ? 7u : (rowb == 64u ? 3u : 1u);
-        const int rows_warp = 32 / P.TW;                  // image rows covered by one warp's 32 pixels
+        const int rows_warp = 32 / P.TW;                  // image rows covered by one quarter's 32 pixels
+        const int cpw = P.n_store >= 32 ? P.n_store / 2 : P.n_store;   // channels of a store block per warp
+        const bool works = P.n_store >= 32 || eh == 0;    // 16-channel blocks are not split
+        const int cbeg = P.n_store >= 32 ? eh * cpw : 0;
+        // stacked layout (n_tile <= 64, one store block): this warp's bias values live in registers
+        float bias_r[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) bias_r[i] = (kKW > 0 && i < cpw) ? bias_s[cbeg + i] : 0.f;
+        const float act_k = P.epi.act_k;
         for (int tile = blockIdx.x; tile < tiles_g; tile += gridDim.x) {
             const int li = tile / P.tiles_per_img;
             const int t = tile - li * P.tiles_per_img;
@@ -400,24 +430,89 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             const int x = tx * P.TW + px;
             mbar_wait(tfull0 + 8 * acc, acc_phase, P.dbg, 5, dead);
             tc_fence_after();
-            for (int m = 0; m < P.MT; ++m) {
-                const uint32_t t0 = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * P.acc_cols + m * P.n_tile;
-                if (kStaged) {
+            for (int m = 0; m < ((P.debug & 8) ? 0 : P.MT); ++m) {
+                const uint32_t t0 = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * P.acc_cols + m * P.ns;
+                if (kKW > 0) {
+                    // ---- stacked layout: the quarter is one image row, lane = box column; filter column kx
+                    // sits in accumulator columns [kx*n_tile, (kx+1)*n_tile) and belongs to the output pixel
+                    // kx - pad lanes to the left, so out[lane] = sum_kx D_kx[lane + kx - pad] (warp shuffles)
+                    constexpr int PAD = kKW / 2;
+                    constexpr int CH = kKW == 3 ? 16 : 8;        // channels gathered per TMEM round trip
+                    const int y = ty * rows_tile + m * P.rows_sub + wq;
+                    const bool lane_ok = lane >= PAD && lane < 32 - PAD;
+                    const int xo = tx * P.UW + lane - PAD;
                     for (int b0 = 0; b0 < P.n_tile; b0 += P.n_store) {
-                        uint32_t r[4][16];
+                        if (kStaged) {
+                            if (eh == 0 && lane == 0) bulk_wait_read<1>();
+                            pair_sync(wq);
+                        }
+                        const uint32_t row_base = stg0 + sbuf * P.stg_bytes + (uint32_t)(wq * 32 + lane - PAD) * rowb;
+                        if (works) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (j * 16 < P.n_store) tmem_ld16_nowait(t0 + b0 + j * 16, r[j]);
-                        if (lane == 0) bulk_wait_read<1>();      // the buffer used two stores ago is free again
-                        __syncwarp();
+                            for (int cc = 0; cc < 2; ++cc) {
+                                const int c0 = cbeg + cc * 16;
+                                if (cc * 16 < cpw) {
+                                    float v[16];
+#pragma unroll
+                                    for (int hh = 0; hh < 16 / CH; ++hh) {
+                                        uint32_t r[kKW > 0 ? kKW : 1][CH];
+#pragma unroll
+                                        for (int kx = 0; kx < kKW; ++kx) tmem_ld_n<CH>(t0 + kx * P.n_tile + b0 + c0 + hh * CH, r[kx]);
+                                        tmem_ld_wait();
+#pragma unroll
+                                        for (int i = 0; i < CH; ++i) {
+                                            float sacc = __uint_as_float(r[PAD][i]) + bias_r[cc * 16 + hh * CH + i];
+#pragma unroll
+                                            for (int kx = 0; kx < kKW; ++kx)
+                                                if (kx != PAD)
+                                                    sacc += __shfl_sync(0xffffffffu, __uint_as_float(r[kx][i]), (lane + kx - PAD) & 31);
+                                            v[hh * CH + i] = fmaxf(sacc, sacc * act_k);
+                                        }
+                                    }
+                                    if (kStaged) {
+                                        if (lane_ok) {
+                                            uint32_t o0 = row_base + (uint32_t)c0 * 2u, o1 = o0 + 16u;
+                                            o0 ^= ((o0 >> 7) & msk) << 4;
+                                            o1 ^= ((o1 >> 7) & msk) << 4;
+                                            st_shared_v4(o0, pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
+                                                         pack_bf16(v[6], v[7]));
+                                            st_shared_v4(o1, pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]),
+                                                         pack_bf16(v[14], v[15]));
+                                        }
+                                    } else if (lane_ok && y < P.H && xo < P.W && !(P.debug & 2)) {
+                                        epi_store16<__nv_bfloat16, false>(P.epi, g, img, y, xo, qb * P.n_tile + b0 + c0, v);
+                                    }
+                                }
+                            }
+                        }
+                        if (kStaged) {
+                            fence_proxy_async();
+                            pair_sync(wq);
+                            if (eh == 0 && lane == 0 && !(P.debug & 2)) {
+                                tma_store_5d(&P.smap[0], stg0 + sbuf * P.stg_bytes + (uint32_t)(wq * 32) * rowb, qb * P.n_tile + b0,
+                                             tx * P.UW, y, li, g);
+                                bulk_commit();
+                            }
+                            sbuf ^= 1;
+                        }
+                    }
+                } else if (kStaged) {
+                    for (int b0 = 0; b0 < P.n_tile; b0 += P.n_store) {
+                        uint32_t r[2][16];
+#pragma unroll
+                        for (int j = 0; j < 2; ++j)
+                            if (works && j * 16 < cpw) tmem_ld16_nowait(t0 + b0 + cbeg + j * 16, r[j]);
+                        if (eh == 0 && lane == 0) bulk_wait_read<1>();      // the buffer used two stores ago is free again
+                        pair_sync(wq);
                         tmem_ld_wait();
                         const uint32_t row_base = stg0 + sbuf * P.stg_bytes + (uint32_t)p * rowb;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (j * 16 < P.n_store) stage_chunk(P.epi, r[j], bias_s + b0 + j * 16, row_base, j * 32u, msk);
+                        for (int j = 0; j < 2; ++j)
+                            if (works && j * 16 < cpw)
+                                stage_chunk(P.epi, r[j], bias_s + b0 + cbeg + j * 16, row_base, (uint32_t)(cbeg + j * 16) * 2u, msk);
                         fence_proxy_async();
-                        __syncwarp();
-                        if (lane == 0 && !(P.debug & 2)) {
+                        pair_sync(wq);
+                        if (eh == 0 && lane == 0 && !(P.debug & 2)) {
                             const int n0 = qb * P.n_tile + b0;
                             const int q = P.epi.pixshuf ? n0 / P.epi.cq : 0;
                             const int ch = P.epi.pixshuf ? n0 - q * P.epi.cq : n0;
@@ -430,7 +525,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 } else {
                     const int y = ty * rows_tile + m * P.rows_sub + py;
                     const bool valid = (y < P.H) && (x < P.W) && !(P.debug & 2);
-                    for (int c0 = 0; c0 < P.n_tile; c0 += 16) {
+                    for (int c0 = eh * 16; c0 < P.n_tile; c0 += 32) {     // the pair interleaves 16-channel chunks
                         uint32_t r[16];
                         tmem_ld16_nowait(t0 + c0, r);
                         tmem_ld_wait();
@@ -447,7 +542,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        if (kStaged && lane == 0) bulk_wait_all();   // staged tiles must be read out before shared memory goes away
+        if (kStaged && eh == 0 && lane == 0) bulk_wait_all();   // staged tiles must be read out before shared memory goes away
     }
 
     tc_fence_before();
@@ -509,8 +604,12 @@ int launch_conv_tc(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t stre
     VSRB_CHECK_ARG(dev >= 0 && dev < 64, "device ordinal %d out of range", dev);
     if (!g_dev_ready[dev]) {
         VSRB_CUDA(cudaDeviceGetAttribute(&g_sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
-        VSRB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
-        VSRB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+        VSRB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+        VSRB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+        VSRB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+        VSRB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+        VSRB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+        VSRB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
         void* ip = nullptr;
         VSRB_CUDA(cudaGetSymbolAddress(&ip, g_identity));
         g_ident_ptr[dev] = reinterpret_cast<const uint8_t*>(ip);
@@ -534,8 +633,12 @@ int launch_conv_tc(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t stre
     }
     fill_epi(a, p, &P.epi);
 
-    P.TW = a->w <= 8 ? 8 : 16;
+    P.TW = p.stacked ? 32 : (a->w <= 8 ? 8 : 16);
     P.rows_sub = 128 / P.TW;
+    P.UW = p.stacked ? P.TW - (p.kw - 1) : P.TW;
+    P.kxs = p.stacked ? 1 : p.kw;
+    P.ns = p.ns;
+    P.res_xoff = p.stacked ? p.kw / 2 : 0;
     const int units = p.groups * p.n_blocks;
     const int ctas_budget = (a->max_ctas > 0 ? a->max_ctas : g_sm_count[dev]);
 
@@ -559,9 +662,9 @@ int launch_conv_tc(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t stre
     const int ident_total = P.res_mma ? kIdentBytes : 0;
 
     const int avail = kSmemMax - kCtrlBytes - 1024 - (staged ? stg_total : 0) - ident_total;
-    int MT = (2 * 2 * p.n_tile <= 512) ? 2 : 1;
+    int MT = (2 * 2 * p.ns <= 512) ? 2 : 1;
     if (MT == 2) {
-        long tiles2 = (long)a->imgs_per_group * ceil_div(a->h, 2 * P.rows_sub) * ceil_div(a->w, P.TW) * units;
+        long tiles2 = (long)a->imgs_per_group * ceil_div(a->h, 2 * P.rows_sub) * ceil_div(a->w, P.UW) * units;
         if (a->h <= P.rows_sub || tiles2 < 2L * ctas_budget) MT = 1;
     }
     for (;; MT = 1) {
@@ -595,14 +698,14 @@ int launch_conv_tc(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t stre
             return VSRB_E_SMEM;
         }
     }
-    P.acc_cols = P.MT * p.n_tile;
-    P.tiles_x = ceil_div(a->w, P.TW);
+    P.acc_cols = P.MT * p.ns;
+    P.tiles_x = ceil_div(a->w, P.UW);
     P.tiles_per_img = P.tiles_x * ceil_div(a->h, P.rows_sub * P.MT);
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     for (int s = 0; s < p.n_seg; ++s) {
         const SegPlan& sp = p.seg[s];
         P.seg_chunks[s] = sp.chunks; P.seg_ck[s] = sp.ck; P.seg_rowbytes[s] = sp.rowbytes;
-        P.seg_layout[s] = sp.layout; P.seg_bstage[s] = p.b_stage_bytes[s]; P.seg_stages[s] = sp.chunks * p.kw;
+        P.seg_layout[s] = sp.layout; P.seg_bstage[s] = p.b_stage_bytes[s]; P.seg_stages[s] = sp.chunks * P.kxs;
         cuuint64_t dims[4] = {(cuuint64_t)a->in_c[s], (cuuint64_t)a->w, (cuuint64_t)a->h, (cuuint64_t)a->batch};
         cuuint64_t strides[3] = {(cuuint64_t)a->in_c[s] * 2, (cuuint64_t)a->w * a->in_c[s] * 2,
                                  (cuuint64_t)a->h * a->w * a->in_c[s] * 2};
@@ -639,7 +742,7 @@ int launch_conv_tc(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t stre
                                   (cuuint64_t)p.groups};
             cuuint64_t strides[4] = {(cuuint64_t)sx * a->out_c * 2, (cuuint64_t)sx * OW * a->out_c * 2, (cuuint64_t)oimg * 2,
                                      (cuuint64_t)ogrp * 2};
-            cuuint32_t box[5] = {(cuuint32_t)P.n_store, (cuuint32_t)P.TW, (cuuint32_t)(32 / P.TW), 1, 1};
+            cuuint32_t box[5] = {(cuuint32_t)P.n_store, (cuuint32_t)P.UW, (cuuint32_t)(p.stacked ? 1 : 32 / P.TW), 1, 1};
             CUresult r = encode(&P.smap[q], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, obase, dims, strides, box, estr,
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(P.n_store), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -656,8 +759,16 @@ int launch_conv_tc(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t stre
     if (ctas_x > tiles_g) ctas_x = tiles_g;
     const int smem = kCtrlBytes + 1024 + (int)P.wres_bytes + ident_total + P.num_slots * P.slot_bytes + (staged ? stg_total : 0);
     dim3 grid(ctas_x, units);
-    if (staged) conv_tc_kernel<true><<<grid, kThreads, smem, stream>>>(P);
-    else conv_tc_kernel<false><<<grid, kThreads, smem, stream>>>(P);
+    const int kkw = p.stacked ? p.kw : 0;
+    if (staged) {
+        if (kkw == 3) conv_tc_kernel<true, 3><<<grid, kThreads, smem, stream>>>(P);
+        else if (kkw == 7) conv_tc_kernel<true, 7><<<grid, kThreads, smem, stream>>>(P);
+        else conv_tc_kernel<true, 0><<<grid, kThreads, smem, stream>>>(P);
+    } else {
+        if (kkw == 3) conv_tc_kernel<false, 3><<<grid, kThreads, smem, stream>>>(P);
+        else if (kkw == 7) conv_tc_kernel<false, 7><<<grid, kThreads, smem, stream>>>(P);
+        else conv_tc_kernel<false, 0><<<grid, kThreads, smem, stream>>>(P);
+    }
     VSRB_LAUNCH_CHECK();
     return VSRB_OK;
 }
