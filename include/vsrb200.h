@@ -60,6 +60,12 @@ extern "C" {
 #define VSRB_EPI_FLOW   2  /* flow = flow_up + relu(acc+bias), fp32 [B,h,w,2] (spynet.py:56-65)         */
 #define VSRB_EPI_SR     3  /* sr_nchw_f32 = acc+bias + bilinear_x4(lq) (basicvsr.py:81-82; ac=False)   */
 
+/* vsrb_conv_args.flags */
+#define VSRB_CONV_PDL 1    /* launch with programmatic dependent launch: the kernel's prologue (TMEM
+                              allocation, barrier set-up, weight fetch) may overlap the tail of the previous
+                              kernel on the stream; only legal when `packed` was complete before that
+                              previous kernel was enqueued                                                */
+
 /* Geometry of one convolution's weights: everything the packer and the launcher
  * must agree on.  Stride 1, 'same' padding (kh//2, kw//2), dilation 1. */
 typedef struct vsrb_conv_geom {
@@ -97,6 +103,7 @@ typedef struct vsrb_conv_args {
     const float* f32_in;      /* EPI_FLOW: flow_up [B,h,w,2]; EPI_SR: lq [B,3,aux_h,aux_w]       */
     int32_t      aux_h, aux_w;/* EPI_SR: extent of the low-resolution skip frame                 */
     int32_t      max_ctas;    /* 0 = one persistent CTA per SM                                   */
+    int32_t      flags;       /* VSRB_CONV_* bits                                                */
 } vsrb_conv_args;
 
 /* ---- library ------------------------------------------------------------------------- */
@@ -119,6 +126,9 @@ size_t vsrb_packed_weight_bytes(const vsrb_conv_geom* g);
 int    vsrb_pack_conv_weight(const vsrb_conv_geom* g, const float* w, int32_t cin_total,
                              const float* bias, void* packed, void* stream);
 int    vsrb_conv2d_fwd(const vsrb_conv_args* a, void* stream);
+/* How the library will tile this geometry (diagnostics / tests): info = {stacked, n_tile, n_blocks,
+ * mma_n, k_chunk of segment 0, k_chunk of segment 1, pipeline stages per tile, weight KiB per block} */
+int    vsrb_conv_plan_info(const vsrb_conv_geom* g, int32_t info[8]);
 
 /* ---- backward warp: replaces flow_warp = meshgrid + normalise + F.grid_sample ---------
  * reference: spynet.py:95-106; callers basicvsr.py:54,69.

@@ -17,6 +17,7 @@ BF16, F32 = 0, 1
 ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
 PAD_ZEROS, PAD_BORDER = 0, 1
 EPI_NHWC, EPI_CLEAN, EPI_FLOW, EPI_SR = 0, 1, 2, 3
+CONV_PDL = 1
 
 
 class ConvGeom(C.Structure):
@@ -54,6 +55,7 @@ class ConvArgs(C.Structure):
         ("f32_in", C.c_void_p),
         ("aux_h", C.c_int32), ("aux_w", C.c_int32),
         ("max_ctas", C.c_int32),
+        ("flags", C.c_int32),
     ]
 
 
@@ -67,6 +69,7 @@ SYMBOLS = {
     "vsrb_packed_weight_bytes": (C.c_size_t, [C.POINTER(ConvGeom)]),
     "vsrb_pack_conv_weight": (C.c_int, [C.POINTER(ConvGeom), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vsrb_conv2d_fwd": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
+    "vsrb_conv_plan_info": (C.c_int, [C.POINTER(ConvGeom), C.POINTER(C.c_int32)]),
     "vsrb_flow_warp": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                  C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "vsrb_nchw_to_nhwc": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p]),

@@ -52,23 +52,46 @@ int make_plan(const vsrb_conv_geom* g, ConvPlan* p) {
     // is undone in the epilogue.  Cuts the A-operand shared-memory traffic per FLOP by kw.
     p->stacked = 0;
     p->ns = p->n_tile;
+    int ck_cap = 64;                                   // largest K chunk (channels) a stage may carry
     if (p->dtype == VSRB_BF16 && !p->pixshuf && (p->kw == 3 || p->kw == 7) && !getenv("VSRB_TC_NO_STACK")) {
-        // widest row any segment will use (same rule as below) bounds one stage's weight tile
-        int rb_max = 0;
-        for (int s = 0; s < g->n_seg; ++s) {
-            const int cpad = (int)round_up(g->seg_c[s], 16);
-            const int rb = 2 * ((cpad % 64 == 0) ? 64 : (cpad % 32 == 0 ? 32 : 16));
-            rb_max = rb > rb_max ? rb : rb_max;
-        }
-        const int cands[3] = {64, 32, 16};
-        for (int i = 0; i < 3; ++i)
-            if (p->cout_pad % cands[i] == 0 && p->kw * cands[i] <= 256 && p->kh * p->kw * cands[i] * rb_max <= 76 * 1024) {
-                p->stacked = 1;
-                p->n_tile = cands[i];
-                p->n_blocks = p->cout_pad / cands[i];
-                p->ns = p->kw * cands[i];
-                break;
+        // Pick classic vs stacked (and the stacked tile) with the operand-fetch model measured on B200
+        // (DESIGN.md "tensor-core cost model"): one K=16 MMA costs (128 + N) shared-memory row fetches, two
+        // per cycle for 64/128-byte rows and one per cycle for 32-byte rows; the stacked epilogue costs
+        // n_tile*(4*(kw-1)+24) cycles per 128 pixels; a stacked tile only yields (33-kw)/32 useful columns.
+        auto rows_cost = [](int ck) { return ck >= 32 ? 0.5 : 1.0; };
+        auto mma_cost = [&](int n_tile, int n, int cap, int stages_kx) {
+            double c = 0;
+            for (int s = 0; s < g->n_seg; ++s) {
+                const int cpad = (int)round_up(g->seg_c[s], 16);
+                int ck = (cpad % 64 == 0) ? 64 : (cpad % 32 == 0 ? 32 : 16);
+                if (ck > cap) ck = cap;
+                c += (double)(cpad / 16) * p->kh * stages_kx * (128 + n) * rows_cost(ck);
             }
+            return c * (p->cout_pad / n_tile);
+        };
+        double best = mma_cost(p->n_tile, p->n_tile, 64, p->kw);
+        const double classic_epi = 10.0 * p->cout_pad;
+        if (best < classic_epi) best = classic_epi;
+        const int cands[3] = {64, 32, 16};
+        for (int i = 0; i < 3; ++i) {
+            if (p->cout_pad % cands[i] != 0 || p->kw * cands[i] > 256) continue;
+            for (int j = 0; j < 3; ++j) {
+                if (p->kh * p->kw * cands[i] * cands[j] * 2 > 76 * 1024) continue;
+                double c = mma_cost(cands[i], p->kw * cands[i], cands[j], 1);
+                const double epi = (double)p->cout_pad * (4 * (p->kw - 1) + 24);
+                if (c < epi) c = epi;
+                c *= 32.0 / (33 - p->kw);
+                if (c < best) {
+                    best = c;
+                    p->stacked = 1;
+                    p->n_tile = cands[i];
+                    p->n_blocks = p->cout_pad / cands[i];
+                    p->ns = p->kw * cands[i];
+                    ck_cap = cands[j];
+                }
+                break;   // smaller chunks of the same tile are never cheaper
+            }
+        }
     }
     const int kx_stages = p->stacked ? 1 : p->kw;      // pipeline stages per channel chunk
     const int kx_rows = p->stacked ? p->kw : 1;        // filter columns inside one stage's B tile
@@ -81,6 +104,7 @@ int make_plan(const vsrb_conv_geom* g, ConvPlan* p) {
         sp.off = g->seg_off[s];
         sp.cpad = (int)round_up(sp.c, 16);
         sp.ck = (sp.cpad % 64 == 0) ? 64 : (sp.cpad % 32 == 0 ? 32 : 16);
+        if (sp.ck > ck_cap) sp.ck = ck_cap;
         sp.chunks = sp.cpad / sp.ck;
         sp.rowbytes = sp.ck * 2;
         sp.swz_mask = sp.ck == 64 ? 7 : (sp.ck == 32 ? 3 : 1);
@@ -288,6 +312,17 @@ int vsrb_pack_conv_weight(const vsrb_conv_geom* g, const float* w, int32_t cin_t
     if (rc != VSRB_OK) return rc;
     VSRB_CHECK_ARG(w && packed, "null weight / packed pointer");
     return launch_pack(g, p, w, cin_total, bias, packed, (cudaStream_t)stream);
+}
+
+int vsrb_conv_plan_info(const vsrb_conv_geom* g, int32_t info[8]) {
+    ConvPlan p;
+    int rc = make_plan(g, &p);
+    if (rc != VSRB_OK) return rc;
+    VSRB_CHECK_ARG(info, "null info");
+    info[0] = p.stacked; info[1] = p.n_tile; info[2] = p.n_blocks; info[3] = p.ns;
+    info[4] = p.seg[0].ck; info[5] = p.n_seg > 1 ? p.seg[1].ck : 0;
+    info[6] = p.stages_per_tile; info[7] = (int32_t)(p.wblock_bytes / 1024);
+    return VSRB_OK;
 }
 
 int vsrb_conv2d_fwd(const vsrb_conv_args* a, void* stream) {

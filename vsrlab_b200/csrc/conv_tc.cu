@@ -64,6 +64,7 @@ struct TcParams {
     uint32_t res_abytes;
     int n_store;           // channels per store block (<= 64)
     int stg_bytes;         // bytes of one staging buffer (two are allocated)
+    int pdl;               // launched with programmatic stream serialization (weights already stable)
     int* dbg;
     int debug;             // VSRB_TC_DEBUG bits (timing experiments only): 1 = no loads, 2 = no stores, 4 = no MMA
 };
@@ -182,6 +183,8 @@ __device__ __forceinline__ void tmem_ld_n<8>(uint32_t taddr, uint32_t (&r)[8]) {
 // the two epilogue warps of TMEM lane quarter `wq` (64 threads) meet on named barrier 1 + wq
 __device__ __forceinline__ void pair_sync(int wq) { asm volatile("bar.sync %0, 64;" ::"r"(wq + 1) : "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
@@ -276,6 +279,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    griddep_launch();      // the next kernel on the stream may start its own prologue as SMs free up
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
     const uint8_t* wsrc = P.w + ((size_t)g * P.n_blocks + qb) * P.wblock_bytes;
     bool dead = false;
@@ -296,6 +300,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             if (P.res_mma) bulk_load(wid, P.ident, kIdentBytes, wbar);
         }
         __syncwarp();
+        griddep_wait();        // activations (and the residual) come from the previous kernel(s)
         int slot = 0;
         uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < tiles_g; tile += gridDim.x) {
@@ -422,6 +427,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #pragma unroll
         for (int i = 0; i < 32; ++i) bias_r[i] = (kKW > 0 && i < cpw) ? bias_s[cbeg + i] : 0.f;
         const float act_k = P.epi.act_k;
+        griddep_wait();        // this role reads/writes global memory other kernels on the stream own
         for (int tile = blockIdx.x; tile < tiles_g; tile += gridDim.x) {
             const int li = tile / P.tiles_per_img;
             const int t = tile - li * P.tiles_per_img;
@@ -760,15 +766,22 @@ int launch_conv_tc(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t stre
     const int smem = kCtrlBytes + 1024 + (int)P.wres_bytes + ident_total + P.num_slots * P.slot_bytes + (staged ? stg_total : 0);
     dim3 grid(ctas_x, units);
     const int kkw = p.stacked ? p.kw : 0;
-    if (staged) {
-        if (kkw == 3) conv_tc_kernel<true, 3><<<grid, kThreads, smem, stream>>>(P);
-        else if (kkw == 7) conv_tc_kernel<true, 7><<<grid, kThreads, smem, stream>>>(P);
-        else conv_tc_kernel<true, 0><<<grid, kThreads, smem, stream>>>(P);
-    } else {
-        if (kkw == 3) conv_tc_kernel<false, 3><<<grid, kThreads, smem, stream>>>(P);
-        else if (kkw == 7) conv_tc_kernel<false, 7><<<grid, kThreads, smem, stream>>>(P);
-        else conv_tc_kernel<false, 0><<<grid, kThreads, smem, stream>>>(P);
-    }
+    P.pdl = (a->flags & VSRB_CONV_PDL) ? 1 : 0;
+    void (*kern)(TcParams) = nullptr;
+    if (staged) kern = kkw == 3 ? conv_tc_kernel<true, 3> : (kkw == 7 ? conv_tc_kernel<true, 7> : conv_tc_kernel<true, 0>);
+    else kern = kkw == 3 ? conv_tc_kernel<false, 3> : (kkw == 7 ? conv_tc_kernel<false, 7> : conv_tc_kernel<false, 0>);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = P.pdl ? 1 : 0;
+    VSRB_CUDA(cudaLaunchKernelEx(&cfg, kern, P));
     VSRB_LAUNCH_CHECK();
     return VSRB_OK;
 }

@@ -26,9 +26,10 @@ from ._lib import (ACT_LRELU, ACT_NONE, ACT_RELU, BF16, EPI_CLEAN, EPI_FLOW, EPI
 _forced: Optional[int] = None
 _NAMES = {"bf16": BF16, "fp32": F32, "f32": F32}
 
-# tunables (frames / images per launch batch; sized so a layer's in+out stays L2-resident)
-CLEAN_CHUNK = int(os.environ.get("VSRB_CLEAN_CHUNK", "6"))
-TAIL_CHUNK = int(os.environ.get("VSRB_TAIL_CHUNK", "2"))
+# tunables: frames / images per launch batch.  Measured on B200 (gpurun_out bench4*): the ~8 us fixed cost per
+# launch outweighs L2 residency, so batches are large; the tail is capped by the HR buffers (118 MB per frame).
+CLEAN_CHUNK = int(os.environ.get("VSRB_CLEAN_CHUNK", "30"))
+TAIL_CHUNK = int(os.environ.get("VSRB_TAIL_CHUNK", "8"))
 
 
 def set_precision(mode: Optional[str]) -> None:

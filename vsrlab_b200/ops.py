@@ -4,6 +4,7 @@ used for device memory and streams, nothing else."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence, Tuple
 
 import torch
@@ -18,6 +19,7 @@ ESIZE = {BF16: 2, F32: 4}
 # bench.py sets this to a list to time every launch with CUDA events on the launching stream:
 # entries are (kind, start_event, end_event, algorithmic work: FLOPs for convs, bytes otherwise)
 PROFILE = None
+PDL = os.environ.get("VSRB_PDL") == "1"   # programmatic dependent launch between consecutive convs (measured: no gain, off)
 TAG = ""          # set by the scheduler so profile entries can be grouped by network part
 
 
@@ -75,6 +77,7 @@ class PackedConv:
         self.cout_pad = (cout + 15) // 16 * 16
         self.dtype = dtype
         self.stamp = self.stamp_of(convs)
+        self.uses = 0            # launches since packing; PDL is enabled from the second one on
         w = torch.stack([c.weight.detach().to(torch.float32) for c in convs]).contiguous()
         b = None
         if convs[0].bias is not None:
@@ -114,6 +117,8 @@ def conv2d_fwd(pc: PackedConv, ins: Sequence, in_c: Sequence[int], batch: int, h
     a.f32_in = _p(f32_in)
     a.aux_h, a.aux_w = aux_hw
     a.max_ctas = max_ctas
+    a.flags = L.CONV_PDL if (pc.uses > 0 and PDL) else 0
+    pc.uses += 1
     g = pc.geom
     flops = 2.0 * batch * h * w * pc.cout * (g.seg_c[0] + (g.seg_c[1] if g.n_seg == 2 else 0)) * pc.kh * pc.kw
     with _Timed("conv_tc" if pc.dtype == BF16 else "conv_f32", flops):
