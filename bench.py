@@ -228,6 +228,28 @@ def main():
             q[2] += 1
     step_s_prof = sum(d[0] for d in fam.values())
 
+    # ---- flow_warp on a working set larger than L2 (64 feature maps, 473 MB in + 473 MB out), L2 flushed ----
+    def warp_standalone():
+        from vsrlab_b200._lib import BF16, PAD_ZEROS
+        n = 64
+        xw = torch.randn(n, LR_H, LR_W, 64, device=dev).to(torch.bfloat16)
+        fw = (torch.rand(n, LR_H, LR_W, 2, device=dev) - 0.5) * 4.0
+        ow = torch.empty_like(xw)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        ts = []
+        for i in range(8):
+            flush.zero_()
+            w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            w0.record()
+            ops.flow_warp(xw, fw, ow, n, LR_H, LR_W, 64, BF16, PAD_ZEROS)
+            w1.record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                ts.append(w0.elapsed_time(w1) * 1e-3)
+        return n * LR_H * LR_W * 264 / (sorted(ts)[len(ts) // 2]) / 1e9
+
+    warp_big = warp_standalone() if rank == 0 else 0.0
+
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -237,6 +259,10 @@ def main():
     e2e = frames_step * a.steps / (ms_e2e * 1e-3)
     if rank == 0:
         pk = peaks()
+        traffic = {}
+        tp = ROOT / "profiles" / "traffic.json"            # dram bytes per launch from `ncu --set full` captures
+        if tp.exists():
+            traffic = json.loads(tp.read_text())
         conv = fam.get("conv_tc", [1e-9, 0.0, 0])
         warp = fam.get("flow_warp", [1e-9, 0.0, 0])
         line = {
@@ -249,11 +275,15 @@ def main():
             "clocks": sampler.summary(),
             "roofline": {"kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, all launches of a step)", "bound": "tensor",
                          "achieved": conv[1] / conv[0] / 1e12, "peak": pk["tf_sust"], "unit": "TFLOP/s",
-                         "frac": conv[1] / conv[0] / 1e12 / pk["tf_sust"], "traffic": None, "peak_source": pk["src"] + " (sustained)",
+                         "frac": conv[1] / conv[0] / 1e12 / pk["tf_sust"], "traffic": traffic.get("conv_tc"),
+                         "peak_source": pk["src"] + " (sustained)",
                          "launches_per_step": conv[2], "share_of_step": conv[0] / max(step_s_prof, 1e-9)},
             "roofline_warp": {"kernel": "flow_warp_kernel", "bound": "hbm", "achieved": warp[1] / warp[0] / 1e9, "peak": pk["hbm"],
-                              "unit": "GB/s", "frac": warp[1] / warp[0] / 1e9 / pk["hbm"], "traffic": None,
-                              "launches_per_step": warp[2], "share_of_step": warp[0] / max(step_s_prof, 1e-9)},
+                              "unit": "GB/s", "frac": warp[1] / warp[0] / 1e9 / pk["hbm"], "traffic": traffic.get("flow_warp"),
+                              "launches_per_step": warp[2], "share_of_step": warp[0] / max(step_s_prof, 1e-9),
+                              "note": "in-step calls move 30 MB each (L2 resident, launch-latency bound); `standalone` is the "
+                                      "same kernel on 64 feature maps (946 MB, L2 flushed)",
+                              "standalone": {"achieved": warp_big, "frac": warp_big / pk["hbm"], "unit": "GB/s"}},
             "kernel_time_share": {k: round(v[0] / max(step_s_prof, 1e-9), 4) for k, v in fam.items()},
             "conv_by_part": {k: {"ms": round(v[0] * 1e3, 3), "tflops": round(v[1] / v[0] / 1e12, 1), "launches": v[2]}
                              for k, v in parts.items()},

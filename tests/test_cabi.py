@@ -54,3 +54,29 @@ def test_struct_layout_matches_header(lib):
     assert C.sizeof(_lib.ConvGeom) == 12 * 4
     assert C.sizeof(_lib.ConvArgs) % 8 == 0
     assert _lib.ConvArgs.packed.offset % 8 == 0 and _lib.ConvArgs.out_img_stride.offset % 8 == 0
+
+
+def test_conv_plan_selection(lib):
+    """The tiling the library picks per geometry (DESIGN.md 4.1 cost model): the hot 3x3 64->64 conv and the
+    SPyNet 7x7 convs use the stacked layout, stems with 3 input channels and 1x1 / pixel-shuffle convs the classic one."""
+    from vsrlab_b200 import _lib
+
+    def plan(k, segs, cout, pixshuf=0):
+        g = _lib.ConvGeom()
+        g.kh = g.kw = k
+        g.n_seg = len(segs)
+        for i, c in enumerate(segs):
+            g.seg_c[i] = c
+        g.cout, g.groups, g.dtype, g.pixshuf = cout, 1, _lib.BF16, pixshuf
+        info = (C.c_int32 * 8)()
+        assert lib.vsrb_conv_plan_info(C.byref(g), info) == 0
+        return list(info)
+    stacked, n_tile, n_blocks, mma_n = plan(3, [64], 64)[:4]
+    assert (stacked, n_tile, n_blocks, mma_n) == (1, 64, 1, 192)
+    assert plan(3, [64, 3], 64)[:4] == [1, 64, 1, 192]          # cat([lr_i, feat]) stem: two K segments
+    assert plan(3, [3], 64)[0] == 0                              # 16-channel (32-byte-row) stem stays classic
+    assert plan(1, [64, 64], 64)[:4] == [0, 64, 1, 64]           # 1x1 fusion conv
+    assert plan(3, [64], 256, pixshuf=2)[:4] == [0, 128, 2, 128]  # upsampling conv: N = 128, two blocks
+    for segs, cout in (([8], 32), ([32], 64), ([64], 32), ([32], 16), ([16], 2)):
+        info = plan(7, segs, cout)
+        assert info[0] == 1 and info[3] <= 256 and info[7] <= 128   # stacked, N <= 256, <= 128 KiB of weights per block

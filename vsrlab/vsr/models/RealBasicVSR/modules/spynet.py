@@ -16,9 +16,8 @@ class SpynetModule(nn.Module):
 
     def __init__(self):
         super().__init__()
-        self.basic_module = nn.Sequential(ConvReLU(8, 32, 7, 1, 3), ConvReLU(32, 64, 7, 1, 3),
-                                          ConvReLU(64, 32, 7, 1, 3), ConvReLU(32, 16, 7, 1, 3),
-                                          ConvReLU(16, 2, 7, 1, 3))
+        widths = (8, 32, 64, 32, 16, 2)     # [ref rgb, warped rgb, flow xy] -> flow residue
+        self.basic_module = nn.Sequential(*[ConvReLU(ci, co, 7, 1, 3) for ci, co in zip(widths[:-1], widths[1:])])
 
     def forward(self, x):
         return VF.conv_chain(x, [m.conv[0] for m in self.basic_module], act="relu")

@@ -75,48 +75,76 @@ template <> struct Vec16<float> {
 
 static constexpr int kWarpPix = 256;
 
-template <typename T>
+struct WarpTap {
+    long long base;   // element offset of the pixel's image inside x
+    TapSet t;
+};
+
+// TPP = 16-byte vectors per pixel (C / VEC); a power of two here so the work split is shifts only
+template <typename T, int TPP>
 __global__ void __launch_bounds__(256) flow_warp_kernel(const T* __restrict__ x, long long x_stride,
                                                         const float2* __restrict__ flow, long long f_stride,
-                                                        T* __restrict__ out, int n, int h, int w, int c, int border) {
-    __shared__ TapSet taps[kWarpPix];
+                                                        T* __restrict__ out, int n, int h, int w, int border) {
+    __shared__ WarpTap taps[kWarpPix];
     constexpr int VEC = Vec16<T>::N;
-    const int tpp = c / VEC;                         // threads (16-byte vectors) per pixel
-    const long long total = (long long)n * h * w;
-    const long long pix0 = (long long)blockIdx.x * kWarpPix;
+    constexpr int C = TPP * VEC;
+    const int hw = h * w;
+    const int total = n * hw;                          // launcher guarantees < 2^31
+    const int pix0 = blockIdx.x * kWarpPix;
     {
-        long long pix = pix0 + threadIdx.x;
+        const int pix = pix0 + threadIdx.x;
         if (pix < total) {
-            int xx = (int)(pix % w);
-            int yy = (int)((pix / w) % h);
-            float2 f = __ldg(flow + (pix / ((long long)h * w)) * f_stride + pix % ((long long)h * w));
+            const int img = pix / hw, r = pix - img * hw;
+            const int yy = r / w, xx = r - yy * w;
+            const float2 f = __ldg(flow + (long long)img * f_stride + r);
             float ix, iy;
             sample_pos((float)xx + f.x, (float)yy + f.y, w, h, ix, iy);
-            make_taps(ix, iy, w, h, border, taps[threadIdx.x]);
+            make_taps(ix, iy, w, h, border, taps[threadIdx.x].t);
+            taps[threadIdx.x].base = (long long)img * x_stride;
         }
     }
     __syncthreads();
-    const int work = kWarpPix * tpp;
+    const int npix = min(kWarpPix, total - pix0);
+    const int work = npix * TPP;
+#pragma unroll 2
     for (int i = threadIdx.x; i < work; i += 256) {
-        const int lp = i / tpp, part = i - lp * tpp;
-        const long long pix = pix0 + lp;
-        if (pix >= total) break;
-        const TapSet t = taps[lp];
-        const T* img = x + (pix / ((long long)h * w)) * x_stride + part * VEC;
+        const int lp = i / TPP, part = i % TPP;          // compile-time power of two: shift / mask
+        const WarpTap wt = taps[lp];
+        const T* img = x + wt.base + part * VEC;
         float acc[VEC];
 #pragma unroll
         for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            if (t.off[k] >= 0) {
+            if (wt.t.off[k] >= 0) {
                 float v[VEC];
-                Vec16<T>::load(img + (long long)t.off[k] * c, v);
+                Vec16<T>::load(img + (long long)wt.t.off[k] * C, v);
 #pragma unroll
-                for (int j = 0; j < VEC; ++j) acc[j] = fmaf(v[j], t.wgt[k], acc[j]);
+                for (int j = 0; j < VEC; ++j) acc[j] = fmaf(v[j], wt.t.wgt[k], acc[j]);
             }
         }
-        Vec16<T>::store(out + pix * c + part * VEC, acc);
+        Vec16<T>::store(out + (long long)(pix0 + lp) * C + part * VEC, acc);
     }
+}
+
+template <typename T>
+static int launch_flow_warp(const T* x, long long xs, const float2* flow, long long fs, T* out, int n, int h, int w, int c,
+                            int border, cudaStream_t s) {
+    constexpr int VEC = Vec16<T>::N;
+    const int tpp = c / VEC;
+    const int blocks = (int)(((long long)n * h * w + kWarpPix - 1) / kWarpPix);
+    switch (tpp) {
+        case 1: flow_warp_kernel<T, 1><<<blocks, 256, 0, s>>>(x, xs, flow, fs, out, n, h, w, border); break;
+        case 2: flow_warp_kernel<T, 2><<<blocks, 256, 0, s>>>(x, xs, flow, fs, out, n, h, w, border); break;
+        case 4: flow_warp_kernel<T, 4><<<blocks, 256, 0, s>>>(x, xs, flow, fs, out, n, h, w, border); break;
+        case 8: flow_warp_kernel<T, 8><<<blocks, 256, 0, s>>>(x, xs, flow, fs, out, n, h, w, border); break;
+        case 16: flow_warp_kernel<T, 16><<<blocks, 256, 0, s>>>(x, xs, flow, fs, out, n, h, w, border); break;
+        case 32: flow_warp_kernel<T, 32><<<blocks, 256, 0, s>>>(x, xs, flow, fs, out, n, h, w, border); break;
+        default:
+            set_error("flow_warp: %d channels is not %d * a power of two <= 32", c, VEC);
+            return VSRB_E_ARG;
+    }
+    return VSRB_OK;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -293,22 +321,21 @@ int vsrb_flow_warp(const void* x, int64_t x_img_stride, const float* flow, int64
     VSRB_CHECK_ARG(x && flow && out && n >= 1 && h >= 1 && w >= 1, "flow_warp: bad arguments");
     VSRB_CHECK_ARG(padding_mode == VSRB_PAD_ZEROS || padding_mode == VSRB_PAD_BORDER, "flow_warp: bad padding mode");
     VSRB_CHECK_ARG((long long)h * w < (1LL << 31), "flow_warp: image too large");
-    const long long total = (long long)n * h * w;
-    const int blocks = (int)((total + kWarpPix - 1) / kWarpPix);
+    VSRB_CHECK_ARG((long long)n * h * w < (1LL << 31), "flow_warp: more than 2^31 pixels in one call");
     cudaStream_t s = (cudaStream_t)stream;
+    int rc = VSRB_OK;
     if (dtype == VSRB_BF16) {
         VSRB_CHECK_ARG(c % 8 == 0, "flow_warp: bf16 needs c %% 8 == 0 (got %d)", c);
-        flow_warp_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), xs,
-                                                               reinterpret_cast<const float2*>(flow), fs,
-                                                               reinterpret_cast<__nv_bfloat16*>(out), n, h, w, c, padding_mode);
+        rc = launch_flow_warp<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(x), xs, reinterpret_cast<const float2*>(flow), fs,
+                                             reinterpret_cast<__nv_bfloat16*>(out), n, h, w, c, padding_mode, s);
     } else if (dtype == VSRB_F32) {
         VSRB_CHECK_ARG(c % 4 == 0, "flow_warp: fp32 needs c %% 4 == 0 (got %d)", c);
-        flow_warp_kernel<float><<<blocks, 256, 0, s>>>(reinterpret_cast<const float*>(x), xs,
-                                                       reinterpret_cast<const float2*>(flow), fs,
-                                                       reinterpret_cast<float*>(out), n, h, w, c, padding_mode);
+        rc = launch_flow_warp<float>(reinterpret_cast<const float*>(x), xs, reinterpret_cast<const float2*>(flow), fs,
+                                     reinterpret_cast<float*>(out), n, h, w, c, padding_mode, s);
     } else {
         VSRB_CHECK_ARG(false, "flow_warp: bad dtype");
     }
+    if (rc != VSRB_OK) return rc;
     VSRB_LAUNCH_CHECK();
     return VSRB_OK;
 }

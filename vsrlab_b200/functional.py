@@ -220,7 +220,10 @@ def flow_warp(x: torch.Tensor, flow: torch.Tensor, padding_mode: str = "zeros") 
     dt = current_dtype()
     n, c, h, w = x.shape
     vec = 8 if dt == BF16 else 4
-    ca = (c + vec - 1) // vec * vec
+    nv = 1
+    while nv * vec < c:                    # the kernel splits a pixel over a power-of-two number of 16-byte vectors
+        nv *= 2
+    ca = nv * vec
     xin, _ = _to_nhwc(x, dt, "m_in", ca)
     out = ws("m_out", (n, h, w, ca), ops.TORCH_DT[dt], x.device)
     ops.flow_warp(xin, flow, out, n, h, w, ca, dt, PAD_BORDER if padding_mode == "border" else PAD_ZEROS)
