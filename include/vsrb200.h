@@ -77,7 +77,9 @@ typedef struct vsrb_conv_geom {
     int32_t pixshuf;        /* 0, or 2 = output channel 4c+2i+j is stored at pixel (2y+i,2x+j)  */
     int32_t groups;         /* independent weight sets applied to consecutive image groups      */
     int32_t dtype;          /* VSRB_BF16 or VSRB_F32                                            */
-    int32_t transpose;      /* reserved (dgrad): 0                                              */
+    int32_t transpose;      /* 1 = pack the input-gradient conv of `w`: channels swapped, filter
+                               flipped; then seg_c[0] = forward cout, cout = forward cin and
+                               cin_total passed to the packer = forward cout                      */
 } vsrb_conv_geom;
 
 typedef struct vsrb_conv_args {
@@ -129,6 +131,21 @@ int    vsrb_conv2d_fwd(const vsrb_conv_args* a, void* stream);
 /* How the library will tile this geometry (diagnostics / tests): info = {stacked, n_tile, n_blocks,
  * mma_n, k_chunk of segment 0, k_chunk of segment 1, pipeline stages per tile, weight KiB per block} */
 int    vsrb_conv_plan_info(const vsrb_conv_geom* g, int32_t info[8]);
+
+/* ---- training (backward of the path; reference: autograd through the same modules) -------
+ * input gradient of a conv: vsrb_conv2d_fwd on the output gradient with weights packed with
+ * geom.transpose = 1.  Weight/bias gradient: dw [groups][cout][cin_total][kh][kw] and db
+ * [groups][cout] (or NULL) are fp32, ACCUMULATED into (zero them first); `g` is the forward
+ * geometry, in[]/in_c[] the forward inputs, dz the gradient wrt the conv output before the
+ * activation, NHWC with dz_c channels per pixel.                                          */
+int vsrb_conv2d_wgrad(const vsrb_conv_geom* g, const void* const* in, const int32_t* in_c, const void* dz,
+                      int32_t dz_c, int32_t batch, int32_t h, int32_t w, int32_t imgs_per_group,
+                      int32_t cin_total, float* dw, float* db, void* stream);
+/* backward of vsrb_flow_warp: dx (fp32 [n,h,w,c], accumulated with atomics, zero it first; or
+ * NULL) and dflow (fp32 [n,h,w,2], overwritten; or NULL; needs the forward input x).        */
+int vsrb_flow_warp_bwd(const void* x, const float* flow, const void* dout, float* dx, float* dflow,
+                       int32_t n, int32_t h, int32_t w, int32_t c, int32_t dtype, int32_t padding_mode,
+                       void* stream);
 
 /* ---- backward warp: replaces flow_warp = meshgrid + normalise + F.grid_sample ---------
  * reference: spynet.py:95-106; callers basicvsr.py:54,69.

@@ -1,0 +1,149 @@
+"""Backward of the hot path: gradients from the CUDA kernels (input-gradient conv = forward
+kernel with transposed packing, weight-gradient kernel, warp backward) against torch autograd through the CPU
+oracle.  bf16 activations: gradients agree to bf16 noise, asserted as cosine similarity and relative L2 error."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import vsr_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    from vsrlab_b200 import load
+    load()
+    return torch.device("cuda:0")
+
+
+def bf16r(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+def rel(a, b):
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+def cos(a, b):
+    return F.cosine_similarity(a.flatten().double(), b.flatten().double(), dim=0).item()
+
+
+@pytest.mark.parametrize("case", [
+    # (segs, cout, k, act, pixshuf, residual)
+    ([(0, 64)], 64, 3, "relu", 0, False),
+    ([(0, 64)], 64, 3, "none", 0, True),
+    ([(3, 64), (0, 3)], 64, 3, "lrelu", 0, False),
+    ([(0, 64), (64, 64)], 64, 1, "lrelu", 0, False),
+    ([(0, 64)], 256, 3, "none", 2, False),
+    ([(0, 64)], 3, 3, "none", 0, False),
+    ([(0, 8)], 32, 7, "relu", 0, False),
+    ([(0, 32)], 16, 7, "relu", 0, False),
+], ids=lambda c: f"k{c[2]}_{c[0]}_{c[1]}_{c[3]}")
+def test_conv_gradients(dev, case):
+    from vsrlab_b200 import autograd as AG
+    segs, cout, k, act, pixshuf, residual = case
+    g = torch.Generator().manual_seed(7)
+    cin = sum(c for _, c in segs)
+    cv = torch.nn.Conv2d(cin, cout, k, 1, k // 2)
+    with torch.no_grad():
+        cv.weight.copy_(bf16r(torch.randn(cv.weight.shape, generator=g) / (cin * k * k) ** 0.5))
+        cv.bias.copy_(torch.randn(cv.bias.shape, generator=g) * 0.1)
+    B, h, w = 2, 20, 28
+    x = bf16r(torch.randn(B, cin, h, w, generator=g))
+    res = bf16r(torch.randn(B, cout, h, w, generator=g)) if residual else None
+    r = pixshuf or 1
+    gy = bf16r(torch.randn(B, cout // (r * r), h * r, w * r, generator=g))
+    # oracle: fp32 autograd on the same bf16-representable operands
+    xr = x.clone().requires_grad_(True)
+    wr, br = cv.weight.detach().clone().requires_grad_(True), cv.bias.detach().clone().requires_grad_(True)
+    rr = res.clone().requires_grad_(True) if residual else None
+    y = F.conv2d(xr, wr, br, padding=k // 2)
+    y = {"none": lambda v: v, "relu": O.relu, "lrelu": O.lrelu}[act](y)
+    if residual:
+        y = y + rr
+    if pixshuf:
+        y = O.pixel_shuffle(y, 2)
+    (y * gy).sum().backward()
+    # device
+    cvd = torch.nn.Conv2d(cin, cout, k, 1, k // 2).to(dev)
+    cvd.load_state_dict(cv.state_dict())
+    ins = []
+    for off, c in segs:
+        ins.append(AG.to_cl16(x[:, off:off + c].to(dev)).requires_grad_(True))
+    rd = AG.to_cl16(res.to(dev)).requires_grad_(True) if residual else None
+    yd = AG.conv(cvd, ins, segs, act, 0.1, pixshuf, rd)
+    co = cout // (r * r)
+    (yd[:, :co].float() * gy.to(dev)).sum().backward()
+    assert rel(yd[:, :co].float().cpu(), y.detach()) < 1e-2
+    assert cos(cvd.weight.grad.cpu(), wr.grad) > 0.9995 and rel(cvd.weight.grad.cpu(), wr.grad) < 2e-2
+    assert rel(cvd.bias.grad.cpu(), br.grad) < 2e-2
+    for (off, c), t in zip(segs, ins):
+        gx = t.grad[:, :c].float().cpu()
+        assert cos(gx, xr.grad[:, off:off + c]) > 0.999 and rel(gx, xr.grad[:, off:off + c]) < 2e-2
+        if t.shape[1] > c:
+            assert t.grad[:, c:].abs().max().item() == 0          # padded channels get no gradient
+    if residual:
+        assert rel(rd.grad[:, :cout].float().cpu(), rr.grad) < 1e-2
+
+
+@pytest.mark.parametrize("border,dtype", [(False, torch.bfloat16), (True, torch.float32)])
+def test_warp_gradients(dev, border, dtype):
+    from vsrlab_b200 import autograd as AG
+    g = torch.Generator().manual_seed(11)
+    c = 64 if dtype == torch.bfloat16 else 4
+    x = bf16r(torch.randn(2, c, 17, 23, generator=g))
+    fl = (torch.rand(2, 17, 23, 2, generator=g) - 0.5) * 12
+    gy = bf16r(torch.randn(2, c, 17, 23, generator=g))
+    xr, fr = x.clone().requires_grad_(True), fl.clone().requires_grad_(True)
+    (O.flow_warp(xr, fr, "border" if border else "zeros") * gy).sum().backward()
+    xd = x.to(dev).to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    fd = fl.to(dev).requires_grad_(True)
+    (AG.WarpFn.apply(xd, fd, border).float() * gy.to(dev)).sum().backward()
+    assert rel(xd.grad.float().cpu(), xr.grad) < (1e-2 if dtype == torch.bfloat16 else 1e-5)
+    assert rel(fd.grad.cpu(), fr.grad) < (2e-2 if dtype == torch.bfloat16 else 1e-4)
+
+
+@pytest.mark.parametrize("train_flow", [False, True])
+def test_realbasicvsr_training_step_gradients(dev, train_flow):
+    from vsrlab.vsr.models.RealBasicVSR.realbasicvsr import RealBasicVSR
+    torch.manual_seed(3)
+    net = RealBasicVSR(cleaning_blocks=1, mid_channels=64, upscale=4, res_blocks=1, pretrained_flow=False, train_flow=train_flow)
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    g = torch.Generator().manual_seed(4)
+    lr = torch.rand(1, 3, 3, 32, 32, generator=g)
+    hr = torch.rand(1, 3, 3, 128, 128, generator=g)
+    # oracle: fp32 autograd on CPU, Charbonnier-style loss as train.py uses (core/losses.py:10-18)
+    P = {k: v.clone().requires_grad_(v.is_floating_point() and not k.endswith(("mean", "std"))) for k, v in sd.items()}
+    sr_o, lq_o = O.realbasicvsr(lr.clone(), P)
+    loss_o = torch.sqrt((sr_o - hr) ** 2 + 1e-9).mean() + torch.sqrt((lq_o - F.interpolate(hr[0], size=(32, 32), mode="bilinear")) ** 2 + 1e-9).mean()
+    loss_o.backward()
+    net = net.to(dev).train()
+    x = lr.clone().to(dev)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        sr, lq = net(x)
+    assert sr.dtype == torch.float32 and sr.requires_grad
+    loss = torch.sqrt((sr - hr.to(dev)) ** 2 + 1e-9).mean() + \
+        torch.sqrt((lq - F.interpolate(hr[0].to(dev), size=(32, 32), mode="bilinear")) ** 2 + 1e-9).mean()
+    loss.backward()
+    assert abs(loss.item() - loss_o.item()) < 2e-3
+    assert torch.allclose(x.cpu(), lq.detach().cpu())             # the caller's clip now holds the cleaned frames
+    # per-tensor direction, and the direction of the whole gradient.  bf16 activations flip a few ReLU masks on
+    # the 1x1 .. 4x4 pyramid levels of SPyNet, so tiny tensors there are noisier than the rest.
+    got, want = [], []
+    for name, p in net.named_parameters():
+        ref = P[name].grad
+        if not p.requires_grad:
+            assert p.grad is None
+            continue
+        assert p.grad is not None, name
+        assert torch.isfinite(p.grad).all(), name
+        if ref is None or ref.norm() < 1e-7:
+            continue
+        got.append(p.grad.flatten().cpu())
+        want.append(ref.flatten())
+        assert cos(p.grad.cpu(), ref) > (0.90 if "spynet" in name else 0.97), (name, cos(p.grad.cpu(), ref))
+    assert cos(torch.cat(got), torch.cat(want)) > 0.99
+    assert rel(torch.cat(got), torch.cat(want)) < 0.1

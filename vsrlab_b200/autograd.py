@@ -1,0 +1,255 @@
+"""Training path: the same modules under torch autograd.
+
+Every convolution (forward, input gradient, weight/bias gradient) and every feature warp (forward,
+backward wrt features and flow) runs in libvsrb200.so; torch autograd only records the graph and
+differentiates the cheap glue around them (concats, the fp32 residue/flow additions, pyramid
+resampling, the bilinear skip).  Activations are bf16 `channels_last` tensors, i.e. exactly the NHWC
+buffers the kernels consume, so there is no layout copy between torch and the kernels.
+
+Reference: train.py:90-101 drives `model(lr)` under autocast and calls `.backward()` on the
+Charbonnier losses (core/utils.py:235-280); this module is what makes that work on the drop-in.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from . import ops
+from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, BF16, F32, PAD_BORDER, PAD_ZEROS, VsrbError
+from . import _lib as L
+import ctypes as C
+
+CL = torch.channels_last
+_packed_t = {}
+_ACT = {"none": ACT_NONE, "relu": ACT_RELU, "lrelu": ACT_LRELU}
+
+
+def _cl(t: torch.Tensor) -> torch.Tensor:
+    return t if t.is_contiguous(memory_format=CL) else t.contiguous(memory_format=CL)
+
+
+def _packed_transposed(conv) -> ops.PackedConvT:
+    key = id(conv)
+    pc = _packed_t.get(key)
+    if pc is None or pc.stamp != ops.PackedConv.stamp_of([conv]):
+        pc = ops.PackedConvT(conv, BF16)
+        _packed_t[key] = pc
+    return pc
+
+
+class ConvFn(torch.autograd.Function):
+    """act(conv(cat(inputs))) [+ residual] [pixel-shuffled], bf16 channels_last in and out."""
+
+    @staticmethod
+    def forward(ctx, weight, bias, conv, segs, act, slope, pixshuf, residual, *inputs):
+        from .functional import packed
+        pc = packed([conv], segs, BF16, pixshuf)
+        ins = [_cl(t) for t in inputs]
+        b, _, h, w = ins[0].shape
+        r = pixshuf or 1
+        co = conv.out_channels // (r * r)
+        oc = (co + 15) // 16 * 16
+        out = torch.empty((b, oc, h * r, w * r), dtype=torch.bfloat16, device=ins[0].device, memory_format=CL)
+        res = _cl(residual) if residual is not None else None
+        if res is not None and act != "none":
+            raise VsrbError("ConvFn: a fused residual needs act='none' (reference conv.py:89-92)")
+        ops.conv2d_fwd(pc, ins, [t.shape[1] for t in ins], b, h, w, act=_ACT[act], slope=slope, out=out, out_c=oc,
+                       residual=res, res_c=0 if res is None else res.shape[1])
+        ctx.conv, ctx.segs, ctx.act, ctx.slope, ctx.pixshuf = conv, segs, act, slope, pixshuf
+        ctx.has_res = res is not None
+        ctx.save_for_backward(weight, out if act != "none" else None, *ins)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        weight, out = ctx.saved_tensors[0], ctx.saved_tensors[1]
+        ins = list(ctx.saved_tensors[2:])
+        conv, segs = ctx.conv, ctx.segs
+        dy = _cl(dy)
+        d_res = dy if ctx.has_res else None
+        dz = dy
+        if ctx.act == "relu":
+            dz = dy * (out > 0)
+        elif ctx.act == "lrelu":
+            dz = torch.where(out > 0, dy, dy * ctx.slope)
+        cout = conv.out_channels
+        if ctx.pixshuf:
+            dz = F.pixel_unshuffle(dz[:, :cout // (ctx.pixshuf ** 2)], ctx.pixshuf)
+        dz = _cl(dz)
+        dz_c = dz.shape[1]
+        b, _, h, w = ins[0].shape
+        # weight / bias gradient
+        g = L.ConvGeom()
+        g.kh, g.kw, g.n_seg = conv.kernel_size[0], conv.kernel_size[1], len(segs)
+        for i, (off, c) in enumerate(segs):
+            g.seg_off[i], g.seg_c[i] = off, c
+        g.cout, g.pixshuf, g.groups, g.dtype, g.transpose = cout, 0, 1, BF16, 0
+        dw = db = None
+        if ctx.needs_input_grad[0]:
+            dw = torch.zeros_like(weight, dtype=torch.float32)
+            db = torch.zeros(cout, dtype=torch.float32, device=weight.device) if conv.bias is not None else None
+            ops.conv2d_wgrad(g, ins, [t.shape[1] for t in ins], dz, dz_c, b, h, w, conv.in_channels, dw, db)
+        # input gradient: the forward kernel on dz with transposed + flipped weights
+        d_ins: List[Optional[torch.Tensor]] = [None] * len(ins)
+        if any(ctx.needs_input_grad[8 + i] for i in range(len(ins))):
+            pt = _packed_transposed(conv)
+            dx = torch.empty((b, pt.cout_pad, h, w), dtype=torch.bfloat16, device=dz.device, memory_format=CL)
+            ops.conv2d_fwd(pt, [dz], [dz_c], b, h, w, act=ACT_NONE, out=dx, out_c=pt.cout_pad)
+            for i, (off, c) in enumerate(segs):
+                if not ctx.needs_input_grad[8 + i]:
+                    continue
+                ca = ins[i].shape[1]
+                if len(segs) == 1 and ca == pt.cout_pad:
+                    d_ins[i] = dx
+                else:
+                    d_ins[i] = F.pad(dx[:, off:off + c], (0, 0, 0, 0, 0, ca - c))
+        return (dw, db if (conv.bias is not None and ctx.needs_input_grad[1]) else None, None, None, None, None, None, d_res, *d_ins)
+
+
+class WarpFn(torch.autograd.Function):
+    """flow_warp on a channels_last tensor (bf16 or fp32); flow [B,h,w,2] fp32."""
+
+    @staticmethod
+    def forward(ctx, x, flow, border):
+        x = _cl(x)
+        flow = flow.contiguous()
+        b, c, h, w = x.shape
+        dt = BF16 if x.dtype == torch.bfloat16 else F32
+        out = torch.empty_like(x, memory_format=CL)
+        ops.flow_warp(x, flow, out, b, h, w, c, dt, PAD_BORDER if border else PAD_ZEROS)
+        ctx.border, ctx.dt = border, dt
+        ctx.save_for_backward(x, flow)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, flow = ctx.saved_tensors
+        dout = _cl(dout)
+        b, c, h, w = x.shape
+        dx32 = torch.zeros((b, h, w, c), dtype=torch.float32, device=x.device) if ctx.needs_input_grad[0] else None
+        dflow = torch.empty_like(flow) if ctx.needs_input_grad[1] else None
+        ops.flow_warp_bwd(x, flow, dout, dx32, dflow, b, h, w, c, ctx.dt, PAD_BORDER if ctx.border else PAD_ZEROS)
+        dx = dx32.to(x.dtype).permute(0, 3, 1, 2) if dx32 is not None else None
+        return dx, dflow, None
+
+
+# --------------------------------------------------------------------------------------
+# the modules, differentiable
+# --------------------------------------------------------------------------------------
+def conv(mod, inputs: Sequence[torch.Tensor], segs, act="none", slope=0.1, pixshuf=0, residual=None) -> torch.Tensor:
+    return ConvFn.apply(mod.weight, mod.bias, mod, tuple(segs), act, slope, pixshuf, residual, *inputs)
+
+
+def to_cl16(x: torch.Tensor) -> torch.Tensor:
+    """[B,c,h,w] -> bf16 channels_last, channels zero-padded to a multiple of 16."""
+    c = x.shape[1]
+    pad = (-c) % 16
+    x = x.to(torch.bfloat16)
+    if pad:
+        x = F.pad(x, (0, 0, 0, 0, 0, pad))
+    return _cl(x)
+
+
+def resblock(rb, inputs, segs) -> torch.Tensor:
+    """ResidualBlock.forward (conv.py:101-103) on bf16 channels_last tensors."""
+    mid = rb.conv[0].out_channels
+    x = conv(rb.conv[0], inputs, segs, "lrelu")
+    for blk in rb.res_block:
+        t = conv(blk.conv1, [x], [(0, mid)], "relu")
+        x = conv(blk.conv2, [t], [(0, mid)], "none", residual=x)
+    return x
+
+
+def cleaner(cl, x: torch.Tensor) -> torch.Tensor:
+    """IterativeRefinement on [B,3,h,w] fp32 (realbasicvsr.py:24-30), out of place under autograd."""
+    mid = cl.resblock.conv[0].out_channels
+    for _ in range(cl.steps):
+        f = resblock(cl.resblock, [to_cl16(x)], [(0, 3)])
+        x = x + conv(cl.conv, [f], [(0, mid)], "none")[:, :3].float()
+    return x
+
+
+def spynet(sp, ref: torch.Tensor, supp: torch.Tensor) -> torch.Tensor:
+    """Spynet.forward with gradients (spynet.py:38-93); resampling glue in torch fp32, convs + warps native."""
+    h, w = ref.shape[-2:]
+    hp, wp = (h + 31) // 32 * 32, (w + 31) // 32 * 32
+    ref = F.interpolate(ref, size=(hp, wp), mode="bilinear", align_corners=False)
+    supp = F.interpolate(supp, size=(hp, wp), mode="bilinear", align_corners=False)
+    refs, supps = [(ref - sp.mean) / sp.std], [(supp - sp.mean) / sp.std]
+    for _ in range(5):
+        refs.append(F.avg_pool2d(refs[-1], 2, 2))
+        supps.append(F.avg_pool2d(supps[-1], 2, 2))
+    refs, supps = refs[::-1], supps[::-1]
+    flow = ref.new_zeros(ref.shape[0], 2, hp // 32, wp // 32)
+    for level in range(6):
+        flow_up = flow if level == 0 else F.interpolate(flow, scale_factor=2, mode="bilinear", align_corners=True) * 2.0
+        s4 = _cl(F.pad(supps[level], (0, 0, 0, 0, 0, 1)))                       # fp32, 4 channels
+        warped = WarpFn.apply(s4, flow_up.permute(0, 2, 3, 1).contiguous(), True)[:, :3]
+        x = to_cl16(torch.cat([refs[level], warped, flow_up], 1))
+        mods = sp.basic_module[level].basic_module
+        for j in range(5):
+            cv = mods[j].conv[0]
+            x = conv(cv, [x], [(0, cv.in_channels)], "relu")
+        flow = flow_up + x[:, :2].float()
+    flow = F.interpolate(flow, size=(h, w), mode="bilinear", align_corners=False)
+    scale = flow.new_tensor([float(w) / float(wp), float(h) / float(hp)]).view(1, 2, 1, 1)
+    return flow * scale
+
+
+def basicvsr(bv, lrs: torch.Tensor) -> torch.Tensor:
+    """BasicVSR.forward with gradients (basicvsr.py:39-83)."""
+    from . import functional as VF
+    n, t, c, h, w = lrs.shape
+    mid = bv.mid_channels
+    train_flow = any(p.requires_grad for p in bv.spynet.parameters())
+    a = lrs[:, :-1].reshape(-1, c, h, w)
+    b = lrs[:, 1:].reshape(-1, c, h, w)
+    if train_flow:
+        fb = spynet(bv.spynet, a, b).view(n, t - 1, 2, h, w).permute(0, 1, 3, 4, 2)
+        ff = spynet(bv.spynet, b, a).view(n, t - 1, 2, h, w).permute(0, 1, 3, 4, 2)
+    else:
+        with torch.no_grad():
+            ref, supp = VF._pair_indices(n, t, lrs.device)
+            fl = VF._spynet_run(bv.spynet, lrs.detach().reshape(n * t, c, h, w).contiguous(), ref, supp, BF16)
+            m = n * (t - 1)
+            fb, ff = fl[:m].view(n, t - 1, h, w, 2), fl[m:].view(n, t - 1, h, w, 2)
+    lr16 = to_cl16(lrs.reshape(n * t, c, h, w)).view(n, t, 16, h, w)
+    segs = [(3, mid), (0, 3)]
+    back: List[Optional[torch.Tensor]] = [None] * t
+    feat = torch.zeros((n, mid, h, w), dtype=torch.bfloat16, device=lrs.device).contiguous(memory_format=CL)
+    for i in range(t - 1, -1, -1):
+        if i < t - 1:
+            feat = WarpFn.apply(feat, fb[:, i], False)
+        feat = resblock(bv.backward_resblocks, [feat, _cl(lr16[:, i])], segs)
+        back[i] = feat
+    fwd: List[torch.Tensor] = []
+    feat = torch.zeros_like(feat)
+    for i in range(t):
+        if i > 0:
+            feat = WarpFn.apply(feat, ff[:, i - 1], False)
+        feat = resblock(bv.forward_resblocks, [feat, _cl(lr16[:, i])], segs)
+        fwd.append(feat)
+    # fusion + reconstruction, batched over frames (frame order (n, t) like the output)
+    bk = _cl(torch.stack(back, 1).flatten(0, 1))
+    fw = _cl(torch.stack(fwd, 1).flatten(0, 1))
+    x = conv(bv.point_conv[0], [bk, fw], [(0, mid), (mid, mid)], "lrelu")
+    for up in bv.upsample:
+        x = conv(up.upconv, [x], [(0, mid)], "none", pixshuf=2)
+    x = conv(bv.conv_last[0], [x], [(0, mid)], "lrelu")
+    x = conv(bv.conv_last[2], [x], [(0, bv.conv_last[2].in_channels)], "none")[:, :3].float()
+    scale = 2 ** len(bv.upsample)
+    skip = F.interpolate(lrs.reshape(n * t, c, h, w), scale_factor=scale, mode="bilinear", align_corners=False)
+    return (x + skip).view(n, t, c, h * scale, w * scale)
+
+
+def realbasicvsr(model, lr: torch.Tensor):
+    """(sr, lq) with gradients.  The cleaned clip is also written back into the caller's `lr`, which is what the
+    reference's in-place refinement leaves there (realbasicvsr.py:26-29)."""
+    n, t, c, h, w = lr.shape
+    lq = cleaner(model.cleaner, lr.reshape(n * t, c, h, w).float()).view(n, t, c, h, w)
+    sr = basicvsr(model.basicvsr, lq)
+    with torch.no_grad():
+        lr.copy_(lq)
+    return sr, lq

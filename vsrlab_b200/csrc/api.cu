@@ -37,7 +37,7 @@ int make_plan(const vsrb_conv_geom* g, ConvPlan* p) {
     VSRB_CHECK_ARG(g->dtype == VSRB_BF16 || g->dtype == VSRB_F32, "bad dtype %d", g->dtype);
     VSRB_CHECK_ARG(g->pixshuf == 0 || (g->pixshuf == 2 && g->cout % 64 == 0),
                    "pixshuf needs factor 2 and cout %% 64 == 0");
-    VSRB_CHECK_ARG(g->transpose == 0, "transpose packing not implemented");
+    VSRB_CHECK_ARG(g->transpose == 0 || (g->transpose == 1 && !g->pixshuf), "transpose packing excludes pixshuf");
     memset(p, 0, sizeof(*p));
     p->kh = g->kh; p->kw = g->kw; p->n_seg = g->n_seg; p->groups = g->groups;
     p->pixshuf = g->pixshuf; p->dtype = g->dtype;
@@ -131,10 +131,19 @@ __host__ __device__ static inline int orig_cout(int np, int cout, int pixshuf) {
     return 4 * c + q;
 }
 
+// element of the OIHW source: forward layout w[g][o][c][ky][kx]; transposed (input-gradient conv): the
+// packed conv maps the forward OUTPUT channels (its input, index c) to the forward INPUT channels (its
+// output, index o) with the filter flipped: w_t[o][c][ky][kx] = w[c][o][kh-1-ky][kw-1-kx]
+#define VSRB_W_SRC(pp, g, o, c, ky, kx)                                                                              \
+    ((pp).transpose                                                                                                 \
+         ? w[((((size_t)(g) * (pp).cin_total + (c)) * (pp).cout + (o)) * (pp).kh + ((pp).kh - 1 - (ky))) * (pp).kw + \
+             ((pp).kw - 1 - (kx))]                                                                                  \
+         : w[((((size_t)(g) * (pp).cout + (o)) * (pp).cin_total + (c)) * (pp).kh + (ky)) * (pp).kw + (kx)])
+
 struct PackParams {
     int kh, kw, n_seg, groups, pixshuf;
     int seg_c[2], seg_off[2], seg_ck[2], seg_chunks[2], seg_rowbytes[2], seg_mask[2], seg_bstage[2];
-    int cin_total, cin_packed, cout, cout_pad, n_tile, n_blocks, stacked;
+    int cin_total, cin_packed, cout, cout_pad, n_tile, n_blocks, stacked, transpose;
     size_t wblock_bytes, bias_bytes;
 };
 
@@ -185,7 +194,7 @@ __global__ void pack_tc_kernel(PackParams pp, const float* __restrict__ w, uint8
         float v = 0.f;
         if (np < pp.cout && ci < pp.seg_c[s]) {
             int o = orig_cout(np, pp.cout, pp.pixshuf);
-            v = w[((((size_t)g * pp.cout + o) * pp.cin_total + pp.seg_off[s] + ci) * pp.kh + ky) * pp.kw + kx];
+            v = VSRB_W_SRC(pp, g, o, pp.seg_off[s] + ci, ky, kx);
         }
         uint32_t off = (uint32_t)row * pp.seg_rowbytes[s] + (uint32_t)kk * 2;
         off ^= ((off >> 7) & pp.seg_mask[s]) << 4;
@@ -211,7 +220,7 @@ __global__ void pack_f32_kernel(PackParams pp, const float* __restrict__ w, floa
         float v = 0.f;
         if (np < pp.cout) {
             int o = orig_cout(np, pp.cout, pp.pixshuf);
-            v = w[((((size_t)g * pp.cout + o) * pp.cin_total + pp.seg_off[s] + ci) * pp.kh + ky) * pp.kw + kx];
+            v = VSRB_W_SRC(pp, g, o, pp.seg_off[s] + ci, ky, kx);
         }
         out[i] = v;
     }
@@ -229,7 +238,7 @@ int launch_pack(const vsrb_conv_geom* g, const ConvPlan& p, const float* w, int 
         VSRB_CHECK_ARG(p.seg[i].off + p.seg[i].c <= cin_total, "segment %d exceeds cin_total %d", i, cin_total);
     }
     pp.cin_total = cin_total; pp.cin_packed = p.cin_packed; pp.cout = p.cout; pp.cout_pad = p.cout_pad;
-    pp.n_tile = p.n_tile; pp.n_blocks = p.n_blocks; pp.stacked = p.stacked; pp.wblock_bytes = p.wblock_bytes; pp.bias_bytes = p.bias_bytes;
+    pp.n_tile = p.n_tile; pp.n_blocks = p.n_blocks; pp.stacked = p.stacked; pp.transpose = g->transpose; pp.wblock_bytes = p.wblock_bytes; pp.bias_bytes = p.bias_bytes;
     int nb = p.groups * p.cout_pad;
     pack_bias_kernel<<<ceil_div(nb, 256), 256, 0, s>>>(pp, bias, reinterpret_cast<float*>(packed));
     VSRB_LAUNCH_CHECK();

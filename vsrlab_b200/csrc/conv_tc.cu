@@ -653,7 +653,7 @@ int launch_conv_tc(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t stre
     const long long oimg = P.epi.out_img_stride, ogrp = P.epi.out_group_stride;
     bool staged = a->epilogue == VSRB_EPI_NHWC && oimg > 0 && ogrp > 0 && oimg % 8 == 0 && ogrp % 8 == 0 &&
                   (reinterpret_cast<uintptr_t>(a->out) & 15) == 0 && !getenv("VSRB_TC_DIRECT_STORE");
-    P.n_store = p.n_tile < 64 ? p.n_tile : 64;
+    P.n_store = (p.n_tile % 64 == 0) ? 64 : ((p.n_tile % 32 == 0) ? 32 : 16);   // store block must divide n_tile
     if (p.pixshuf && p.cout / 4 < P.n_store) P.n_store = p.cout / 4;
     if (P.n_store != 16 && P.n_store != 32 && P.n_store != 64) staged = false;
     P.stg_bytes = (int)round_up((size_t)128 * P.n_store * 2, 4096);

@@ -1,0 +1,331 @@
+// Backward kernels of the hot path (training).
+//
+//  * input gradient of a conv  = the forward conv kernel run on the output gradient with the weights packed
+//    transposed + flipped (vsrb_conv_geom.transpose = 1) - no new kernel;
+//  * weight / bias gradient     = conv_wgrad_kernel below: dW[co][ci][ky][kx] = sum_pixels dz[p][co] * x[p + tap][ci]
+//    (reference: autograd's ConvolutionBackward0 of every nn.Conv2d on the path);
+//  * flow_warp backward         = flow_warp_bwd_kernel: scatter of the output gradient through the four bilinear
+//    taps (grad wrt the warped features) and the derivative of the taps wrt the sample position (grad wrt the
+//    flow, needed when train_flow=True) - reference: GridSampler2DBackward0 behind spynet.py:95-106.
+#include "common.cuh"
+
+namespace vsrb {
+
+template <typename T> struct Ld8;
+template <> struct Ld8<__nv_bfloat16> {
+    __device__ static void load(const __nv_bfloat16* p, float (&v)[8]) {
+        uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+        float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+    }
+};
+template <> struct Ld8<float> {
+    __device__ static void load(const float* p, float (&v)[8]) {
+        float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+// weight gradient.  One CTA = one filter tap x one 64(co) x 64(ci) tile x a run of pixels; fp32 accumulate in
+// registers (4x4 per thread), bf16/fp32 operands staged through shared memory 32 pixels at a time, result
+// added to the OIHW fp32 gradient with atomics (several pixel runs and the groups' images share it).
+// ---------------------------------------------------------------------------------------
+struct WgradParams {
+    const void* in[2];
+    int in_c[2], seg_c[2], seg_off[2];
+    int n_seg;
+    const void* dz;
+    int dz_c;
+    int kh, kw, H, W, imgs_per_group, groups;
+    int cout, cin_total;
+    int pix_per_cta;          // pixels of one group handled by one CTA
+    int n_co_blk, n_ci_blk;   // 64-wide blocks
+    int ci_blk_seg[8], ci_blk_c0[8];
+    float* dw;
+    float* db;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) conv_wgrad_kernel(WgradParams P) {
+    __shared__ __align__(16) float zs[32][64];
+    __shared__ __align__(16) float xs[32][64];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;             // 4 ci per tx, 4 co per ty
+    const int tap = blockIdx.y;
+    const int ky = tap / P.kw, kx = tap - ky * P.kw;
+    int z = blockIdx.z;
+    const int cib = z % P.n_ci_blk; z /= P.n_ci_blk;
+    const int cob = z % P.n_co_blk;
+    const int g = z / P.n_co_blk;
+    const int s = P.ci_blk_seg[cib], c0 = P.ci_blk_c0[cib];
+    const int co0 = cob * 64;
+    const int hw = P.H * P.W;
+    const int pix_g = P.imgs_per_group * hw;            // pixels of this group
+    const int p_begin = blockIdx.x * P.pix_per_cta;
+    const int p_end = min(p_begin + P.pix_per_cta, pix_g);
+    const T* zin = reinterpret_cast<const T*>(P.dz);
+    const T* xin = reinterpret_cast<const T*>(P.in[s]);
+    const int lp = tid >> 3, lc = (tid & 7) * 8;        // loader: pixel lp of the 32, channels lc..lc+8
+    const int dy = ky - P.kh / 2, dx = kx - P.kw / 2;
+
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+
+    for (int p0 = p_begin; p0 < p_end; p0 += 32) {
+        const int p = p0 + lp;
+        float zv[8], xv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { zv[i] = 0.f; xv[i] = 0.f; }
+        if (p < p_end) {
+            const int li = p / hw, r = p - li * hw;
+            const int y = r / P.W, x = r - y * P.W;
+            const long long img = (long long)g * P.imgs_per_group + li;
+            if (co0 + lc < P.dz_c) {
+                Ld8<T>::load(zin + (img * hw + r) * P.dz_c + co0 + lc, zv);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (co0 + lc + i >= P.cout) zv[i] = 0.f;
+            }
+            const int yy = y + dy, xx = x + dx;
+            if (yy >= 0 && yy < P.H && xx >= 0 && xx < P.W && c0 + lc < P.in_c[s]) {
+                Ld8<T>::load(xin + (img * hw + (long long)yy * P.W + xx) * P.in_c[s] + c0 + lc, xv);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (c0 + lc + i >= P.seg_c[s]) xv[i] = 0.f;
+            }
+        }
+        __syncthreads();
+        *reinterpret_cast<float4*>(&zs[lp][lc]) = make_float4(zv[0], zv[1], zv[2], zv[3]);
+        *reinterpret_cast<float4*>(&zs[lp][lc + 4]) = make_float4(zv[4], zv[5], zv[6], zv[7]);
+        *reinterpret_cast<float4*>(&xs[lp][lc]) = make_float4(xv[0], xv[1], xv[2], xv[3]);
+        *reinterpret_cast<float4*>(&xs[lp][lc + 4]) = make_float4(xv[4], xv[5], xv[6], xv[7]);
+        __syncthreads();
+#pragma unroll 8
+        for (int q = 0; q < 32; ++q) {
+            const float4 a = *reinterpret_cast<const float4*>(&zs[q][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&xs[q][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+                bsum[i] += av[i];
+            }
+        }
+    }
+    const int taps = P.kh * P.kw;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int co = co0 + ty * 4 + i;
+        if (co >= P.cout) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int ci = c0 + tx * 4 + j;
+            if (ci < P.seg_c[s])
+                atomicAdd(P.dw + (((size_t)g * P.cout + co) * P.cin_total + P.seg_off[s] + ci) * taps + tap, acc[i][j]);
+        }
+        if (P.db && tx == 0 && cib == 0 && tap == taps / 2) atomicAdd(P.db + (size_t)g * P.cout + co, bsum[i]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// flow_warp backward.  C/8 (bf16) or C/4 (fp32) threads per pixel as in the forward kernel; dx is an fp32
+// buffer (zeroed by the caller) updated with atomics; dflow gets the channel-reduced tap derivative.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void sample_pos_b(float px, float py, int w, int h, float& ix, float& iy) {
+    float nx = 2.0f * px / (float)max(w - 1, 1) - 1.0f;
+    float ny = 2.0f * py / (float)max(h - 1, 1) - 1.0f;
+    ix = (nx + 1.0f) / 2.0f * (float)(w - 1);
+    iy = (ny + 1.0f) / 2.0f * (float)(h - 1);
+}
+
+template <typename T, int TPP>
+__global__ void __launch_bounds__(256) flow_warp_bwd_kernel(const T* __restrict__ x, const float2* __restrict__ flow,
+                                                            const T* __restrict__ dout, float* __restrict__ dx,
+                                                            float2* __restrict__ dflow, int n, int h, int w, int border) {
+    constexpr int VEC = 16 / sizeof(T);
+    constexpr int C = TPP * VEC;
+    const int hw = h * w;
+    const long long total = (long long)n * hw * TPP;
+    const long long total_up = (total + 31) / 32 * 32;          // whole warps iterate together (shuffles below)
+    for (long long i0 = (long long)blockIdx.x * 256 + threadIdx.x; i0 < total_up; i0 += (long long)gridDim.x * 256) {
+        const bool live = i0 < total;
+        const long long i = live ? i0 : total - 1;              // dead lanes shadow the last item, write nothing
+        const int part = (int)(i % TPP);
+        const long long pix = i / TPP;
+        const int img = (int)(pix / hw), r = (int)(pix - (long long)img * hw);
+        const int yy = r / w, xx = r - yy * w;
+        const float2 f = __ldg(flow + pix);
+        float ix, iy;
+        sample_pos_b((float)xx + f.x, (float)yy + f.y, w, h, ix, iy);
+        float gmx = 1.f, gmy = 1.f;                    // derivative of the border clamp
+        if (border) {
+            if (ix < 0.f || ix > (float)(w - 1)) gmx = 0.f;
+            if (iy < 0.f || iy > (float)(h - 1)) gmy = 0.f;
+            ix = fminf(fmaxf(ix, 0.f), (float)(w - 1));
+            iy = fminf(fmaxf(iy, 0.f), (float)(h - 1));
+        }
+        float fx = floorf(ix), fy = floorf(iy);
+        const float wx1 = ix - fx, wy1 = iy - fy, wx0 = 1.f - wx1, wy0 = 1.f - wy1;
+        fx = fminf(fmaxf(fx, -2.f), (float)w);
+        fy = fminf(fmaxf(fy, -2.f), (float)h);
+        const int x0 = (int)fx, y0 = (int)fy;
+        float go[VEC];
+        {
+            float tmp[8];
+            if (VEC == 8) {
+                Ld8<T>::load(dout + pix * C + part * VEC, tmp);
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) go[j] = tmp[j];
+            } else {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(dout + pix * C + part * VEC));
+                go[0] = q.x; go[1] = q.y; go[2] = q.z; go[3] = q.w;
+            }
+        }
+        float gx = 0.f, gy = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int xi = x0 + (k & 1), yi = y0 + (k >> 1);
+            if (xi < 0 || xi >= w || yi < 0 || yi >= h) continue;
+            const float wgt = ((k & 1) ? wx1 : wx0) * ((k >> 1) ? wy1 : wy0);
+            const float dwx = ((k & 1) ? 1.f : -1.f) * ((k >> 1) ? wy1 : wy0);   // d wgt / d ix
+            const float dwy = ((k >> 1) ? 1.f : -1.f) * ((k & 1) ? wx1 : wx0);   // d wgt / d iy
+            const long long tp = ((long long)img * hw + (long long)yi * w + xi) * C + part * VEC;
+            float xv[VEC];
+            if (dflow) {
+                if (VEC == 8) {
+                    float tmp[8];
+                    Ld8<T>::load(x + tp, tmp);
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) xv[j] = tmp[j];
+                } else {
+                    const float4 q = __ldg(reinterpret_cast<const float4*>(x + tp));
+                    xv[0] = q.x; xv[1] = q.y; xv[2] = q.z; xv[3] = q.w;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                if (dx && live) atomicAdd(dx + tp + j, go[j] * wgt);
+                if (dflow) {
+                    gx = fmaf(go[j] * xv[j], dwx, gx);
+                    gy = fmaf(go[j] * xv[j], dwy, gy);
+                }
+            }
+        }
+        if (dflow) {
+            // reduce over the TPP lanes of this pixel (TPP is a power of two <= 32, lanes are consecutive)
+#pragma unroll
+            for (int o = TPP / 2; o > 0; o >>= 1) {
+                gx += __shfl_xor_sync(0xffffffffu, gx, o);
+                gy += __shfl_xor_sync(0xffffffffu, gy, o);
+            }
+            if (part == 0 && live) dflow[pix] = make_float2(gx * gmx, gy * gmy);
+        }
+    }
+}
+
+template <typename T>
+static int launch_warp_bwd(const T* x, const float2* flow, const T* dout, float* dx, float2* dflow, int n, int h, int w, int c,
+                           int border, cudaStream_t s) {
+    constexpr int VEC = 16 / sizeof(T);
+    const int tpp = c / VEC;
+    const long long total = (long long)n * h * w * tpp;
+    long long b = (total + 255) / 256;
+    // whole warps must stay inside the loop together for the shuffles: total is a multiple of tpp and
+    // 256 % tpp == 0, and a grid-stride of gridDim*256 keeps a pixel's lanes in one warp
+    if (b > 148 * 16) b = 148 * 16;
+    const int blocks = (int)b;
+    switch (tpp) {
+        case 1: flow_warp_bwd_kernel<T, 1><<<blocks, 256, 0, s>>>(x, flow, dout, dx, dflow, n, h, w, border); break;
+        case 2: flow_warp_bwd_kernel<T, 2><<<blocks, 256, 0, s>>>(x, flow, dout, dx, dflow, n, h, w, border); break;
+        case 4: flow_warp_bwd_kernel<T, 4><<<blocks, 256, 0, s>>>(x, flow, dout, dx, dflow, n, h, w, border); break;
+        case 8: flow_warp_bwd_kernel<T, 8><<<blocks, 256, 0, s>>>(x, flow, dout, dx, dflow, n, h, w, border); break;
+        case 16: flow_warp_bwd_kernel<T, 16><<<blocks, 256, 0, s>>>(x, flow, dout, dx, dflow, n, h, w, border); break;
+        case 32: flow_warp_bwd_kernel<T, 32><<<blocks, 256, 0, s>>>(x, flow, dout, dx, dflow, n, h, w, border); break;
+        default:
+            set_error("flow_warp_bwd: %d channels is not %d * a power of two <= 32", c, VEC);
+            return VSRB_E_ARG;
+    }
+    return VSRB_OK;
+}
+
+}  // namespace vsrb
+
+using namespace vsrb;
+
+extern "C" {
+
+int vsrb_conv2d_wgrad(const vsrb_conv_geom* g, const void* const* in, const int32_t* in_c, const void* dz, int32_t dz_c,
+                      int32_t batch, int32_t h, int32_t w, int32_t imgs_per_group, int32_t cin_total, float* dw, float* db,
+                      void* stream) {
+    VSRB_CHECK_ARG(g && in && in_c && dz && dw, "wgrad: null argument");
+    VSRB_CHECK_ARG(g->n_seg == 1 || g->n_seg == 2, "wgrad: n_seg must be 1 or 2");
+    VSRB_CHECK_ARG(!g->pixshuf && !g->transpose, "wgrad: pass the plain forward geometry (un-shuffle the gradient first)");
+    VSRB_CHECK_ARG(imgs_per_group >= 1 && imgs_per_group * g->groups == batch, "wgrad: batch/groups mismatch");
+    VSRB_CHECK_ARG((long long)imgs_per_group * h * w < (1LL << 31), "wgrad: too many pixels per group");
+    const int vec = g->dtype == VSRB_BF16 ? 8 : 8;
+    VSRB_CHECK_ARG(dz_c % vec == 0, "wgrad: dz channel stride must be a multiple of 8");
+    WgradParams P;
+    memset(&P, 0, sizeof(P));
+    P.n_seg = g->n_seg;
+    P.n_ci_blk = 0;
+    for (int s = 0; s < g->n_seg; ++s) {
+        VSRB_CHECK_ARG(in[s] && in_c[s] % 8 == 0 && in_c[s] >= g->seg_c[s], "wgrad: bad input segment %d", s);
+        VSRB_CHECK_ARG(g->seg_off[s] + g->seg_c[s] <= cin_total, "wgrad: segment %d exceeds cin_total", s);
+        P.in[s] = in[s]; P.in_c[s] = in_c[s]; P.seg_c[s] = g->seg_c[s]; P.seg_off[s] = g->seg_off[s];
+        for (int c0 = 0; c0 < g->seg_c[s]; c0 += 64) {
+            VSRB_CHECK_ARG(P.n_ci_blk < 8, "wgrad: more than 512 input channels");
+            P.ci_blk_seg[P.n_ci_blk] = s;
+            P.ci_blk_c0[P.n_ci_blk] = c0;
+            ++P.n_ci_blk;
+        }
+    }
+    P.dz = dz; P.dz_c = dz_c;
+    P.kh = g->kh; P.kw = g->kw; P.H = h; P.W = w; P.imgs_per_group = imgs_per_group; P.groups = g->groups;
+    P.cout = g->cout; P.cin_total = cin_total;
+    P.n_co_blk = ceil_div(g->cout, 64);
+    P.dw = dw; P.db = db;
+    const long long pix_g = (long long)imgs_per_group * h * w;
+    // enough CTAs for ~8 waves of the 148 SMs, at least 1024 pixels each
+    const long long other = (long long)g->kh * g->kw * P.n_co_blk * P.n_ci_blk * g->groups;
+    long long chunks = (148LL * 8 + other - 1) / other;
+    long long per = (pix_g + chunks - 1) / chunks;
+    if (per < 1024) per = 1024;
+    per = (per + 31) / 32 * 32;
+    P.pix_per_cta = (int)per;
+    dim3 grid((unsigned)((pix_g + per - 1) / per), g->kh * g->kw, P.n_co_blk * P.n_ci_blk * g->groups);
+    if (g->dtype == VSRB_BF16) conv_wgrad_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(P);
+    else conv_wgrad_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(P);
+    VSRB_LAUNCH_CHECK();
+    return VSRB_OK;
+}
+
+int vsrb_flow_warp_bwd(const void* x, const float* flow, const void* dout, float* dx, float* dflow, int32_t n, int32_t h,
+                       int32_t w, int32_t c, int32_t dtype, int32_t padding_mode, void* stream) {
+    VSRB_CHECK_ARG(flow && dout && (dx || dflow) && n >= 1 && h >= 1 && w >= 1, "flow_warp_bwd: bad arguments");
+    VSRB_CHECK_ARG(!dflow || x, "flow_warp_bwd: the flow gradient needs the forward input x");
+    VSRB_CHECK_ARG((long long)n * h * w * c < (1LL << 40), "flow_warp_bwd: tensor too large");
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc;
+    if (dtype == VSRB_BF16) {
+        VSRB_CHECK_ARG(c % 8 == 0, "flow_warp_bwd: bf16 needs c %% 8 == 0");
+        rc = launch_warp_bwd<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const float2*>(flow),
+                                            reinterpret_cast<const __nv_bfloat16*>(dout), dx, reinterpret_cast<float2*>(dflow), n, h,
+                                            w, c, padding_mode, s);
+    } else {
+        VSRB_CHECK_ARG(c % 4 == 0, "flow_warp_bwd: fp32 needs c %% 4 == 0");
+        rc = launch_warp_bwd<float>(reinterpret_cast<const float*>(x), reinterpret_cast<const float2*>(flow),
+                                    reinterpret_cast<const float*>(dout), dx, reinterpret_cast<float2*>(dflow), n, h, w, c,
+                                    padding_mode, s);
+    }
+    if (rc != VSRB_OK) return rc;
+    VSRB_LAUNCH_CHECK();
+    return VSRB_OK;
+}
+
+}  // extern "C"

@@ -101,11 +101,9 @@ def _check_input(x: torch.Tensor, what: str) -> torch.Tensor:
     return x
 
 
-def _no_training(mod: torch.nn.Module) -> None:
-    if torch.is_grad_enabled() and mod.training and any(p.requires_grad for p in mod.parameters()):
-        raise NotImplementedError(
-            "vsrlab_b200: the backward (dgrad/wgrad/warp-grad) kernels are not built yet; call the model under "
-            "torch.no_grad() or in eval() mode.")
+def _wants_grad(mod: torch.nn.Module) -> bool:
+    """True when the call must be recorded for autograd (training step): grad mode on and something to train."""
+    return torch.is_grad_enabled() and any(p.requires_grad for p in mod.parameters())
 
 
 def _act_c(c: int, dt: int) -> int:
@@ -446,15 +444,20 @@ def _basicvsr_run(bv, lrs: torch.Tensor, dt: int, x_nhwc: Optional[torch.Tensor]
 
 
 def basicvsr_forward(bv, lrs: torch.Tensor) -> torch.Tensor:
-    _no_training(bv)
+    if _wants_grad(bv):
+        from . import autograd as AG
+        ops.require_cuda(lrs, "lrs")
+        return AG.basicvsr(bv, lrs.float())
     lrs = _check_input(lrs, "lrs").contiguous()
     return _basicvsr_run(bv, lrs, current_dtype())
 
 
 def realbasicvsr_forward(model, lr: torch.Tensor):
     """(sr, lq) = RealBasicVSR.forward; `lq` is `lr` itself, refined in place (realbasicvsr.py:11-15, 26-29)."""
-    _no_training(model)
     ops.require_cuda(lr, "lr")
+    if _wants_grad(model):
+        from . import autograd as AG
+        return AG.realbasicvsr(model, lr)
     if lr.dtype != torch.float32:
         raise VsrbError("RealBasicVSR refines its input in place and needs an fp32 tensor (reference realbasicvsr.py:29)")
     if not lr.is_contiguous():

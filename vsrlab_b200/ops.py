@@ -172,3 +172,50 @@ def device_info() -> Tuple[int, int, int]:
     a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
     L.check(L.load().vsrb_device_info(C.byref(a), C.byref(b), C.byref(c)), "vsrb_device_info")
     return a.value, b.value, c.value
+
+
+# --------------------------------------------------------------------------------------
+# training kernels
+# --------------------------------------------------------------------------------------
+class PackedConvT(PackedConv):
+    """Weights packed for the INPUT-GRADIENT convolution (transposed + flipped, geom.transpose = 1)."""
+
+    def __init__(self, conv: torch.nn.Conv2d, dtype: int):
+        lib = L.load()
+        w0 = conv.weight
+        require_cuda(w0, "conv weight")
+        cout, cin, kh, kw = w0.shape
+        g = L.ConvGeom()
+        g.kh, g.kw, g.n_seg = kh, kw, 1
+        g.seg_off[0], g.seg_c[0] = 0, cout
+        g.cout, g.pixshuf, g.groups, g.dtype, g.transpose = cin, 0, 1, dtype, 1
+        self.geom = g
+        self.cout, self.cin, self.kh, self.kw = cin, cout, kh, kw      # of the gradient conv
+        self.cout_pad = (cin + 15) // 16 * 16
+        self.dtype = dtype
+        self.stamp = self.stamp_of([conv])
+        self.uses = 0
+        w = w0.detach().to(torch.float32).contiguous()
+        nbytes = lib.vsrb_packed_weight_bytes(C.byref(g))
+        if nbytes == 0:
+            raise L.VsrbError(f"unsupported conv geometry: {lib.vsrb_last_error().decode()}")
+        self.buf = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+        L.check(lib.vsrb_pack_conv_weight(C.byref(g), _p(w), cout, None, _p(self.buf), _stream()), "vsrb_pack_conv_weight")
+
+
+def conv2d_wgrad(geom: "L.ConvGeom", ins: Sequence[torch.Tensor], in_c: Sequence[int], dz: torch.Tensor, dz_c: int, batch: int,
+                 h: int, w: int, cin_total: int, dw: torch.Tensor, db: Optional[torch.Tensor]) -> None:
+    """dw (fp32 OIHW) += sum_pixels dz (x) x ;  db += sum_pixels dz.  `geom` = forward geometry without pixshuf."""
+    n = len(ins)
+    ptrs = (C.c_void_p * 2)(*[t.data_ptr() for t in ins], *([None] * (2 - n)))
+    cs = (C.c_int32 * 2)(*in_c, *([0] * (2 - n)))
+    flops = 2.0 * batch * h * w * geom.cout * sum(geom.seg_c[i] for i in range(geom.n_seg)) * geom.kh * geom.kw
+    with _Timed("conv_wgrad", flops):
+        L.check(L.load().vsrb_conv2d_wgrad(C.byref(geom), ptrs, cs, _p(dz), dz_c, batch, h, w, batch // geom.groups, cin_total,
+                                           _p(dw), _p(db), _stream()), "vsrb_conv2d_wgrad")
+
+
+def flow_warp_bwd(x, flow, dout, dx, dflow, n: int, h: int, w: int, c: int, dtype: int, padding: int = PAD_ZEROS) -> None:
+    with _Timed("flow_warp_bwd", float(n) * h * w * (3 * c * ESIZE[dtype] + 4 * c * 4)):
+        L.check(L.load().vsrb_flow_warp_bwd(_p(x), _p(flow), _p(dout), _p(dx), _p(dflow), n, h, w, c, dtype, padding, _stream()),
+                "vsrb_flow_warp_bwd")
