@@ -246,3 +246,27 @@ def test_full_size_properties(dev):
     torch.cuda.synchronize()
     assert torch.equal(ya.float() * 2, yb.float())            # exact: scaling by 2 commutes with every rounding
     assert ops.debug_status() == 0
+
+
+@pytest.mark.parametrize("mid,upscale,blocks", [(32, 4, 1), (64, 2, 1), (48, 4, 2)])
+def test_other_widths_and_scales(dev, mid, upscale, blocks):
+    """Constructor arguments other than the benchmarked ones (mid_channels, upscale) go through the generic
+    kernel paths; checked against the CPU oracle on the module's own random-init weights."""
+    from vsrlab.vsr.models.RealBasicVSR.realbasicvsr import RealBasicVSR
+    from vsrlab_b200 import functional as VF, ops
+    torch.manual_seed(mid + upscale)
+    net = RealBasicVSR(cleaning_blocks=blocks, mid_channels=mid, upscale=upscale, res_blocks=blocks, pretrained_flow=False,
+                       train_flow=False).eval()
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    x = torch.rand(2, 3, 3, 24, 40, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        sr_ref, lq_ref = O.realbasicvsr(x.clone(), sd)
+    net = net.to(dev)
+    with torch.no_grad(), VF.precision("fp32"):
+        sr, lq = net(x.clone().to(dev))
+    assert sr.shape == sr_ref.shape
+    assert (sr.cpu() - sr_ref).abs().max().item() <= 1e-4 and (lq.cpu() - lq_ref).abs().max().item() <= 1e-4
+    with torch.no_grad(), VF.precision("bf16"):
+        sr16, _ = net(x.clone().to(dev))
+    assert O.psnr(sr16.cpu(), sr_ref) > 40.0
+    assert ops.debug_status() == 0

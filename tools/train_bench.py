@@ -1,0 +1,107 @@
+"""BASELINE cfg4: Real-BasicVSR (experiment=basic, 5/5 blocks) training step on 15-frame 64x64 LR patches,
+batch 8 per GPU, Adam, Charbonnier losses as reference train.py / core/utils.py:235-280, DDP over NCCL when
+launched with torchrun.  Prints one JSON line (rank 0)."""
+import argparse
+import json
+import os
+import sys
+import time
+from pathlib import Path
+
+import torch
+import torch.nn.functional as F
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+
+
+def charbonnier(a, b):
+    return torch.sqrt((a - b) ** 2 + 1e-9).mean()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--frames", type=int, default=15)
+    ap.add_argument("--blocks", type=int, default=5)
+    ap.add_argument("--train-flow", type=int, default=1)
+    a = ap.parse_args()
+    import torch.distributed as dist
+    from vsrlab.vsr.models.RealBasicVSR.realbasicvsr import RealBasicVSR
+    from vsrlab_b200 import ops
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(0)
+    model = RealBasicVSR(cleaning_blocks=a.blocks, mid_channels=64, upscale=4, res_blocks=a.blocks, pretrained_flow=False,
+                         train_flow=bool(a.train_flow)).to(dev).train()
+    net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local]) if world > 1 else model
+    opt = torch.optim.Adam(net.parameters(), lr=1e-4, betas=(0.9, 0.99))
+    g = torch.Generator().manual_seed(rank)
+    lr = torch.rand(a.batch, a.frames, 3, 64, 64, generator=g).to(dev)
+    hr = torch.rand(a.batch, a.frames, 3, 256, 256, generator=g).to(dev)
+
+    def step():
+        x = lr.clone()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            sr, lq = net(x)
+        loss = charbonnier(sr, hr) + charbonnier(lq, F.interpolate(hr.flatten(0, 1), size=(64, 64), mode="bilinear").view_as(lq))
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(net.parameters(), 1.0)
+        opt.step()
+        return loss
+
+    losses = []
+    for _ in range(a.warmup):
+        losses.append(step().item())
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        losses.append(step())
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / a.steps
+    ops.PROFILE = []
+    step()
+    torch.cuda.synchronize()
+    prof, ops.PROFILE = ops.PROFILE, None
+    fam = {}
+    for kind, ev0, ev1, work, tag in prof:
+        d = fam.setdefault(kind, [0.0, 0.0, 0])
+        d[0] += ev0.elapsed_time(ev1)
+        d[1] += work
+        d[2] += 1
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        # replicas must hold identical weights after the all-reduced steps
+        w0 = torch.cat([p.detach().flatten() for p in model.parameters()])
+        ref = w0.clone()
+        dist.broadcast(ref, 0)
+        same = bool(torch.equal(w0, ref))
+    else:
+        same = True
+    if rank == 0:
+        print(json.dumps({
+            "workload": f"cfg4 training step: batch {a.batch}/GPU x {a.frames} frames 64x64, {a.blocks}/{a.blocks} blocks, train_flow={a.train_flow}",
+            "n_gpus": world, "ms_per_step": t.item(), "clips_per_sec": world * a.batch / (t.item() * 1e-3),
+            "loss_first": float(losses[0]), "loss_last": float(losses[-1]), "replicas_identical": same,
+            "kernels_ms": {k: {"ms": round(v[0], 2), "launches": v[2], "tflops_or_gbs": round(v[1] / max(v[0], 1e-9) / 1e9, 1)}
+                           for k, v in fam.items()},
+        }), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

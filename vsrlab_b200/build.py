@@ -9,7 +9,7 @@ from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
-SOURCES = ["api.cu", "conv_tc.cu", "conv_f32.cu", "warp.cu", "train.cu"]
+SOURCES = ["api.cu", "conv_tc.cu", "conv_f32.cu", "warp.cu", "train.cu", "wgrad_tc.cu"]
 OUT = CSRC / "libvsrb200.so"
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "-shared"]
@@ -19,7 +19,7 @@ def needs_build() -> bool:
     if not OUT.exists():
         return True
     t = OUT.stat().st_mtime
-    deps = [CSRC / s for s in SOURCES] + [CSRC / "common.cuh", HERE.parent / "include" / "vsrb200.h"]
+    deps = [CSRC / s for s in SOURCES] + [CSRC / "common.cuh", CSRC / "tc_ptx.cuh", HERE.parent / "include" / "vsrb200.h"]
     return any(d.stat().st_mtime > t for d in deps)
 
 

@@ -7,6 +7,8 @@
 //  * flow_warp backward         = flow_warp_bwd_kernel: scatter of the output gradient through the four bilinear
 //    taps (grad wrt the warped features) and the derivative of the taps wrt the sample position (grad wrt the
 //    flow, needed when train_flow=True) - reference: GridSampler2DBackward0 behind spynet.py:95-106.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace vsrb {
@@ -27,9 +29,11 @@ template <> struct Ld8<float> {
 };
 
 // ---------------------------------------------------------------------------------------
-// weight gradient.  One CTA = one filter tap x one 64(co) x 64(ci) tile x a run of pixels; fp32 accumulate in
-// registers (4x4 per thread), bf16/fp32 operands staged through shared memory 32 pixels at a time, result
-// added to the OIHW fp32 gradient with atomics (several pixel runs and the groups' images share it).
+// weight gradient (FFMA fallback for the shapes the tensor-core kernel does not take: 7x7, 1x1, 3-channel
+// segments).  One CTA = one filter ROW ky x one 64(co) x 64(ci) tile x a run of 32-pixel row chunks.  Per chunk it
+// stages dz [32 px][64 co] and ONE extended activation strip [32 + kw - 1 px][64 ci] of image row y + ky - pad, and
+// updates the kw taps of the row from it (kw x 4x4 fp32 accumulators per thread), so dz is read kh times instead
+// of kh*kw times.  Results are added to the OIHW fp32 gradient with atomics.
 // ---------------------------------------------------------------------------------------
 struct WgradParams {
     const void* in[2];
@@ -39,21 +43,19 @@ struct WgradParams {
     int dz_c;
     int kh, kw, H, W, imgs_per_group, groups;
     int cout, cin_total;
-    int pix_per_cta;          // pixels of one group handled by one CTA
-    int n_co_blk, n_ci_blk;   // 64-wide blocks
+    int chunks_per_row, units_g, units_per_cta;   // unit = (image of the group, row y, 32-pixel chunk)
+    int n_co_blk, n_ci_blk;                       // 64-wide blocks
     int ci_blk_seg[8], ci_blk_c0[8];
     float* dw;
-    float* db;
 };
 
-template <typename T>
+template <typename T, int KW>
 __global__ void __launch_bounds__(256) conv_wgrad_kernel(WgradParams P) {
     __shared__ __align__(16) float zs[32][64];
-    __shared__ __align__(16) float xs[32][64];
+    __shared__ __align__(16) float xs[32 + KW - 1][64];
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;             // 4 ci per tx, 4 co per ty
-    const int tap = blockIdx.y;
-    const int ky = tap / P.kw, kx = tap - ky * P.kw;
+    const int ky = blockIdx.y;
     int z = blockIdx.z;
     const int cib = z % P.n_ci_blk; z /= P.n_ci_blk;
     const int cob = z % P.n_co_blk;
@@ -61,76 +63,84 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(WgradParams P) {
     const int s = P.ci_blk_seg[cib], c0 = P.ci_blk_c0[cib];
     const int co0 = cob * 64;
     const int hw = P.H * P.W;
-    const int pix_g = P.imgs_per_group * hw;            // pixels of this group
-    const int p_begin = blockIdx.x * P.pix_per_cta;
-    const int p_end = min(p_begin + P.pix_per_cta, pix_g);
+    const int u_begin = blockIdx.x * P.units_per_cta;
+    const int u_end = min(u_begin + P.units_per_cta, P.units_g);
     const T* zin = reinterpret_cast<const T*>(P.dz);
     const T* xin = reinterpret_cast<const T*>(P.in[s]);
-    const int lp = tid >> 3, lc = (tid & 7) * 8;        // loader: pixel lp of the 32, channels lc..lc+8
-    const int dy = ky - P.kh / 2, dx = kx - P.kw / 2;
+    const int lp = tid >> 3, lc = (tid & 7) * 8;        // loader: pixel lp of the chunk, channels lc..lc+8
+    const int dy = ky - P.kh / 2, pad = KW / 2;
 
-    float acc[4][4];
+    float acc[KW][4][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int k = 0; k < KW; ++k)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[k][i][j] = 0.f;
 
-    for (int p0 = p_begin; p0 < p_end; p0 += 32) {
-        const int p = p0 + lp;
-        float zv[8], xv[8];
+    for (int u = u_begin; u < u_end; ++u) {
+        const int xc = u % P.chunks_per_row;
+        const int rowi = u / P.chunks_per_row;
+        const int y = rowi % P.H;
+        const long long img = (long long)g * P.imgs_per_group + rowi / P.H;
+        const int x0 = xc * 32;
+        float zv[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { zv[i] = 0.f; xv[i] = 0.f; }
-        if (p < p_end) {
-            const int li = p / hw, r = p - li * hw;
-            const int y = r / P.W, x = r - y * P.W;
-            const long long img = (long long)g * P.imgs_per_group + li;
-            if (co0 + lc < P.dz_c) {
-                Ld8<T>::load(zin + (img * hw + r) * P.dz_c + co0 + lc, zv);
+        for (int i = 0; i < 8; ++i) zv[i] = 0.f;
+        if (x0 + lp < P.W && co0 + lc < P.dz_c) {
+            Ld8<T>::load(zin + (img * hw + (long long)y * P.W + x0 + lp) * P.dz_c + co0 + lc, zv);
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    if (co0 + lc + i >= P.cout) zv[i] = 0.f;
-            }
-            const int yy = y + dy, xx = x + dx;
+            for (int i = 0; i < 8; ++i)
+                if (co0 + lc + i >= P.cout) zv[i] = 0.f;
+        }
+        __syncthreads();
+        *reinterpret_cast<float4*>(&zs[lp][lc]) = make_float4(zv[0], zv[1], zv[2], zv[3]);
+        *reinterpret_cast<float4*>(&zs[lp][lc + 4]) = make_float4(zv[4], zv[5], zv[6], zv[7]);
+        const int yy = y + dy;
+        for (int e = lp; e < 32 + KW - 1; e += 32) {     // extended strip: image columns x0 - pad + e
+            float xv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) xv[i] = 0.f;
+            const int xx = x0 - pad + e;
             if (yy >= 0 && yy < P.H && xx >= 0 && xx < P.W && c0 + lc < P.in_c[s]) {
                 Ld8<T>::load(xin + (img * hw + (long long)yy * P.W + xx) * P.in_c[s] + c0 + lc, xv);
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
                     if (c0 + lc + i >= P.seg_c[s]) xv[i] = 0.f;
             }
+            *reinterpret_cast<float4*>(&xs[e][lc]) = make_float4(xv[0], xv[1], xv[2], xv[3]);
+            *reinterpret_cast<float4*>(&xs[e][lc + 4]) = make_float4(xv[4], xv[5], xv[6], xv[7]);
         }
         __syncthreads();
-        *reinterpret_cast<float4*>(&zs[lp][lc]) = make_float4(zv[0], zv[1], zv[2], zv[3]);
-        *reinterpret_cast<float4*>(&zs[lp][lc + 4]) = make_float4(zv[4], zv[5], zv[6], zv[7]);
-        *reinterpret_cast<float4*>(&xs[lp][lc]) = make_float4(xv[0], xv[1], xv[2], xv[3]);
-        *reinterpret_cast<float4*>(&xs[lp][lc + 4]) = make_float4(xv[4], xv[5], xv[6], xv[7]);
-        __syncthreads();
-#pragma unroll 8
+#pragma unroll 4
         for (int q = 0; q < 32; ++q) {
             const float4 a = *reinterpret_cast<const float4*>(&zs[q][ty * 4]);
-            const float4 b = *reinterpret_cast<const float4*>(&xs[q][tx * 4]);
-            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+            const float av[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int k = 0; k < KW; ++k) {
+                const float4 b = *reinterpret_cast<const float4*>(&xs[q + k][tx * 4]);
+                const float bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-                bsum[i] += av[i];
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[k][i][j] = fmaf(av[i], bv[j], acc[k][i][j]);
             }
         }
     }
-    const int taps = P.kh * P.kw;
+    const int taps = P.kh * KW;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int co = co0 + ty * 4 + i;
-        if (co >= P.cout) continue;
+    for (int k = 0; k < KW; ++k)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int ci = c0 + tx * 4 + j;
-            if (ci < P.seg_c[s])
-                atomicAdd(P.dw + (((size_t)g * P.cout + co) * P.cin_total + P.seg_off[s] + ci) * taps + tap, acc[i][j]);
+        for (int i = 0; i < 4; ++i) {
+            const int co = co0 + ty * 4 + i;
+            if (co >= P.cout) continue;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int ci = c0 + tx * 4 + j;
+                if (ci < P.seg_c[s])
+                    atomicAdd(P.dw + (((size_t)g * P.cout + co) * P.cin_total + P.seg_off[s] + ci) * taps + ky * KW + k, acc[k][i][j]);
+            }
         }
-        if (P.db && tx == 0 && cib == 0 && tap == taps / 2) atomicAdd(P.db + (size_t)g * P.cout + co, bsum[i]);
-    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -147,17 +157,19 @@ __device__ __forceinline__ void sample_pos_b(float px, float py, int w, int h, f
 template <typename T, int TPP>
 __global__ void __launch_bounds__(256) flow_warp_bwd_kernel(const T* __restrict__ x, const float2* __restrict__ flow,
                                                             const T* __restrict__ dout, float* __restrict__ dx,
-                                                            float2* __restrict__ dflow, int n, int h, int w, int border) {
+                                                            float2* __restrict__ dflow, int n, int h, int w, int border,
+                                                            int tpp_rt) {
     constexpr int VEC = 16 / sizeof(T);
-    constexpr int C = TPP * VEC;
+    const int tpp = TPP > 0 ? TPP : tpp_rt;            // TPP == 0: any channel count; dflow must then be zeroed (atomics)
+    const int C = tpp * VEC;
     const int hw = h * w;
-    const long long total = (long long)n * hw * TPP;
+    const long long total = (long long)n * hw * tpp;
     const long long total_up = (total + 31) / 32 * 32;          // whole warps iterate together (shuffles below)
     for (long long i0 = (long long)blockIdx.x * 256 + threadIdx.x; i0 < total_up; i0 += (long long)gridDim.x * 256) {
         const bool live = i0 < total;
         const long long i = live ? i0 : total - 1;              // dead lanes shadow the last item, write nothing
-        const int part = (int)(i % TPP);
-        const long long pix = i / TPP;
+        const int part = (int)(i % tpp);
+        const long long pix = i / tpp;
         const int img = (int)(pix / hw), r = (int)(pix - (long long)img * hw);
         const int yy = r / w, xx = r - yy * w;
         const float2 f = __ldg(flow + pix);
@@ -218,13 +230,18 @@ __global__ void __launch_bounds__(256) flow_warp_bwd_kernel(const T* __restrict_
             }
         }
         if (dflow) {
-            // reduce over the TPP lanes of this pixel (TPP is a power of two <= 32, lanes are consecutive)
+            if (TPP > 0) {
+                // reduce over the TPP lanes of this pixel (TPP is a power of two <= 32, lanes are consecutive)
 #pragma unroll
-            for (int o = TPP / 2; o > 0; o >>= 1) {
-                gx += __shfl_xor_sync(0xffffffffu, gx, o);
-                gy += __shfl_xor_sync(0xffffffffu, gy, o);
+                for (int o = TPP / 2; o > 0; o >>= 1) {
+                    gx += __shfl_xor_sync(0xffffffffu, gx, o);
+                    gy += __shfl_xor_sync(0xffffffffu, gy, o);
+                }
+                if (part == 0 && live) dflow[pix] = make_float2(gx * gmx, gy * gmy);
+            } else if (live) {
+                atomicAdd(&dflow[pix].x, gx * gmx);
+                atomicAdd(&dflow[pix].y, gy * gmy);
             }
-            if (part == 0 && live) dflow[pix] = make_float2(gx * gmx, gy * gmy);
         }
     }
 }
@@ -241,18 +258,23 @@ static int launch_warp_bwd(const T* x, const float2* flow, const T* dout, float*
     if (b > 148 * 16) b = 148 * 16;
     const int blocks = (int)b;
     switch (tpp) {
-        case 1: flow_warp_bwd_kernel<T, 1><<<blocks, 256, 0, s>>>(x, flow, dout, dx, dflow, n, h, w, border); break;
-        case 2: flow_warp_bwd_kernel<T, 2><<<blocks, 256, 0, s>>>(x, flow, dout, dx, dflow, n, h, w, border); break;
-        case 4: flow_warp_bwd_kernel<T, 4><<<blocks, 256, 0, s>>>(x, flow, dout, dx, dflow, n, h, w, border); break;
-        case 8: flow_warp_bwd_kernel<T, 8><<<blocks, 256, 0, s>>>(x, flow, dout, dx, dflow, n, h, w, border); break;
-        case 16: flow_warp_bwd_kernel<T, 16><<<blocks, 256, 0, s>>>(x, flow, dout, dx, dflow, n, h, w, border); break;
-        case 32: flow_warp_bwd_kernel<T, 32><<<blocks, 256, 0, s>>>(x, flow, dout, dx, dflow, n, h, w, border); break;
+        case 1: flow_warp_bwd_kernel<T, 1><<<blocks, 256, 0, s>>>(x, flow, dout, dx, dflow, n, h, w, border, tpp); break;
+        case 2: flow_warp_bwd_kernel<T, 2><<<blocks, 256, 0, s>>>(x, flow, dout, dx, dflow, n, h, w, border, tpp); break;
+        case 4: flow_warp_bwd_kernel<T, 4><<<blocks, 256, 0, s>>>(x, flow, dout, dx, dflow, n, h, w, border, tpp); break;
+        case 8: flow_warp_bwd_kernel<T, 8><<<blocks, 256, 0, s>>>(x, flow, dout, dx, dflow, n, h, w, border, tpp); break;
+        case 16: flow_warp_bwd_kernel<T, 16><<<blocks, 256, 0, s>>>(x, flow, dout, dx, dflow, n, h, w, border, tpp); break;
+        case 32: flow_warp_bwd_kernel<T, 32><<<blocks, 256, 0, s>>>(x, flow, dout, dx, dflow, n, h, w, border, tpp); break;
         default:
-            set_error("flow_warp_bwd: %d channels is not %d * a power of two <= 32", c, VEC);
-            return VSRB_E_ARG;
+            if (dflow) cudaMemsetAsync(dflow, 0, sizeof(float2) * (size_t)n * h * w, s);
+            flow_warp_bwd_kernel<T, 0><<<blocks, 256, 0, s>>>(x, flow, dout, dx, dflow, n, h, w, border, tpp);
+            break;
     }
     return VSRB_OK;
 }
+
+int launch_wgrad_tc(const void* x, int x_c, int c0, int ci_off, const void* dz, int dz_c, int batch, int h, int w, int cout,
+                    int cin_total, float* dw, cudaStream_t stream);
+int launch_bias_grad(const void* dz, int dz_c, long long pixels, int cout, int dtype, float* db, cudaStream_t s);
 
 }  // namespace vsrb
 
@@ -274,10 +296,24 @@ int vsrb_conv2d_wgrad(const vsrb_conv_geom* g, const void* const* in, const int3
     memset(&P, 0, sizeof(P));
     P.n_seg = g->n_seg;
     P.n_ci_blk = 0;
+    // 3x3 layers whose segment has a multiple of 64 channels (the resblock, upsampling and HR convs: > 85 % of
+    // the FLOPs; a cout below 64 is zero-filled by the TMA box) run on the tensor cores; everything else on the
+    // FFMA kernel
+    const bool tc_ok = g->dtype == VSRB_BF16 && g->kh == 3 && g->kw == 3 && g->groups == 1 && dz_c >= g->cout &&
+                       !getenv("VSRB_WGRAD_SIMT");
     for (int s = 0; s < g->n_seg; ++s) {
         VSRB_CHECK_ARG(in[s] && in_c[s] % 8 == 0 && in_c[s] >= g->seg_c[s], "wgrad: bad input segment %d", s);
         VSRB_CHECK_ARG(g->seg_off[s] + g->seg_c[s] <= cin_total, "wgrad: segment %d exceeds cin_total", s);
         P.in[s] = in[s]; P.in_c[s] = in_c[s]; P.seg_c[s] = g->seg_c[s]; P.seg_off[s] = g->seg_off[s];
+        if (tc_ok && g->seg_c[s] % 64 == 0 && (reinterpret_cast<uintptr_t>(in[s]) & 15) == 0 &&
+            (reinterpret_cast<uintptr_t>(dz) & 15) == 0) {
+            for (int c0 = 0; c0 < g->seg_c[s]; c0 += 64) {
+                int rc = launch_wgrad_tc(in[s], in_c[s], c0, g->seg_off[s] + c0, dz, dz_c, batch, h, w, g->cout, cin_total, dw,
+                                         (cudaStream_t)stream);
+                if (rc != VSRB_OK) return rc;
+            }
+            continue;
+        }
         for (int c0 = 0; c0 < g->seg_c[s]; c0 += 64) {
             VSRB_CHECK_ARG(P.n_ci_blk < 8, "wgrad: more than 512 input channels");
             P.ci_blk_seg[P.n_ci_blk] = s;
@@ -285,22 +321,39 @@ int vsrb_conv2d_wgrad(const vsrb_conv_geom* g, const void* const* in, const int3
             ++P.n_ci_blk;
         }
     }
+    if (db) {
+        int rc = launch_bias_grad(dz, dz_c, (long long)batch * h * w, g->cout * g->groups == g->cout ? g->cout : g->cout, g->dtype, db,
+                                  (cudaStream_t)stream);
+        if (rc != VSRB_OK) return rc;
+    }
+    if (P.n_ci_blk == 0) return VSRB_OK;
     P.dz = dz; P.dz_c = dz_c;
     P.kh = g->kh; P.kw = g->kw; P.H = h; P.W = w; P.imgs_per_group = imgs_per_group; P.groups = g->groups;
     P.cout = g->cout; P.cin_total = cin_total;
     P.n_co_blk = ceil_div(g->cout, 64);
-    P.dw = dw; P.db = db;
-    const long long pix_g = (long long)imgs_per_group * h * w;
-    // enough CTAs for ~8 waves of the 148 SMs, at least 1024 pixels each
-    const long long other = (long long)g->kh * g->kw * P.n_co_blk * P.n_ci_blk * g->groups;
-    long long chunks = (148LL * 8 + other - 1) / other;
-    long long per = (pix_g + chunks - 1) / chunks;
-    if (per < 1024) per = 1024;
-    per = (per + 31) / 32 * 32;
-    P.pix_per_cta = (int)per;
-    dim3 grid((unsigned)((pix_g + per - 1) / per), g->kh * g->kw, P.n_co_blk * P.n_ci_blk * g->groups);
-    if (g->dtype == VSRB_BF16) conv_wgrad_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(P);
-    else conv_wgrad_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(P);
+    P.dw = dw;
+    P.chunks_per_row = ceil_div(w, 32);
+    const long long units_g = (long long)imgs_per_group * h * P.chunks_per_row;
+    VSRB_CHECK_ARG(units_g < (1LL << 31), "wgrad: too many pixels per group");
+    P.units_g = (int)units_g;
+    // ~6 waves of the 148 SMs, at least 16 chunks (512 pixels) per CTA to amortise the final atomics
+    const long long other = (long long)g->kh * P.n_co_blk * P.n_ci_blk * g->groups;
+    long long ctas = (148LL * 6 + other - 1) / other;
+    long long per = (units_g + ctas - 1) / ctas;
+    if (per < 16) per = 16;
+    P.units_per_cta = (int)per;
+    dim3 grid((unsigned)((units_g + per - 1) / per), g->kh, P.n_co_blk * P.n_ci_blk * g->groups);
+    cudaStream_t st = (cudaStream_t)stream;
+#define VSRB_WG_LAUNCH(T)                                                        \
+    do {                                                                          \
+        if (g->kw == 1) conv_wgrad_kernel<T, 1><<<grid, 256, 0, st>>>(P);         \
+        else if (g->kw == 3) conv_wgrad_kernel<T, 3><<<grid, 256, 0, st>>>(P);    \
+        else if (g->kw == 5) conv_wgrad_kernel<T, 5><<<grid, 256, 0, st>>>(P);    \
+        else conv_wgrad_kernel<T, 7><<<grid, 256, 0, st>>>(P);                    \
+    } while (0)
+    if (g->dtype == VSRB_BF16) VSRB_WG_LAUNCH(__nv_bfloat16);
+    else VSRB_WG_LAUNCH(float);
+#undef VSRB_WG_LAUNCH
     VSRB_LAUNCH_CHECK();
     return VSRB_OK;
 }

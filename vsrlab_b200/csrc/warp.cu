@@ -84,10 +84,11 @@ struct WarpTap {
 template <typename T, int TPP>
 __global__ void __launch_bounds__(256) flow_warp_kernel(const T* __restrict__ x, long long x_stride,
                                                         const float2* __restrict__ flow, long long f_stride,
-                                                        T* __restrict__ out, int n, int h, int w, int border) {
+                                                        T* __restrict__ out, int n, int h, int w, int border, int tpp_rt) {
     __shared__ WarpTap taps[kWarpPix];
     constexpr int VEC = Vec16<T>::N;
-    constexpr int C = TPP * VEC;
+    const int tpp = TPP > 0 ? TPP : tpp_rt;            // TPP == 0: any channel count (runtime divisions)
+    const int C = tpp * VEC;
     const int hw = h * w;
     const int total = n * hw;                          // launcher guarantees < 2^31
     const int pix0 = blockIdx.x * kWarpPix;
@@ -105,10 +106,10 @@ __global__ void __launch_bounds__(256) flow_warp_kernel(const T* __restrict__ x,
     }
     __syncthreads();
     const int npix = min(kWarpPix, total - pix0);
-    const int work = npix * TPP;
+    const int work = npix * tpp;
 #pragma unroll 2
     for (int i = threadIdx.x; i < work; i += 256) {
-        const int lp = i / TPP, part = i % TPP;          // compile-time power of two: shift / mask
+        const int lp = i / tpp, part = i % tpp;          // compile-time power of two: shift / mask
         const WarpTap wt = taps[lp];
         const T* img = x + wt.base + part * VEC;
         float acc[VEC];
@@ -134,15 +135,13 @@ static int launch_flow_warp(const T* x, long long xs, const float2* flow, long l
     const int tpp = c / VEC;
     const int blocks = (int)(((long long)n * h * w + kWarpPix - 1) / kWarpPix);
     switch (tpp) {
-        case 1: flow_warp_kernel<T, 1><<<blocks, 256, 0, s>>>(x, xs, flow, fs, out, n, h, w, border); break;
-        case 2: flow_warp_kernel<T, 2><<<blocks, 256, 0, s>>>(x, xs, flow, fs, out, n, h, w, border); break;
-        case 4: flow_warp_kernel<T, 4><<<blocks, 256, 0, s>>>(x, xs, flow, fs, out, n, h, w, border); break;
-        case 8: flow_warp_kernel<T, 8><<<blocks, 256, 0, s>>>(x, xs, flow, fs, out, n, h, w, border); break;
-        case 16: flow_warp_kernel<T, 16><<<blocks, 256, 0, s>>>(x, xs, flow, fs, out, n, h, w, border); break;
-        case 32: flow_warp_kernel<T, 32><<<blocks, 256, 0, s>>>(x, xs, flow, fs, out, n, h, w, border); break;
-        default:
-            set_error("flow_warp: %d channels is not %d * a power of two <= 32", c, VEC);
-            return VSRB_E_ARG;
+        case 1: flow_warp_kernel<T, 1><<<blocks, 256, 0, s>>>(x, xs, flow, fs, out, n, h, w, border, tpp); break;
+        case 2: flow_warp_kernel<T, 2><<<blocks, 256, 0, s>>>(x, xs, flow, fs, out, n, h, w, border, tpp); break;
+        case 4: flow_warp_kernel<T, 4><<<blocks, 256, 0, s>>>(x, xs, flow, fs, out, n, h, w, border, tpp); break;
+        case 8: flow_warp_kernel<T, 8><<<blocks, 256, 0, s>>>(x, xs, flow, fs, out, n, h, w, border, tpp); break;
+        case 16: flow_warp_kernel<T, 16><<<blocks, 256, 0, s>>>(x, xs, flow, fs, out, n, h, w, border, tpp); break;
+        case 32: flow_warp_kernel<T, 32><<<blocks, 256, 0, s>>>(x, xs, flow, fs, out, n, h, w, border, tpp); break;
+        default: flow_warp_kernel<T, 0><<<blocks, 256, 0, s>>>(x, xs, flow, fs, out, n, h, w, border, tpp); break;
     }
     return VSRB_OK;
 }

@@ -1,0 +1,253 @@
+// Weight gradient of the 3x3, 64-input-channel convolutions on the tensor cores (tcgen05 + TMEM, TMA fed).
+//
+//   dW[tap][ci][co] = sum over pixels p of  x[p + tap][ci] * dz[p][co]
+//
+// is a GEMM whose K dimension is the pixel index.  Both operands are "MN-major" for UMMA: a TMA box of
+// 128 pixels x 64 channels lands in shared memory as 128 rows of 128 bytes (128B swizzle) = K rows of 64
+// contiguous M (resp. N) elements, which is exactly the canonical MN-major layout, so no transpose is needed:
+//   A (M side) = the activation x, shifted by the filter tap: the same three kx-shifted halo copies the forward
+//                conv uses; a tap (ky,kx) is copy kx starting ky*16 rows further down.  Two taps are issued as ONE
+//                M=128 MMA: the descriptor's leading-dimension byte offset (the distance between consecutive
+//                64-element M blocks) points from the first tap's tile to the second tap's tile.
+//   B (N side) = the output gradient dz (N = 64 output channels).
+//   D          = five accumulators of 128 x 64 fp32 in TMEM (9 taps = 4 pairs + 1 single), kept for the whole
+//                persistent CTA; K advances 16 pixels (2048 bytes) per MMA.
+// Every pixel tile is read once; at the end each CTA adds its partial dW into the fp32 OIHW gradient with atomics.
+// Replaces the wgrad half of autograd's ConvolutionBackward0 for the hot 64->64 / 64->256 3x3 layers.
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace vsrb {
+
+static constexpr int kWgThreads = 256;
+static constexpr int kWgTW = 16, kWgRows = 8;                               // 128-pixel tiles
+static constexpr int kWgCopyBytes = (kWgRows + 2) * kWgTW * 128;            // one kx-shifted halo copy: 20 KiB
+static constexpr int kWgZBytes = kWgRows * kWgTW * 128;                     // dz tile: 16 KiB
+static constexpr int kWgStageBytes = 3 * kWgCopyBytes + kWgZBytes;          // 76 KiB
+static constexpr int kWgStages = 2;
+static constexpr int kWgSmem = 1024 + 1024 + kWgStages * kWgStageBytes;
+
+struct WgTcParams {
+    CUtensorMap xmap, zmap;
+    int H, W, batch;
+    int tiles_x, tiles_per_img, total_tiles;
+    int c0, n0;                 // channel offsets inside x / dz
+    int cout, cin_total, ci_off;   // OIHW geometry of dw; ci_off = first input channel of this block on the OIHW axis
+    float* dw;
+    int* dbg;
+};
+
+// MN-major, 128B-swizzled operand descriptor: start>>4 | LBO>>4 @16 | SBO>>4 @32 (8 K-rows = 1024 B) | version 1 @46 | layout 2 @61
+__device__ __forceinline__ uint64_t mn_desc(uint32_t saddr, uint32_t lbo_bytes) {
+    const uint32_t lo = ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+    const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    return ((uint64_t)hi << 32) | lo;
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_constant__ WgTcParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (base - raw);
+    const uint32_t full0 = base, empty0 = base + 64, done = base + 128;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + 192);
+    const uint32_t stage0 = base + 1024;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < kWgStages; ++i) {
+            mbar_init(full0 + 8 * i, 1);
+            mbar_init(empty0 + 8 * i, 1);
+        }
+        mbar_init(done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(smem_u32(tmem_slot), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+    bool dead = false;
+    const int my_tiles = (P.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (warp == 0) {
+        // ---- producer: three kx-shifted halo copies of x and the dz tile per pixel tile ----
+        int slot = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+            const int img = tile / P.tiles_per_img;
+            const int t = tile - img * P.tiles_per_img;
+            const int ty = t / P.tiles_x, tx = t - ty * P.tiles_x;
+            const uint32_t sa = stage0 + slot * kWgStageBytes;
+            mbar_wait(empty0 + 8 * slot, phase ^ 1, P.dbg, 11, dead);
+            if (elect_one()) {
+                mbar_expect_tx(full0 + 8 * slot, kWgStageBytes);
+                for (int kx = 0; kx < 3; ++kx)
+                    tma_load_4d(&P.xmap, full0 + 8 * slot, sa + kx * kWgCopyBytes, P.c0, tx * kWgTW + kx - 1, ty * kWgRows - 1, img);
+                tma_load_4d(&P.zmap, full0 + 8 * slot, sa + 3 * kWgCopyBytes, P.n0, tx * kWgTW, ty * kWgRows, img);
+            }
+            __syncwarp();
+            if (++slot == kWgStages) { slot = 0; phase ^= 1; }
+        }
+    } else if (warp == 1) {
+        // ---- MMA issuer: D_pair[128 x 64] += X_pair^T[128 x 16] * dZ[16 x 64] for 8 K steps x 5 tap pairs ----
+        // instruction descriptor: D=f32, A=B=bf16, A and B MN-major (bits 15, 16), N=64, M=128
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | (8u << 24);
+        int slot = 0;
+        uint32_t phase = 0;
+        bool first = true;
+        for (int it = 0; it < my_tiles; ++it) {
+            const uint32_t sa = stage0 + slot * kWgStageBytes;
+            mbar_wait(full0 + 8 * slot, phase, P.dbg, 12, dead);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t zb = sa + 3 * kWgCopyBytes;
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    const uint64_t bd = mn_desc(zb + ks * 2048u, 0u);
+                    const uint32_t acc = (first && ks == 0) ? 0u : 1u;
+                    // pairs (ky,0)&(ky,1): second tile lives one halo copy further
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky)
+                        umma_bf16(tmem_base + ky * 64, mn_desc(sa + (ky + ks) * 2048u, kWgCopyBytes), bd, idesc, acc);
+                    // pair (0,2)&(1,2): same copy, one filter row (16 pixels = 2048 B) further
+                    umma_bf16(tmem_base + 3 * 64, mn_desc(sa + 2 * kWgCopyBytes + ks * 2048u, 2048u), bd, idesc, acc);
+                    // (2,2) & a don't-care second half
+                    umma_bf16(tmem_base + 4 * 64, mn_desc(sa + 2 * kWgCopyBytes + (2 + ks) * 2048u, 2048u), bd, idesc, acc);
+                }
+                umma_commit(empty0 + 8 * slot);
+            }
+            __syncwarp();
+            first = false;
+            if (++slot == kWgStages) { slot = 0; phase ^= 1; }
+        }
+        if (elect_one()) umma_commit(done);
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ---- epilogue (once): TMEM -> atomics into dw[co][ci][tap] ----
+        const int wq = warp - 4;
+        mbar_wait(done, 0, P.dbg, 13, dead);
+        tc_fence_after();
+        if (my_tiles > 0) {
+            const int half = wq >> 1;                       // rows 0..63 = first tap of the pair, 64..127 = second
+            const int ci = (wq & 1) * 32 + lane;
+            // tap = ky*3 + kx of (pair, half)
+            const int tapA[5] = {0, 3, 6, 2, 8}, tapB[5] = {1, 4, 7, 5, -1};
+            for (int pr = 0; pr < 5; ++pr) {
+                const int tap = half ? tapB[pr] : tapA[pr];
+                for (int c0 = 0; c0 < 64; c0 += 16) {
+                    uint32_t r[16];
+                    tmem_ld16_nowait(tmem_base + ((uint32_t)(wq * 32) << 16) + pr * 64 + c0, r);
+                    tmem_ld_wait();
+                    if (tap >= 0) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int co = P.n0 + c0 + j;
+                            if (co < P.cout)
+                                atomicAdd(P.dw + ((size_t)co * P.cin_total + P.ci_off + ci) * 9 + tap, __uint_as_float(r[j]));
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// bias gradient: db[co] += sum over pixels of dz[p][co]
+template <typename T>
+__global__ void bias_grad_kernel(const T* __restrict__ dz, int dz_c, long long pixels, int cout, float* __restrict__ db) {
+    // blockDim = (64 channels, 4 pixel lanes); grid.y = channel block
+    const int c = blockIdx.y * 64 + threadIdx.x;
+    float s = 0.f;
+    if (c < cout)
+        for (long long p = (long long)blockIdx.x * blockDim.y + threadIdx.y; p < pixels; p += (long long)gridDim.x * blockDim.y)
+            s += (float)dz[p * dz_c + c];
+    __shared__ float red[4][64];
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < cout) atomicAdd(db + c, red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x]);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int launch_bias_grad(const void* dz, int dz_c, long long pixels, int cout, int dtype, float* db, cudaStream_t s) {
+    dim3 block(64, 4), grid(296, ceil_div(cout, 64));
+    if (dtype == VSRB_BF16) bias_grad_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dz), dz_c, pixels, cout, db);
+    else bias_grad_kernel<float><<<grid, block, 0, s>>>(reinterpret_cast<const float*>(dz), dz_c, pixels, cout, db);
+    VSRB_LAUNCH_CHECK();
+    return VSRB_OK;
+}
+
+// one 64-input-channel block (x channels [c0, c0+64), OIHW offset ci_off) against all 64-wide output blocks
+int launch_wgrad_tc(const void* x, int x_c, int c0, int ci_off, const void* dz, int dz_c, int batch, int h, int w, int cout,
+                    int cin_total, float* dw, cudaStream_t stream) {
+    static EncodeTiledFn encode = nullptr;
+    static bool attr = false;
+    if (!encode) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            set_error("cuTensorMapEncodeTiled not available from the driver");
+            return VSRB_E_NODEVICE;
+        }
+        encode = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    if (!attr) {
+        VSRB_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem));
+        attr = true;
+    }
+    int sms = 148;
+    {
+        int dev = 0;
+        VSRB_CUDA(cudaGetDevice(&dev));
+        VSRB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    WgTcParams P;
+    memset(&P, 0, sizeof(P));
+    P.H = h; P.W = w; P.batch = batch;
+    P.tiles_x = ceil_div(w, kWgTW);
+    P.tiles_per_img = P.tiles_x * ceil_div(h, kWgRows);
+    P.total_tiles = P.tiles_per_img * batch;
+    P.c0 = c0; P.cout = cout; P.cin_total = cin_total; P.ci_off = ci_off; P.dw = dw;
+    P.dbg = debug_flag();
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)x_c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)batch};
+        cuuint64_t strides[3] = {(cuuint64_t)x_c * 2, (cuuint64_t)w * x_c * 2, (cuuint64_t)h * w * x_c * 2};
+        cuuint32_t box[4] = {64, kWgTW, kWgRows + 2, 1};
+        CUresult r = encode(&P.xmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("wgrad: tensor map (x) failed with %d", (int)r); return VSRB_E_CUDA; }
+    }
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)dz_c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)batch};
+        cuuint64_t strides[3] = {(cuuint64_t)dz_c * 2, (cuuint64_t)w * dz_c * 2, (cuuint64_t)h * w * dz_c * 2};
+        cuuint32_t box[4] = {64, kWgTW, kWgRows, 1};
+        CUresult r = encode(&P.zmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(dz), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("wgrad: tensor map (dz) failed with %d", (int)r); return VSRB_E_CUDA; }
+    }
+    const int n_blocks = ceil_div(cout, 64);
+    // every CTA ends with 9*64*64 atomics, so small problems use fewer CTAs (>= 16 pixel tiles each)
+    int ctas = sms / n_blocks;
+    if (ctas > P.total_tiles / 16) ctas = P.total_tiles / 16;
+    if (ctas < 1) ctas = 1;
+    for (int nb = 0; nb < n_blocks; ++nb) {          // one launch per 64-wide output block; they run concurrently-ish back to back
+        P.n0 = nb * 64;
+        wgrad_tc_kernel<<<ctas, kWgThreads, kWgSmem, stream>>>(P);
+        VSRB_LAUNCH_CHECK();
+    }
+    return VSRB_OK;
+}
+
+}  // namespace vsrb

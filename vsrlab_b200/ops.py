@@ -19,6 +19,7 @@ ESIZE = {BF16: 2, F32: 4}
 # bench.py sets this to a list to time every launch with CUDA events on the launching stream:
 # entries are (kind, start_event, end_event, algorithmic work: FLOPs for convs, bytes otherwise)
 PROFILE = None
+PROFILE_SHAPES = os.environ.get("VSRB_PROFILE_SHAPES") == "1"
 PDL = os.environ.get("VSRB_PDL") == "1"   # programmatic dependent launch between consecutive convs (measured: no gain, off)
 TAG = ""          # set by the scheduler so profile entries can be grouped by network part
 
@@ -210,7 +211,8 @@ def conv2d_wgrad(geom: "L.ConvGeom", ins: Sequence[torch.Tensor], in_c: Sequence
     ptrs = (C.c_void_p * 2)(*[t.data_ptr() for t in ins], *([None] * (2 - n)))
     cs = (C.c_int32 * 2)(*in_c, *([0] * (2 - n)))
     flops = 2.0 * batch * h * w * geom.cout * sum(geom.seg_c[i] for i in range(geom.n_seg)) * geom.kh * geom.kw
-    with _Timed("conv_wgrad", flops):
+    cin = sum(geom.seg_c[i] for i in range(geom.n_seg))
+    with _Timed(f"conv_wgrad[{geom.kh}x{geom.kw} {cin}->{geom.cout} {h}x{w}]" if PROFILE_SHAPES else "conv_wgrad", flops):
         L.check(L.load().vsrb_conv2d_wgrad(C.byref(geom), ptrs, cs, _p(dz), dz_c, batch, h, w, batch // geom.groups, cin_total,
                                            _p(dw), _p(db), _stream()), "vsrb_conv2d_wgrad")
 
