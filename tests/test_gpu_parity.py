@@ -270,3 +270,26 @@ def test_other_widths_and_scales(dev, mid, upscale, blocks):
         sr16, _ = net(x.clone().to(dev))
     assert O.psnr(sr16.cpu(), sr_ref) > 40.0
     assert ops.debug_status() == 0
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 3, 16, 16), (1, 2, 3, 8, 8), (3, 2, 3, 33, 17), (1, 4, 3, 70, 100)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_edge_shapes(dev, shape):
+    """Degenerate clips: a single frame (no flow, no warp at all), two frames, images smaller than one tile,
+    odd sizes that need the /32 resize inside SPyNet, several clips.  Checked against the CPU oracle."""
+    from vsrlab.vsr.models.RealBasicVSR.realbasicvsr import RealBasicVSR
+    from vsrlab_b200 import functional as VF, ops
+    torch.manual_seed(17)
+    net = RealBasicVSR(cleaning_blocks=1, mid_channels=64, upscale=4, res_blocks=1, pretrained_flow=False, train_flow=False).eval()
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    x = torch.rand(*shape, generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        sr_ref, lq_ref = O.realbasicvsr(x.clone(), sd)
+    net = net.to(dev)
+    with torch.no_grad(), VF.precision("fp32"):
+        sr, lq = net(x.clone().to(dev))
+    assert (sr.cpu() - sr_ref).abs().max().item() <= 1e-4 and (lq.cpu() - lq_ref).abs().max().item() <= 1e-4
+    with torch.no_grad(), VF.precision("bf16"):
+        sr16, _ = net(x.clone().to(dev))
+    assert O.psnr(sr16.cpu(), sr_ref) > 40.0
+    assert ops.debug_status() == 0
