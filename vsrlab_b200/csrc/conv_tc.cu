@@ -33,7 +33,8 @@
 namespace vsrb {
 
 static constexpr int kMaxSlots = 8;
-static constexpr int kThreads = 384;   // 4 control warps + 8 epilogue warps
+static constexpr int kEpiPerQ = 2;     // epilogue warps per TMEM lane quarter (they split the channels)
+static constexpr int kThreads = 128 + 128 * kEpiPerQ;   // 4 control warps + 4*kEpiPerQ epilogue warps
 static constexpr int kSmemMax = 232448;   // 227 KiB opt-in maximum per CTA on sm_100
 static constexpr int kCtrlBytes = 1024;
 static constexpr int kIdentBytes = 8192;  // 64 x 64 bf16 identity, swizzle-128B K-major image
@@ -147,7 +148,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(tfull0 + 8 * i, 1);
-            mbar_init(tempty0 + 8 * i, 8);
+            mbar_init(tempty0 + 8 * i, 4 * kEpiPerQ);
         }
         mbar_init(wbar, 1);
         fence_barrier_init();
@@ -285,8 +286,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
     } else if (warp >= 4) {
         // =============================== epilogue ===================================
-        // Two warps per TMEM lane quarter (hardware rule: a warp reads lanes 32*(warp%4)..+31): warp pair
-        // (wq, eh=0/1) shares the 32 pixels of quarter wq and splits their channels.
+        // kEpiPerQ warps per TMEM lane quarter (hardware rule: a warp reads lanes 32*(warp%4)..+31): the warps
+        // (wq, eh=0..kEpiPerQ-1) share the 32 pixels of quarter wq and split their channels.
         const int wq = (warp - 4) & 3;
         const int eh = (warp - 4) >> 2;
         const int p = wq * 32 + lane;
@@ -298,9 +299,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const uint32_t rowb = (uint32_t)P.n_store * 2u;
         const uint32_t msk = rowb == 128u ? 7u : (rowb == 64u ? 3u : 1u);
         const int rows_warp = 32 / P.TW;                  // image rows covered by one quarter's 32 pixels
-        const int cpw = P.n_store >= 32 ? P.n_store / 2 : P.n_store;   // channels of a store block per warp
-        const bool works = P.n_store >= 32 || eh == 0;    // 16-channel blocks are not split
-        const int cbeg = P.n_store >= 32 ? eh * cpw : 0;
+        // a store block of n_store channels is split in 16-channel chunks over the kEpiPerQ warps of the quarter
+        const int nsplit = min(kEpiPerQ, P.n_store / 16);
+        const int cpw = P.n_store / nsplit;               // channels of a store block per working warp (16 or 32)
+        const bool works = eh < nsplit;
+        const int cbeg = works ? eh * cpw : 0;
         // stacked layout (n_tile <= 64, one store block): this warp's bias values live in registers
         float bias_r[32];
 #pragma unroll
@@ -329,7 +332,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                     for (int b0 = 0; b0 < P.n_tile; b0 += P.n_store) {
                         if (kStaged) {
                             if (eh == 0 && lane == 0) bulk_wait_read<1>();
-                            pair_sync(wq);
+                            pair_sync(wq, 32 * kEpiPerQ);
                         }
                         const uint32_t row_base = stg0 + sbuf * P.stg_bytes + (uint32_t)(wq * 32 + lane - PAD) * rowb;
                         if (works) {
@@ -372,7 +375,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                         }
                         if (kStaged) {
                             fence_proxy_async();
-                            pair_sync(wq);
+                            pair_sync(wq, 32 * kEpiPerQ);
                             if (eh == 0 && lane == 0 && !(P.debug & 2)) {
                                 tma_store_5d(&P.smap[0], stg0 + sbuf * P.stg_bytes + (uint32_t)(wq * 32) * rowb, qb * P.n_tile + b0,
                                              tx * P.UW, y, li, g);
@@ -388,7 +391,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                         for (int j = 0; j < 2; ++j)
                             if (works && j * 16 < cpw) tmem_ld16_nowait(t0 + b0 + cbeg + j * 16, r[j]);
                         if (eh == 0 && lane == 0) bulk_wait_read<1>();      // the buffer used two stores ago is free again
-                        pair_sync(wq);
+                        pair_sync(wq, 32 * kEpiPerQ);
                         tmem_ld_wait();
                         const uint32_t row_base = stg0 + sbuf * P.stg_bytes + (uint32_t)p * rowb;
 #pragma unroll
@@ -396,7 +399,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                             if (works && j * 16 < cpw)
                                 stage_chunk(P.epi, r[j], bias_s + b0 + cbeg + j * 16, row_base, (uint32_t)(cbeg + j * 16) * 2u, msk);
                         fence_proxy_async();
-                        pair_sync(wq);
+                        pair_sync(wq, 32 * kEpiPerQ);
                         if (eh == 0 && lane == 0 && !(P.debug & 2)) {
                             const int n0 = qb * P.n_tile + b0;
                             const int q = P.epi.pixshuf ? n0 / P.epi.cq : 0;
@@ -410,7 +413,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 } else {
                     const int y = ty * rows_tile + m * P.rows_sub + py;
                     const bool valid = (y < P.H) && (x < P.W) && !(P.debug & 2);
-                    for (int c0 = eh * 16; c0 < P.n_tile; c0 += 32) {     // the pair interleaves 16-channel chunks
+                    for (int c0 = eh * 16; c0 < P.n_tile; c0 += 16 * kEpiPerQ) {     // the quarter's warps interleave 16-channel chunks
                         uint32_t r[16];
                         tmem_ld16_nowait(t0 + c0, r);
                         tmem_ld_wait();

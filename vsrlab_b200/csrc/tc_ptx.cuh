@@ -116,7 +116,9 @@ __device__ __forceinline__ void tmem_ld_n<8>(uint32_t taddr, uint32_t (&r)[8]) {
                  : "r"(taddr));
 }
 // the two epilogue warps of TMEM lane quarter `wq` (64 threads) meet on named barrier 1 + wq
-__device__ __forceinline__ void pair_sync(int wq) { asm volatile("bar.sync %0, 64;" ::"r"(wq + 1) : "memory"); }
+__device__ __forceinline__ void pair_sync(int wq, int threads = 64) {
+    asm volatile("bar.sync %0, %1;" ::"r"(wq + 1), "r"(threads) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
