@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(256) flow_warp_kernel(const T* __restrict__ x,
     __syncthreads();
     const int npix = min(kWarpPix, total - pix0);
     const int work = npix * tpp;
-#pragma unroll 2
+#pragma unroll 4
     for (int i = threadIdx.x; i < work; i += 256) {
         const int lp = i / tpp, part = i % tpp;          // compile-time power of two: shift / mask
         const WarpTap wt = taps[lp];

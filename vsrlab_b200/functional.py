@@ -80,7 +80,8 @@ def ws(name: str, shape: Sequence[int], dtype: torch.dtype, device) -> torch.Ten
     n = 1
     for s in shape:
         n *= int(s)
-    key = (name, dtype, str(device))
+    # per stream: two clips processed on two streams must not share scratch memory
+    key = (name, dtype, str(device), torch.cuda.current_stream(device).cuda_stream)
     t = _ws.get(key)
     if t is None or t.numel() < n:
         t = torch.empty(max(n, 1), dtype=dtype, device=device)
