@@ -124,7 +124,7 @@ def run_reference(a):
 def workload_config(a, clips):
     return {"workload": f"cfg3: Real-BasicVSR x4 inference, {T_FRAMES}-frame {LR_H}x{LR_W}->{4*LR_H}x{4*LR_W} clips, "
                         f"{a.blocks}/{a.blocks} blocks", "clips_per_gpu_per_step": clips, "frames_per_clip": T_FRAMES,
-            "precision": "bf16 activations, fp32 accumulate", "parallelism": f"clips sharded over {a.gpus} GPU(s), no collective",
+            "precision": "bf16 activations, fp32 accumulate", "cuda_graph": "whole forward captured once, replayed per step", "parallelism": f"clips sharded over {a.gpus} GPU(s), no collective",
             "l2": "per-step working set (GBs of activations) exceeds the 126 MB L2; no explicit flush"}
 
 

@@ -97,6 +97,13 @@ def load() -> C.CDLL:
     if _lib is not None:
         return _lib
     path = Path(os.environ.get("VSRB200_LIB", LIB_PATH))
+    if not path.exists() and "VSRB200_LIB" not in os.environ:
+        # not built yet (fresh checkout): compile the kernels in-tree with nvcc; there is still no non-CUDA path
+        try:
+            from . import build as _build
+            _build.build()
+        except Exception as e:  # noqa: BLE001
+            raise VsrbError(f"{path} is missing and building it failed: {e}") from e
     if not path.exists():
         raise VsrbError(
             f"{path} not found: build the sm_100a kernels first (python -m vsrlab_b200.build). "

@@ -11,6 +11,7 @@ Charbonnier losses (core/utils.py:235-280); this module is what makes that work 
 """
 from __future__ import annotations
 
+import weakref
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -33,8 +34,9 @@ def _cl(t: torch.Tensor) -> torch.Tensor:
 def _packed_transposed(conv) -> ops.PackedConvT:
     key = id(conv)
     pc = _packed_t.get(key)
-    if pc is None or pc.stamp != ops.PackedConv.stamp_of([conv]):
+    if pc is None or pc.stamp != ops.PackedConv.stamp_of([conv]) or pc.owner() is not conv:   # ids are recycled
         pc = ops.PackedConvT(conv, BF16)
+        pc.owner = weakref.ref(conv)
         _packed_t[key] = pc
     return pc
 

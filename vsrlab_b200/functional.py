@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import contextlib
 import os
+import weakref
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -66,11 +67,17 @@ _ws: Dict[tuple, torch.Tensor] = {}
 _consts: Dict[tuple, object] = {}
 
 
+def _same_objects(refs, objs) -> bool:
+    """id() values are recycled after garbage collection: a cache hit must be for the very same live modules."""
+    return len(refs) == len(objs) and all(r() is o for r, o in zip(refs, objs))
+
+
 def packed(convs: Sequence[torch.nn.Conv2d], segs: Sequence[Tuple[int, int]], dt: int, pixshuf: int = 0) -> ops.PackedConv:
     key = (tuple(id(c) for c in convs), tuple(segs), dt, pixshuf)
     pc = _packed.get(key)
-    if pc is None or pc.stamp != ops.PackedConv.stamp_of(convs):
+    if pc is None or pc.stamp != ops.PackedConv.stamp_of(convs) or not _same_objects(pc.owners, convs):
         pc = ops.PackedConv(convs, segs, dt, pixshuf)
+        pc.owners = [weakref.ref(c) for c in convs]
         _packed[key] = pc
     return pc
 
@@ -93,6 +100,7 @@ def clear_caches() -> None:
     _packed.clear()
     _ws.clear()
     _consts.clear()
+    _graphs.clear()
 
 
 def _check_input(x: torch.Tensor, what: str) -> torch.Tensor:
@@ -235,10 +243,10 @@ def flow_warp(x: torch.Tensor, flow: torch.Tensor, padding_mode: str = "zeros") 
 def _spynet_consts(sp) -> Tuple[List[float], List[float]]:
     key = ("spynet_norm", id(sp), sp.mean.data_ptr(), sp.mean._version, sp.std._version)
     v = _consts.get(key)
-    if v is None:
-        v = (sp.mean.detach().flatten().cpu().tolist(), sp.std.detach().flatten().cpu().tolist())
+    if v is None or v[2]() is not sp:
+        v = (sp.mean.detach().flatten().cpu().tolist(), sp.std.detach().flatten().cpu().tolist(), weakref.ref(sp))
         _consts[key] = v
-    return v
+    return v[0], v[1]
 
 
 def _spynet_run(sp, frames: torch.Tensor, ref_idx: torch.Tensor, supp_idx: torch.Tensor, dt: int, resize: bool = True) -> torch.Tensor:
@@ -464,7 +472,55 @@ def realbasicvsr_forward(model, lr: torch.Tensor):
     if not lr.is_contiguous():
         raise RuntimeError("RealBasicVSR works in place on a view of its input; pass a contiguous tensor")
     dt = current_dtype()
+    if GRAPHS and ops.PROFILE is None:
+        return _graphed_forward(model, lr, dt)
     n, t, c, h, w = lr.shape
     x_nhwc = _cleaner_run(model.cleaner, lr.view(n * t, c, h, w), dt)
     sr = _basicvsr_run(model.basicvsr, lr, dt, x_nhwc)
     return sr, lr
+
+
+# --------------------------------------------------------------------------------------
+# CUDA-graph replay of the whole forward (several hundred dependent launches per call)
+# --------------------------------------------------------------------------------------
+GRAPHS = os.environ.get("VSRB_GRAPHS", "1") == "1"      # VSRB_GRAPHS=0: launch every kernel eagerly
+MAX_GRAPHS = 4                                          # captured (model, shape, precision) combinations kept alive
+_graphs: Dict[tuple, tuple] = {}
+
+
+def _weights_stamp(model) -> tuple:
+    return tuple((p.data_ptr(), p._version) for p in model.parameters())
+
+
+def _graphed_forward(model, lr: torch.Tensor, dt: int):
+    """Capture `cleaner + BasicVSR` once per (model weights, shape, precision) and replay it.  The captured graph
+    works on a private input buffer; the caller's `lr` receives the cleaned frames afterwards, so the in-place
+    contract (`lq is lr`, overwritten) is unchanged, and `sr` is copied out of the graph's static output."""
+    key = (id(model), dt, tuple(lr.shape), str(lr.device))
+    stamp = _weights_stamp(model)
+    entry = _graphs.get(key)
+    if entry is None or entry[0] != stamp or entry[4]() is not model:
+        n, t, c, h, w = lr.shape
+        static_in = torch.empty_like(lr)
+        side = torch.cuda.Stream(device=lr.device)
+        side.wait_stream(torch.cuda.current_stream(lr.device))
+        with torch.cuda.stream(side):              # warm-up on the capture stream: packs weights, sizes workspaces
+            static_in.copy_(lr)
+            x_nhwc = _cleaner_run(model.cleaner, static_in.view(n * t, c, h, w), dt)
+            _basicvsr_run(model.basicvsr, static_in, dt, x_nhwc)
+        torch.cuda.current_stream(lr.device).wait_stream(side)
+        torch.cuda.synchronize(lr.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            x_nhwc = _cleaner_run(model.cleaner, static_in.view(n * t, c, h, w), dt)
+            static_sr = _basicvsr_run(model.basicvsr, static_in, dt, x_nhwc)
+        entry = (stamp, graph, static_in, static_sr, weakref.ref(model))
+        _graphs.pop(key, None)
+        while len(_graphs) >= MAX_GRAPHS:          # dicts keep insertion order: drop the oldest capture
+            _graphs.pop(next(iter(_graphs)))
+        _graphs[key] = entry
+    _, graph, static_in, static_sr, _ = entry
+    static_in.copy_(lr)
+    graph.replay()
+    lr.copy_(static_in)
+    return static_sr.clone(), lr
