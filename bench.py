@@ -152,6 +152,8 @@ def main():
     ap.add_argument("--streams", type=int, default=1,
                     help="process the step's clips on this many CUDA streams (fills the fill/drain bubbles of the "
                          "sequential propagation kernels with another clip's work)")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "fp32_ffma"],
+                    help="bf16 (headline) | fp32 = fp32-accurate split-bf16 on the tensor cores | fp32_ffma = FFMA kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl != "reference" else a.warmup
@@ -168,7 +170,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    VF.set_precision("bf16")
+    VF.set_precision(a.precision)
     model = build_model(a.blocks, dev)
     clips = a.clips
     gen = torch.Generator().manual_seed(1000 + rank)
@@ -276,7 +278,7 @@ def main():
         d[0] += sec
         d[1] += work_units
         d[2] += 1
-        if kind == "conv_tc":
+        if kind.startswith("conv_"):
             q = parts.setdefault(tag, [0.0, 0.0, 0])
             q[0] += sec
             q[1] += work_units
@@ -318,11 +320,12 @@ def main():
         tp = ROOT / "profiles" / "traffic.json"            # dram bytes per launch from `ncu --set full` captures
         if tp.exists():
             traffic = json.loads(tp.read_text())
-        conv = fam.get("conv_tc", [1e-9, 0.0, 0])
+        conv = fam.get("conv_tc") or fam.get("conv_tc_x3") or fam.get("conv_f32") or [1e-9, 0.0, 0]
         warp = fam.get("flow_warp", [1e-9, 0.0, 0])
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"bf16": "bf16", "fp32": "bf16x3 (split-bf16, fp32-accurate)", "fp32_ffma": "f32"}[a.precision],
             "data": "synthetic", "config": workload_config(a, clips),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": host_lr.numel() * 4,
                     "d2h_bytes_per_step": (host_sr[0].numel() + host_lq[0].numel()) * 4,

@@ -42,6 +42,7 @@ extern "C" {
 /* dtypes */
 #define VSRB_BF16 0
 #define VSRB_F32  1
+#define VSRB_BF16X2 2      /* layout kernels only: split-bf16, per pixel [hi C | lo C], value = hi + lo   */
 
 /* activations fused in the conv epilogue */
 #define VSRB_ACT_NONE  0
@@ -70,9 +71,9 @@ extern "C" {
  * must agree on.  Stride 1, 'same' padding (kh//2, kw//2), dilation 1. */
 typedef struct vsrb_conv_geom {
     int32_t kh, kw;         /* 1, 3 or 7                                                        */
-    int32_t n_seg;          /* 1 or 2 input segments (a fused torch.cat along channels)         */
-    int32_t seg_c[2];       /* real channels of each segment                                    */
-    int32_t seg_off[2];     /* where the segment sits on the OIHW input-channel axis            */
+    int32_t n_seg;          /* 1..4 weight segments (a fused torch.cat along channels)          */
+    int32_t seg_c[4];       /* real channels of each segment                                    */
+    int32_t seg_off[4];     /* where the segment sits on the OIHW input-channel axis            */
     int32_t cout;           /* real output channels                                             */
     int32_t pixshuf;        /* 0, or 2 = output channel 4c+2i+j is stored at pixel (2y+i,2x+j)  */
     int32_t groups;         /* independent weight sets applied to consecutive image groups      */
@@ -84,8 +85,15 @@ typedef struct vsrb_conv_geom {
 
 typedef struct vsrb_conv_args {
     vsrb_conv_geom geom;
-    const void*  in[2];       /* NHWC inputs, one per segment                                    */
-    int32_t      in_c[2];     /* channels allocated per pixel in in[s] (>= padded seg_c[s])      */
+    int32_t      n_in;        /* 0: in[s] is the input of weight segment s.  Otherwise the number of
+                                 input OPERANDS (<= 6): operand i multiplies weight segment in_wseg[i]
+                                 and reads geom.seg_c[in_wseg[i]] channels of in[i] starting at channel
+                                 in_c0[i].  Several operands may share one weight segment - the
+                                 split-bf16 fp32 mode feeds (hi, W_hi), (lo, W_hi), (hi, W_lo).       */
+    const void*  in[6];       /* NHWC inputs                                                     */
+    int32_t      in_c[6];     /* channels allocated per pixel in in[i]                           */
+    int32_t      in_c0[6];    /* first channel of operand i inside in[i] (n_in > 0)              */
+    int32_t      in_wseg[6];  /* weight segment of operand i (n_in > 0)                          */
     int32_t      batch, h, w; /* input (== pre-shuffle output) extent                            */
     int32_t      imgs_per_group; /* images per weight group (batch = groups*imgs_per_group)      */
     const void*  packed;      /* buffer written by vsrb_pack_conv_weight                         */
@@ -106,6 +114,8 @@ typedef struct vsrb_conv_args {
     int32_t      aux_h, aux_w;/* EPI_SR: extent of the low-resolution skip frame                 */
     int32_t      max_ctas;    /* 0 = one persistent CTA per SM                                   */
     int32_t      flags;       /* VSRB_CONV_* bits                                                */
+    int32_t      split;       /* 1: `out`, `residual` (and the EPI_CLEAN frame) are split-bf16: per pixel
+                                 [hi C | lo C] with C = out_c/2, value = hi + lo                  */
 } vsrb_conv_args;
 
 /* ---- library ------------------------------------------------------------------------- */

@@ -13,7 +13,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 LIB_PATH = HERE / "csrc" / "libvsrb200.so"
 
-BF16, F32 = 0, 1
+BF16, F32, BF16X2 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
 PAD_ZEROS, PAD_BORDER = 0, 1
 EPI_NHWC, EPI_CLEAN, EPI_FLOW, EPI_SR = 0, 1, 2, 3
@@ -24,8 +24,8 @@ class ConvGeom(C.Structure):
     _fields_ = [
         ("kh", C.c_int32), ("kw", C.c_int32),
         ("n_seg", C.c_int32),
-        ("seg_c", C.c_int32 * 2),
-        ("seg_off", C.c_int32 * 2),
+        ("seg_c", C.c_int32 * 4),
+        ("seg_off", C.c_int32 * 4),
         ("cout", C.c_int32),
         ("pixshuf", C.c_int32),
         ("groups", C.c_int32),
@@ -37,8 +37,11 @@ class ConvGeom(C.Structure):
 class ConvArgs(C.Structure):
     _fields_ = [
         ("geom", ConvGeom),
-        ("inp", C.c_void_p * 2),
-        ("in_c", C.c_int32 * 2),
+        ("n_in", C.c_int32),
+        ("inp", C.c_void_p * 6),
+        ("in_c", C.c_int32 * 6),
+        ("in_c0", C.c_int32 * 6),
+        ("in_wseg", C.c_int32 * 6),
         ("batch", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
         ("imgs_per_group", C.c_int32),
         ("packed", C.c_void_p),
@@ -56,6 +59,7 @@ class ConvArgs(C.Structure):
         ("aux_h", C.c_int32), ("aux_w", C.c_int32),
         ("max_ctas", C.c_int32),
         ("flags", C.c_int32),
+        ("split", C.c_int32),
     ]
 
 

@@ -31,7 +31,7 @@ int make_plan(const vsrb_conv_geom* g, ConvPlan* p) {
     VSRB_CHECK_ARG(g && p, "null geometry");
     VSRB_CHECK_ARG(g->kh >= 1 && g->kh <= 7 && (g->kh & 1) && g->kw >= 1 && g->kw <= 7 && (g->kw & 1),
                    "kernel %dx%d unsupported (odd sizes 1..7)", g->kh, g->kw);
-    VSRB_CHECK_ARG(g->n_seg == 1 || g->n_seg == 2, "n_seg must be 1 or 2, got %d", g->n_seg);
+    VSRB_CHECK_ARG(g->n_seg >= 1 && g->n_seg <= 4, "n_seg must be 1..4, got %d", g->n_seg);
     VSRB_CHECK_ARG(g->cout >= 1 && g->cout <= 1024, "cout %d unsupported", g->cout);
     VSRB_CHECK_ARG(g->groups >= 1, "groups must be >= 1");
     VSRB_CHECK_ARG(g->dtype == VSRB_BF16 || g->dtype == VSRB_F32, "bad dtype %d", g->dtype);
@@ -142,7 +142,7 @@ __host__ __device__ static inline int orig_cout(int np, int cout, int pixshuf) {
 
 struct PackParams {
     int kh, kw, n_seg, groups, pixshuf;
-    int seg_c[2], seg_off[2], seg_ck[2], seg_chunks[2], seg_rowbytes[2], seg_mask[2], seg_bstage[2];
+    int seg_c[4], seg_off[4], seg_ck[4], seg_chunks[4], seg_rowbytes[4], seg_mask[4], seg_bstage[4];
     int cin_total, cin_packed, cout, cout_pad, n_tile, n_blocks, stacked, transpose;
     size_t wblock_bytes, bias_bytes;
 };
@@ -170,9 +170,13 @@ __global__ void pack_tc_kernel(PackParams pp, const float* __restrict__ w, uint8
         // locate segment / stage
         int s = 0;
         const int kxs = pp.stacked ? 1 : pp.kw;        // stages per channel chunk
-        size_t seg0_elems = (size_t)pp.seg_chunks[0] * kxs * pp.seg_bstage[0] / 2;
         size_t base_bytes = 0;
-        if (r >= seg0_elems) { s = 1; r -= seg0_elems; base_bytes = seg0_elems * 2; }
+        for (; s < pp.n_seg - 1; ++s) {
+            const size_t seg_elems = (size_t)pp.seg_chunks[s] * kxs * pp.seg_bstage[s] / 2;
+            if (r < seg_elems) break;
+            r -= seg_elems;
+            base_bytes += seg_elems * 2;
+        }
         size_t st_elems = (size_t)pp.seg_bstage[s] / 2;
         int local = (int)(r / st_elems);
         size_t e = r - (size_t)local * st_elems;
@@ -216,7 +220,7 @@ __global__ void pack_f32_kernel(PackParams pp, const float* __restrict__ w, floa
         int tap = (int)(r / pp.cin_packed);
         int ky = tap / pp.kw, kx = tap - ky * pp.kw;
         int s = 0, ci = cp;
-        if (pp.n_seg == 2 && cp >= pp.seg_c[0]) { s = 1; ci = cp - pp.seg_c[0]; }
+        while (s < pp.n_seg - 1 && ci >= pp.seg_c[s]) { ci -= pp.seg_c[s]; ++s; }
         float v = 0.f;
         if (np < pp.cout) {
             int o = orig_cout(np, pp.cout, pp.pixshuf);
@@ -269,6 +273,7 @@ void fill_epi(const vsrb_conv_args* a, const ConvPlan& p, EpiParams* e) {
         e->out_img_stride = a->out_img_stride ? a->out_img_stride : oh * ow * a->out_c;
         e->out_group_stride = a->out_group_stride ? a->out_group_stride : e->out_img_stride * a->imgs_per_group;
         e->imgs_per_group = a->imgs_per_group;
+        e->split = a->split;
     }
     e->f32_io = a->f32_io; e->f32_in = a->f32_in; e->aux_h = a->aux_h; e->aux_w = a->aux_w;
     e->bias = reinterpret_cast<const float*>(a->packed);
@@ -344,20 +349,27 @@ int vsrb_conv2d_fwd(const vsrb_conv_args* a, void* stream) {
                    "batch %d != groups %d * imgs_per_group %d", a->batch, p.groups, a->imgs_per_group);
     VSRB_CHECK_ARG(a->packed, "null packed weights");
     VSRB_CHECK_ARG(a->act != VSRB_ACT_LRELU || (a->slope >= 0.f && a->slope <= 1.f), "LeakyReLU slope must be in [0,1]");
-    for (int s = 0; s < p.n_seg; ++s) {
-        VSRB_CHECK_ARG(a->in[s], "null input segment %d", s);
+    VSRB_CHECK_ARG(a->n_in >= 0 && a->n_in <= 6, "n_in must be 0..6");
+    VSRB_CHECK_ARG(a->n_in == 0 || p.dtype == VSRB_BF16, "operand lists (n_in > 0) exist for the tensor-core path only");
+    const int n_ops = a->n_in ? a->n_in : p.n_seg;
+    for (int i = 0; i < n_ops; ++i) {
+        const int s = a->n_in ? a->in_wseg[i] : i, c0 = a->n_in ? a->in_c0[i] : 0;
+        VSRB_CHECK_ARG(s >= 0 && s < p.n_seg && c0 >= 0, "operand %d: bad weight segment / channel offset", i);
+        VSRB_CHECK_ARG(a->in[i], "null input operand %d", i);
         int need = p.dtype == VSRB_BF16 ? p.seg[s].cpad : p.seg[s].c;
-        VSRB_CHECK_ARG(a->in_c[s] >= need, "segment %d: %d channels allocated, need %d", s, a->in_c[s], need);
+        VSRB_CHECK_ARG(a->in_c[i] >= c0 + need, "operand %d: %d channels allocated, need %d", i, a->in_c[i], c0 + need);
     }
+    VSRB_CHECK_ARG(!a->split || (p.dtype == VSRB_BF16 && (a->epilogue == VSRB_EPI_NHWC || a->epilogue == VSRB_EPI_CLEAN)),
+                   "split outputs exist for bf16 EPI_NHWC / EPI_CLEAN only");
     switch (a->epilogue) {
         case VSRB_EPI_NHWC:
-            VSRB_CHECK_ARG(a->out && a->out_c >= (p.pixshuf ? p.cout / 4 : p.cout_pad),
+            VSRB_CHECK_ARG(a->out && (a->split ? a->out_c / 2 : a->out_c) >= (p.pixshuf ? p.cout / 4 : p.cout_pad),
                            "EPI_NHWC: out_c %d too small", a->out_c);
-            VSRB_CHECK_ARG(!a->residual || (!p.pixshuf && a->res_c >= p.cout_pad), "bad residual");
+            VSRB_CHECK_ARG(!a->residual || (!p.pixshuf && (a->split ? a->res_c / 2 : a->res_c) >= p.cout_pad), "bad residual");
             VSRB_CHECK_ARG(a->out_c % 8 == 0 && (!a->residual || a->res_c % 8 == 0), "channel strides must be %% 8");
             break;
         case VSRB_EPI_CLEAN:
-            VSRB_CHECK_ARG(p.cout == 3 && a->f32_io && a->out && a->out_c >= 3 && a->out_c <= 16 && !p.pixshuf,
+            VSRB_CHECK_ARG(p.cout == 3 && a->f32_io && a->out && a->out_c >= 3 && a->out_c <= (a->split ? 32 : 16) && !p.pixshuf,
                            "EPI_CLEAN needs cout==3, f32_io, out with 3..16 channels");
             break;
         case VSRB_EPI_FLOW:

@@ -66,13 +66,13 @@ struct SegPlan {
 
 struct ConvPlan {
     int kh, kw, n_seg, groups, pixshuf, dtype;
-    SegPlan seg[2];
+    SegPlan seg[4];
     int cin_packed;        // sum of real segment channels (fp32 path K extent per tap)
     int cout, cout_pad;    // cout_pad = round_up(cout, 16)
     int n_tile, n_blocks;  // tensor-core path: output channels per CTA, CTAs along N
     int stacked, ns;       // stacked layout: kw filter columns side by side along the MMA N (ns = kw*n_tile)
     int stages_per_tile;   // sum over segments of chunks*kw
-    int b_stage_bytes[2];  // kh * n_tile * rowbytes
+    int b_stage_bytes[4];  // kh * n_tile * rowbytes
     size_t wblock_bytes;   // packed weights of one (group, n_block)
     size_t bias_bytes;     // groups*cout_pad floats rounded to 1 KiB
     size_t total_bytes;
@@ -94,6 +94,7 @@ struct EpiParams {
     int out_c;
     long long out_img_stride, out_group_stride;   // elements
     int imgs_per_group;
+    int split;            // out / residual are split-bf16 [hi | lo]; half = out_c / 2 (res_c / 2)
     const void* res;
     int res_c;
     float* f32_io;
@@ -211,9 +212,25 @@ __device__ __forceinline__ void epi_store16(const EpiParams& e, int g, int b, in
             Act<T>::load16(reinterpret_cast<const T*>(e.res) + pix * e.res_c + c0, r);
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] += r[i];
+            if (e.split) {                       // split-bf16 residual: value = hi + lo
+                Act<T>::load16(reinterpret_cast<const T*>(e.res) + pix * e.res_c + e.res_c / 2 + c0, r);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] += r[i];
+            }
         }
         long long o = (long long)g * e.out_group_stride + (long long)(b - g * e.imgs_per_group) * e.out_img_stride +
                       ((long long)Y * OW + X) * e.out_c + c0;
+        if (e.split) {                           // split-bf16 output: hi = bf16(v), lo = bf16(v - hi)
+            float hi[16], lo[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                hi[i] = __bfloat162float(__float2bfloat16_rn(v[i]));
+                lo[i] = v[i] - hi[i];
+            }
+            Act<T>::store16(reinterpret_cast<T*>(e.out) + o, hi);
+            Act<T>::store16(reinterpret_cast<T*>(e.out) + o + e.out_c / 2, lo);
+            return;
+        }
         Act<T>::store16(reinterpret_cast<T*>(e.out) + o, v);
     } else if (e.mode == VSRB_EPI_CLEAN) {
         if (n0 != 0) return;
@@ -230,7 +247,16 @@ __device__ __forceinline__ void epi_store16(const EpiParams& e, int g, int b, in
         }
         size_t pix = ((size_t)b * e.H + y) * e.W + x;
         T* op = reinterpret_cast<T*>(e.out) + pix * e.out_c;
-        if (e.out_c >= 16) Act<T>::store16(op, nv);
+        if (e.split) {                           // refreshed frame as [hi 16 | lo 16]
+            float hi[16], lo[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                hi[i] = __bfloat162float(__float2bfloat16_rn(nv[i]));
+                lo[i] = nv[i] - hi[i];
+            }
+            Act<T>::store16(op, hi);
+            Act<T>::store16(op + e.out_c / 2, lo);
+        } else if (e.out_c >= 16) Act<T>::store16(op, nv);
         else Act<T>::store_n(op, nv, e.out_c);
     } else if (e.mode == VSRB_EPI_FLOW) {
         if (n0 != 0) return;

@@ -12,8 +12,8 @@
 namespace vsrb {
 
 struct F32Params {
-    const float* in[2];
-    int in_c[2], seg_c[2];
+    const float* in[4];
+    int in_c[4], seg_c[4];
     int n_seg;
     const float* w;   // [group][tap][cin_packed][cout_pad]
     EpiParams epi;

@@ -40,14 +40,17 @@ static constexpr int kCtrlBytes = 1024;
 static constexpr int kIdentBytes = 8192;  // 64 x 64 bf16 identity, swizzle-128B K-major image
 
 struct TcParams {
-    CUtensorMap tmap[2];
+    CUtensorMap tmap[6];   // one per input operand
     CUtensorMap rmap;      // residual (MMA-identity path)
     CUtensorMap smap[4];   // output maps for the staged TMA store (one per pixel-shuffle sub-position)
     const uint8_t* w;      // packed weights (after the bias header)
     const uint8_t* ident;  // identity image in global memory
     EpiParams epi;
     int n_seg;
-    int seg_chunks[2], seg_ck[2], seg_rowbytes[2], seg_layout[2], seg_bstage[2], seg_abytes[2], seg_stages[2];
+    int seg_chunks[4], seg_ck[4], seg_rowbytes[4], seg_layout[4], seg_bstage[4], seg_abytes[4], seg_stages[4];   // per weight segment
+    uint32_t seg_woff[4];  // byte offset of the segment's first stage inside a packed weight block
+    int n_ops;             // input operands; operand o multiplies weight segment op_wseg[o], starts at channel op_c0[o]
+    int op_wseg[6], op_c0[6];
     int kh, kw;
     int H, W;
     int TW, rows_sub, MT, box_rows;
@@ -189,9 +192,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             const int img = g * P.imgs_per_group + li;
             const int ty = t / P.tiles_x, tx = t - ty * P.tiles_x;
             const int y0 = ty * rows_tile - P.kh / 2, x0 = tx * P.UW - P.kw / 2;
-            uint32_t boff = 0;
-            for (int s = 0; s < P.n_seg; ++s) {
+            for (int o = 0; o < P.n_ops; ++o) {
+                const int s = P.op_wseg[o];
                 const uint32_t abytes = P.seg_abytes[s], bbytes = P.seg_bstage[s];
+                uint32_t boff = P.seg_woff[s];
                 int chunk = 0, kx = 0;
                 for (int local = 0; local < P.seg_stages[s]; ++local) {
                     const uint32_t sa = slots0 + slot * P.slot_bytes;
@@ -201,7 +205,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                             mbar_arrive(full0 + 8 * slot);
                         } else {
                             mbar_expect_tx(full0 + 8 * slot, abytes + (P.resident ? 0 : bbytes));
-                            tma_load_4d(&P.tmap[s], full0 + 8 * slot, sa, chunk * P.seg_ck[s], x0 + kx, y0, img);
+                            tma_load_4d(&P.tmap[o], full0 + 8 * slot, sa, P.op_c0[o] + chunk * P.seg_ck[s], x0 + kx, y0, img);
                             if (!P.resident) bulk_load(sa + abytes, wsrc + boff, bbytes, full0 + 8 * slot);
                         }
                     }
@@ -238,9 +242,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1, P.dbg, 3, dead);
             tc_fence_after();
             const uint32_t d0 = tmem_base + acc * P.acc_cols;
-            uint32_t boff = 0;
             bool first = true;
-            for (int s = 0; s < P.n_seg; ++s) {
+            for (int o = 0; o < P.n_ops; ++o) {
+                const int s = P.op_wseg[o];
+                uint32_t boff = P.seg_woff[s];
                 const uint32_t rb = P.seg_rowbytes[s];
                 const uint32_t desc_hi = ((rb * 8u) >> 4) | (1u << 14) | ((uint32_t)P.seg_layout[s] << 29);
                 const uint32_t a_ky = (P.TW * rb) >> 4, b_ky = (P.ns * rb) >> 4, a_m = (P.rows_sub * P.TW * rb) >> 4;
@@ -533,7 +538,7 @@ int launch_conv_tc(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t stre
     // EPI_NHWC tiles leave through two swizzled staging buffers and TMA stores (full-line, asynchronous
     // writes); needs positive 16-byte-multiple strides.  VSRB_TC_DIRECT_STORE=1 forces per-thread stores.
     const long long oimg = P.epi.out_img_stride, ogrp = P.epi.out_group_stride;
-    bool staged = a->epilogue == VSRB_EPI_NHWC && oimg > 0 && ogrp > 0 && oimg % 8 == 0 && ogrp % 8 == 0 &&
+    bool staged = a->epilogue == VSRB_EPI_NHWC && oimg > 0 && ogrp > 0 && oimg % 8 == 0 && ogrp % 8 == 0 && !a->split &&
                   (reinterpret_cast<uintptr_t>(a->out) & 15) == 0 && !getenv("VSRB_TC_DIRECT_STORE");
     P.n_store = (p.n_tile % 64 == 0) ? 64 : ((p.n_tile % 32 == 0) ? 32 : 16);   // store block must divide n_tile
     if (p.pixshuf && p.cout / 4 < P.n_store) P.n_store = p.cout / 4;
@@ -590,10 +595,21 @@ int launch_conv_tc(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t stre
     P.tiles_x = ceil_div(a->w, P.UW);
     P.tiles_per_img = P.tiles_x * ceil_div(a->h, P.rows_sub * P.MT);
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    for (int s = 0; s < p.n_seg; ++s) {
-        const SegPlan& sp = p.seg[s];
-        P.seg_chunks[s] = sp.chunks; P.seg_ck[s] = sp.ck; P.seg_rowbytes[s] = sp.rowbytes;
-        P.seg_layout[s] = sp.layout; P.seg_bstage[s] = p.b_stage_bytes[s]; P.seg_stages[s] = sp.chunks * P.kxs;
+    {
+        uint32_t woff = 0;
+        for (int s = 0; s < p.n_seg; ++s) {
+            const SegPlan& sp = p.seg[s];
+            P.seg_chunks[s] = sp.chunks; P.seg_ck[s] = sp.ck; P.seg_rowbytes[s] = sp.rowbytes;
+            P.seg_layout[s] = sp.layout; P.seg_bstage[s] = p.b_stage_bytes[s]; P.seg_stages[s] = sp.chunks * P.kxs;
+            P.seg_woff[s] = woff;
+            woff += (uint32_t)P.seg_stages[s] * (uint32_t)p.b_stage_bytes[s];
+        }
+    }
+    P.n_ops = a->n_in ? a->n_in : p.n_seg;
+    for (int s = 0; s < P.n_ops; ++s) {            // s = operand index
+        P.op_wseg[s] = a->n_in ? a->in_wseg[s] : s;
+        P.op_c0[s] = a->n_in ? a->in_c0[s] : 0;
+        const SegPlan& sp = p.seg[P.op_wseg[s]];
         cuuint64_t dims[4] = {(cuuint64_t)a->in_c[s], (cuuint64_t)a->w, (cuuint64_t)a->h, (cuuint64_t)a->batch};
         cuuint64_t strides[3] = {(cuuint64_t)a->in_c[s] * 2, (cuuint64_t)a->w * a->in_c[s] * 2,
                                  (cuuint64_t)a->h * a->w * a->in_c[s] * 2};

@@ -81,14 +81,17 @@ struct WarpTap {
 };
 
 // TPP = 16-byte vectors per pixel (C / VEC); a power of two here so the work split is shifts only
-template <typename T, int TPP>
+// kSplit (bf16 only): the tensor is split-bf16 [hi C | lo C] per pixel (value = hi + lo); taps are blended on
+// the fp32 sum and the result is split again, so the warp keeps fp32-level accuracy.  tpp counts C / 8.
+template <typename T, int TPP, bool kSplit = false>
 __global__ void __launch_bounds__(256) flow_warp_kernel(const T* __restrict__ x, long long x_stride,
                                                         const float2* __restrict__ flow, long long f_stride,
                                                         T* __restrict__ out, int n, int h, int w, int border, int tpp_rt) {
     __shared__ WarpTap taps[kWarpPix];
     constexpr int VEC = Vec16<T>::N;
     const int tpp = TPP > 0 ? TPP : tpp_rt;            // TPP == 0: any channel count (runtime divisions)
-    const int C = tpp * VEC;
+    const int half = tpp * VEC;                        // channels of one half when kSplit
+    const int C = kSplit ? 2 * half : half;
     const int hw = h * w;
     const int total = n * hw;                          // launcher guarantees < 2^31
     const int pix0 = blockIdx.x * kWarpPix;
@@ -120,11 +123,28 @@ __global__ void __launch_bounds__(256) flow_warp_kernel(const T* __restrict__ x,
             if (wt.t.off[k] >= 0) {
                 float v[VEC];
                 Vec16<T>::load(img + (long long)wt.t.off[k] * C, v);
+                if (kSplit) {
+                    float lo[VEC];
+                    Vec16<T>::load(img + (long long)wt.t.off[k] * C + half, lo);
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) v[j] += lo[j];
+                }
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) acc[j] = fmaf(v[j], wt.t.wgt[k], acc[j]);
             }
         }
-        Vec16<T>::store(out + (long long)(pix0 + lp) * C + part * VEC, acc);
+        if (kSplit) {
+            float hi[VEC], lo[VEC];
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                hi[j] = (float)(T)acc[j];
+                lo[j] = acc[j] - hi[j];
+            }
+            Vec16<T>::store(out + (long long)(pix0 + lp) * C + part * VEC, hi);
+            Vec16<T>::store(out + (long long)(pix0 + lp) * C + half + part * VEC, lo);
+        } else {
+            Vec16<T>::store(out + (long long)(pix0 + lp) * C + part * VEC, acc);
+        }
     }
 }
 
@@ -162,6 +182,41 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict
             float v = k < c ? __ldg(sp + k * plane) : 0.f;
             dp[k] = (T)v;
         }
+    }
+}
+
+// split-bf16: channels [0, c_dst/2) hold hi = bf16(v), channels [c_dst/2, c_dst) hold lo = bf16(v - hi)
+__global__ void nchw_to_nhwc_split_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int n, int c, int h, int w,
+                                          int c_dst) {
+    const long long plane = (long long)h * w;
+    const long long total = (long long)n * plane;
+    const int half = c_dst / 2;
+    for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < total;
+         pix += (long long)gridDim.x * blockDim.x) {
+        const long long img = pix / plane, r = pix - img * plane;
+        const float* sp = src + img * c * plane + r;
+        __nv_bfloat16* dp = dst + pix * c_dst;
+        for (int k = 0; k < half; ++k) {
+            const float v = k < c ? __ldg(sp + k * plane) : 0.f;
+            const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+            dp[k] = hi;
+            dp[half + k] = __float2bfloat16_rn(v - __bfloat162float(hi));
+        }
+    }
+}
+
+__global__ void nhwc_split_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int n, int c, int h, int w,
+                                          int c_src) {
+    const long long plane = (long long)h * w;
+    const long long total = (long long)n * c * plane;
+    const int half = c_src / 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i % plane;
+        const long long nc = i / plane;
+        const int k = (int)(nc % c);
+        const long long img = nc / c;
+        const __nv_bfloat16* p = src + (img * plane + r) * c_src;
+        dst[i] = __bfloat162float(p[k]) + __bfloat162float(p[half + k]);
     }
 }
 
@@ -232,7 +287,8 @@ __device__ __forceinline__ void up_tap_ac(int dst, int in_size, int out_size, in
 template <typename T>
 __global__ void level_input_kernel(const float4* __restrict__ lvl, const int* __restrict__ ref_idx,
                                    const int* __restrict__ supp_idx, const float2* __restrict__ flow_prev,
-                                   float2* __restrict__ flow_up, T* __restrict__ conv_in, int P, int Hl, int Wl, int c_in) {
+                                   float2* __restrict__ flow_up, T* __restrict__ conv_in, int P, int Hl, int Wl, int c_in,
+                                   int split) {
     const long long plane = (long long)Hl * Wl;
     const long long total = (long long)P * plane;
     const int Hi = Hl / 2, Wi = Wl / 2;
@@ -271,7 +327,16 @@ __global__ void level_input_kernel(const float4* __restrict__ lvl, const int* __
         const float4 r = __ldg(lvl + (long long)__ldg(ref_idx + p) * plane + (long long)Y * Wl + X);
         float v[16] = {r.x, r.y, r.z, wr, wg, wb, fu.x, fu.y, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         T* op = conv_in + i * c_in;
-        if (c_in == 16) Act<T>::store16(op, v);
+        if (split) {                                   // [hi 16 | lo 16]
+            float hi[16], lo[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                hi[k] = (float)(T)v[k];
+                lo[k] = v[k] - hi[k];
+            }
+            Act<T>::store16(op, hi);
+            Act<T>::store16(op + 16, lo);
+        } else if (c_in == 16) Act<T>::store16(op, v);
         else {
             for (int k = 0; k < c_in; ++k) op[k] = (T)(k < 8 ? v[k] : 0.f);
         }
@@ -327,6 +392,12 @@ int vsrb_flow_warp(const void* x, int64_t x_img_stride, const float* flow, int64
         VSRB_CHECK_ARG(c % 8 == 0, "flow_warp: bf16 needs c %% 8 == 0 (got %d)", c);
         rc = launch_flow_warp<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(x), xs, reinterpret_cast<const float2*>(flow), fs,
                                              reinterpret_cast<__nv_bfloat16*>(out), n, h, w, c, padding_mode, s);
+    } else if (dtype == VSRB_BF16X2) {
+        VSRB_CHECK_ARG(c % 16 == 0, "flow_warp: split-bf16 needs c %% 16 == 0 (got %d)", c);
+        const int blocks = (int)(((long long)n * h * w + kWarpPix - 1) / kWarpPix);
+        flow_warp_kernel<__nv_bfloat16, 0, true><<<blocks, 256, 0, s>>>(
+            reinterpret_cast<const __nv_bfloat16*>(x), xs, reinterpret_cast<const float2*>(flow), fs,
+            reinterpret_cast<__nv_bfloat16*>(out), n, h, w, padding_mode, c / 16);
     } else if (dtype == VSRB_F32) {
         VSRB_CHECK_ARG(c % 4 == 0, "flow_warp: fp32 needs c %% 4 == 0 (got %d)", c);
         rc = launch_flow_warp<float>(reinterpret_cast<const float*>(x), xs, reinterpret_cast<const float2*>(flow), fs,
@@ -344,7 +415,10 @@ int vsrb_nchw_to_nhwc(const float* src, void* dst, int32_t n, int32_t c, int32_t
     VSRB_CHECK_ARG(src && dst && n >= 1 && c >= 1 && c_dst >= c, "nchw_to_nhwc: bad arguments");
     const long long total = (long long)n * h * w;
     cudaStream_t s = (cudaStream_t)stream;
-    if (dtype == VSRB_BF16)
+    if (dtype == VSRB_BF16X2) {
+        VSRB_CHECK_ARG(c_dst % 2 == 0 && c_dst / 2 >= c, "nchw_to_nhwc: split layout needs c_dst = 2 * padded channels");
+        nchw_to_nhwc_split_kernel<<<grid_for(total, 256), 256, 0, s>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n, c, h, w, c_dst);
+    } else if (dtype == VSRB_BF16)
         nchw_to_nhwc_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, s>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n, c, h,
                                                                                  w, c_dst);
     else
@@ -358,7 +432,11 @@ int vsrb_nhwc_to_nchw(const void* src, float* dst, int32_t n, int32_t c, int32_t
     VSRB_CHECK_ARG(src && dst && n >= 1 && c >= 1 && c_src >= c, "nhwc_to_nchw: bad arguments");
     const long long total = (long long)n * c * h * w;
     cudaStream_t s = (cudaStream_t)stream;
-    if (dtype == VSRB_BF16)
+    if (dtype == VSRB_BF16X2) {
+        VSRB_CHECK_ARG(c_src % 2 == 0 && c_src / 2 >= c, "nhwc_to_nchw: split layout needs c_src = 2 * padded channels");
+        nhwc_split_to_nchw_kernel<<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(src), dst, n, c, h, w,
+                                                                        c_src);
+    } else if (dtype == VSRB_BF16)
         nhwc_to_nchw_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(src), dst, n,
                                                                                  c, h, w, c_src);
     else
@@ -399,12 +477,17 @@ int vsrb_spynet_level_input(const float* lvl, const int32_t* ref_idx, const int3
         VSRB_CHECK_ARG(c_in == 16, "level_input: bf16 path expects 16 allocated channels");
         level_input_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, s>>>(
             reinterpret_cast<const float4*>(lvl), ref_idx, supp_idx, reinterpret_cast<const float2*>(flow_prev),
-            reinterpret_cast<float2*>(flow_up), reinterpret_cast<__nv_bfloat16*>(conv_in), P, Hl, Wl, c_in);
+            reinterpret_cast<float2*>(flow_up), reinterpret_cast<__nv_bfloat16*>(conv_in), P, Hl, Wl, c_in, 0);
+    } else if (dtype == VSRB_BF16X2) {
+        VSRB_CHECK_ARG(c_in == 32, "level_input: split-bf16 path expects 2 x 16 allocated channels");
+        level_input_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, s>>>(
+            reinterpret_cast<const float4*>(lvl), ref_idx, supp_idx, reinterpret_cast<const float2*>(flow_prev),
+            reinterpret_cast<float2*>(flow_up), reinterpret_cast<__nv_bfloat16*>(conv_in), P, Hl, Wl, c_in, 1);
     } else {
         VSRB_CHECK_ARG(c_in % 4 == 0, "level_input: fp32 channel stride must be %% 4");
         level_input_kernel<float><<<grid_for(total, 256), 256, 0, s>>>(
             reinterpret_cast<const float4*>(lvl), ref_idx, supp_idx, reinterpret_cast<const float2*>(flow_prev),
-            reinterpret_cast<float2*>(flow_up), reinterpret_cast<float*>(conv_in), P, Hl, Wl, c_in);
+            reinterpret_cast<float2*>(flow_up), reinterpret_cast<float*>(conv_in), P, Hl, Wl, c_in, 0);
     }
     VSRB_LAUNCH_CHECK();
     return VSRB_OK;

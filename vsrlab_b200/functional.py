@@ -21,11 +21,14 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 
 from . import ops
-from ._lib import (ACT_LRELU, ACT_NONE, ACT_RELU, BF16, EPI_CLEAN, EPI_FLOW, EPI_NHWC, EPI_SR, F32, PAD_BORDER, PAD_ZEROS,
-                   VsrbError)
+from ._lib import (ACT_LRELU, ACT_NONE, ACT_RELU, BF16, BF16X2, EPI_CLEAN, EPI_FLOW, EPI_NHWC, EPI_SR, F32, PAD_BORDER,
+                   PAD_ZEROS, VsrbError)
 
 _forced: Optional[int] = None
-_NAMES = {"bf16": BF16, "fp32": F32, "f32": F32}
+# "fp32" = fp32-accurate mode.  Default implementation: split-bf16 (x = hi + lo) on the tensor cores, three MMA passes
+# per product (hi*hi + lo*hi + hi*lo), fp32 accumulate; VSRB_FP32_IMPL=ffma selects the plain FFMA kernel instead.
+_FP32 = F32 if os.environ.get("VSRB_FP32_IMPL", "x3") == "ffma" else BF16X2
+_NAMES = {"bf16": BF16, "fp32": _FP32, "f32": _FP32, "fp32_ffma": F32, "fp32_x3": BF16X2}
 
 # tunables: frames / images per launch batch.  Measured on B200 (gpurun_out bench4*): the ~8 us fixed cost per
 # launch outweighs L2 residency, so batches are large; the tail is capped by the HR buffers (118 MB per frame).
@@ -56,7 +59,7 @@ def current_dtype() -> int:
     env = os.environ.get("VSRLAB_B200_PRECISION")
     if env:
         return _NAMES[env]
-    return BF16 if torch.is_autocast_enabled() else F32
+    return BF16 if torch.is_autocast_enabled() else _FP32
 
 
 # --------------------------------------------------------------------------------------
@@ -117,6 +120,8 @@ def _wants_grad(mod: torch.nn.Module) -> bool:
 
 def _act_c(c: int, dt: int) -> int:
     """channels allocated per pixel for a c-channel activation"""
+    if dt == BF16X2:
+        return 2 * ((c + 15) // 16 * 16)       # [hi | lo]
     return (c + 15) // 16 * 16 if dt == BF16 else (c + 3) // 4 * 4
 
 
@@ -149,7 +154,7 @@ def conv2d(x: torch.Tensor, conv: torch.nn.Conv2d, act: str = "none", slope: flo
     pc = packed([conv], [(0, c)], dt, pixel_shuffle)
     r = pixel_shuffle or 1
     co = conv.out_channels // (r * r)
-    oc = _act_c(co, dt) if r > 1 else pc.cout_pad
+    oc = _act_c(co, dt) if (r > 1 or dt == BF16X2) else pc.cout_pad
     out = ws("m_out", (n, h * r, w * r, oc), ops.TORCH_DT[dt], x.device)
     ops.conv2d_fwd(pc, [xin], [ca], n, h, w, act=_ACTS[act], slope=slope, out=out, out_c=oc)
     return _to_nchw(out, n, co, h * r, w * r, oc, dt)
@@ -163,7 +168,7 @@ def conv_chain(x: torch.Tensor, convs: Sequence[torch.nn.Conv2d], act: str = "re
     cur, ca = _to_nhwc(x, dt, "m_in")
     for j, conv in enumerate(convs):
         pc = packed([conv], [(0, conv.in_channels)], dt)
-        oc = pc.cout_pad
+        oc = _act_c(conv.out_channels, dt) if dt == BF16X2 else pc.cout_pad
         out = ws(f"m_chain{j % 2}", (n, h, w, oc), ops.TORCH_DT[dt], x.device)
         ops.conv2d_fwd(pc, [cur], [ca], n, h, w, act=_ACTS[act], out=out, out_c=oc)
         cur, ca = out, oc
@@ -226,11 +231,14 @@ def flow_warp(x: torch.Tensor, flow: torch.Tensor, padding_mode: str = "zeros") 
     flow = _check_input(flow, "flow").contiguous()
     dt = current_dtype()
     n, c, h, w = x.shape
-    vec = 8 if dt == BF16 else 4
-    nv = 1
-    while nv * vec < c:                    # the kernel splits a pixel over a power-of-two number of 16-byte vectors
-        nv *= 2
-    ca = nv * vec
+    if dt == BF16X2:
+        ca = _act_c(c, dt)
+    else:
+        vec = 8 if dt == BF16 else 4
+        nv = 1
+        while nv * vec < c:                # the kernel splits a pixel over a power-of-two number of 16-byte vectors
+            nv *= 2
+        ca = nv * vec
     xin, _ = _to_nhwc(x, dt, "m_in", ca)
     out = ws("m_out", (n, h, w, ca), ops.TORCH_DT[dt], x.device)
     ops.flow_warp(xin, flow, out, n, h, w, ca, dt, PAD_BORDER if padding_mode == "border" else PAD_ZEROS)
@@ -268,7 +276,7 @@ def _spynet_run(sp, frames: torch.Tensor, ref_idx: torch.Tensor, supp_idx: torch
     for k in range(1, 6):
         ops.avgpool2_c4(lv[k - 1], lv[k], F_, Hp >> (k - 1), Wp >> (k - 1))
     P = ref_idx.numel()
-    cin0 = 16 if dt == BF16 else 8
+    cin0 = {BF16: 16, F32: 8, BF16X2: 32}[dt]
     chans = [cin0, _act_c(32, dt), _act_c(64, dt), _act_c(32, dt), _act_c(16, dt)]
     full = [ws(f"sp_act{j}", (P, Hp, Wp, chans[j]), tdt, dev) for j in range(5)]
     fup_full = ws("sp_fup", (P, Hp, Wp, 2), torch.float32, dev)

@@ -10,10 +10,12 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib as L
-from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, BF16, EPI_CLEAN, EPI_FLOW, EPI_NHWC, EPI_SR, F32, PAD_BORDER, PAD_ZEROS
+from ._lib import (ACT_LRELU, ACT_NONE, ACT_RELU, BF16, BF16X2, EPI_CLEAN, EPI_FLOW, EPI_NHWC, EPI_SR, F32, PAD_BORDER,
+                   PAD_ZEROS)
 
-TORCH_DT = {BF16: torch.bfloat16, F32: torch.float32}
-ESIZE = {BF16: 2, F32: 4}
+# BF16X2 = split-bf16 (fp32-accurate tensor-core mode): per pixel [hi C | lo C] bf16, value = hi + lo
+TORCH_DT = {BF16: torch.bfloat16, F32: torch.float32, BF16X2: torch.bfloat16}
+ESIZE = {BF16: 2, F32: 4, BF16X2: 2}
 
 
 # bench.py sets this to a list to time every launch with CUDA events on the launching stream:
@@ -68,6 +70,21 @@ class PackedConv:
         w0 = convs[0].weight
         require_cuda(w0, "conv weight")
         cout, cin, kh, kw = w0.shape
+        self.split = dtype == BF16X2
+        self.real_segs = tuple(segs)
+        w = torch.stack([c.weight.detach().to(torch.float32) for c in convs]).contiguous()
+        if self.split:
+            # fp32-accurate mode: W = W_hi + W_lo (both bf16); every real segment becomes two weight segments
+            # [W_hi | W_lo]; the launcher feeds (x_hi, W_hi), (x_lo, W_hi), (x_hi, W_lo) - the lo*lo term is dropped
+            parts, new_segs, o = [], [], 0
+            for off, c in segs:
+                ws = w[:, :, off:off + c]
+                hi = ws.to(torch.bfloat16).to(torch.float32)
+                parts += [hi, ws - hi]
+                new_segs += [(o, c), (o + c, c)]
+                o += 2 * c
+            w = torch.cat(parts, 2).contiguous()
+            segs, cin, dtype = new_segs, o, BF16
         g = L.ConvGeom()
         g.kh, g.kw, g.n_seg = kh, kw, len(segs)
         for i, (off, c) in enumerate(segs):
@@ -79,7 +96,6 @@ class PackedConv:
         self.dtype = dtype
         self.stamp = self.stamp_of(convs)
         self.uses = 0            # launches since packing; PDL is enabled from the second one on
-        w = torch.stack([c.weight.detach().to(torch.float32) for c in convs]).contiguous()
         b = None
         if convs[0].bias is not None:
             b = torch.stack([c.bias.detach().to(torch.float32) for c in convs]).contiguous()
@@ -102,9 +118,21 @@ def conv2d_fwd(pc: PackedConv, ins: Sequence, in_c: Sequence[int], batch: int, h
     (or raw int device addresses) that the caller keeps alive."""
     a = L.ConvArgs()
     a.geom = pc.geom
-    for i, t in enumerate(ins):
-        a.inp[i] = t if isinstance(t, int) else t.data_ptr()
-        a.in_c[i] = in_c[i]
+    if pc.split:
+        # inputs are split-bf16 tensors [hi Cp | lo Cp]; three operands per real segment share two weight segments
+        k = 0
+        for i, t in enumerate(ins):
+            ptr = t if isinstance(t, int) else t.data_ptr()
+            cp = in_c[i] // 2
+            for c0, wseg in ((0, 2 * i), (cp, 2 * i), (0, 2 * i + 1)):
+                a.inp[k], a.in_c[k], a.in_c0[k], a.in_wseg[k] = ptr, in_c[i], c0, wseg
+                k += 1
+        a.n_in = k
+        a.split = 1 if epilogue in (EPI_NHWC, EPI_CLEAN) else 0
+    else:
+        for i, t in enumerate(ins):
+            a.inp[i] = t if isinstance(t, int) else t.data_ptr()
+            a.in_c[i] = in_c[i]
     a.batch, a.h, a.w = batch, h, w
     a.imgs_per_group = imgs_per_group if imgs_per_group is not None else batch // pc.geom.groups
     a.packed = pc.buf.data_ptr()
@@ -121,8 +149,8 @@ def conv2d_fwd(pc: PackedConv, ins: Sequence, in_c: Sequence[int], batch: int, h
     a.flags = L.CONV_PDL if (pc.uses > 0 and PDL) else 0
     pc.uses += 1
     g = pc.geom
-    flops = 2.0 * batch * h * w * pc.cout * (g.seg_c[0] + (g.seg_c[1] if g.n_seg == 2 else 0)) * pc.kh * pc.kw
-    with _Timed("conv_tc" if pc.dtype == BF16 else "conv_f32", flops):
+    flops = 2.0 * batch * h * w * pc.cout * sum(c for _, c in pc.real_segs) * pc.kh * pc.kw   # algorithmic (not x3)
+    with _Timed(("conv_tc_x3" if pc.split else "conv_tc") if pc.dtype == BF16 else "conv_f32", flops):
         L.check(L.load().vsrb_conv2d_fwd(C.byref(a), _stream()), "vsrb_conv2d_fwd")
 
 
@@ -196,6 +224,8 @@ class PackedConvT(PackedConv):
         self.dtype = dtype
         self.stamp = self.stamp_of([conv])
         self.uses = 0
+        self.split = False
+        self.real_segs = ((0, cout),)
         w = w0.detach().to(torch.float32).contiguous()
         nbytes = lib.vsrb_packed_weight_bytes(C.byref(g))
         if nbytes == 0:
