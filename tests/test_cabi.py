@@ -51,7 +51,7 @@ def test_version_and_geometry_helpers_run_on_cpu(lib):
 def test_struct_layout_matches_header(lib):
     """ctypes mirrors of the C structs: sizes follow the C layout rules of the header."""
     from vsrlab_b200 import _lib
-    assert C.sizeof(_lib.ConvGeom) == 12 * 4
+    assert C.sizeof(_lib.ConvGeom) == 16 * 4          # kh kw n_seg seg_c[4] seg_off[4] cout pixshuf groups dtype transpose
     assert C.sizeof(_lib.ConvArgs) % 8 == 0
     assert _lib.ConvArgs.packed.offset % 8 == 0 and _lib.ConvArgs.out_img_stride.offset % 8 == 0
 
