@@ -506,9 +506,14 @@ int launch_conv_tc(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t stre
         void* ip = nullptr;
         VSRB_CUDA(cudaGetSymbolAddress(&ip, g_identity));
         g_ident_ptr[dev] = reinterpret_cast<const uint8_t*>(ip);
-        // legacy default stream: ordered before every later launch of this process on this device
+        // one-time: finish before any other stream of this process can launch a conv that reads it
         fill_identity_kernel<<<16, 256, 0, stream>>>();
         VSRB_LAUNCH_CHECK();
+        {
+            cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+            cudaStreamIsCapturing(stream, &cap);
+            if (cap == cudaStreamCaptureStatusNone) VSRB_CUDA(cudaStreamSynchronize(stream));
+        }
         g_dev_ready[dev] = true;
     }
     TcParams P;

@@ -49,25 +49,29 @@ struct WgradParams {
     float* dw;
 };
 
-template <typename T, int KW>
+// CO_T x CI_T = the (co, ci) tile of one CTA (16, 32 or 64 each).  A thread owns a 4x4 patch of it; the 256 threads
+// form 256 / (CO_T/4 * CI_T/4) pixel groups that split the 32 pixels of a chunk between them, so narrow layers
+// (SPyNet's 8->32, 32->16, 16->2 ...) do not pay for a full 64x64 tile.
+template <typename T, int KW, int CO_T, int CI_T>
 __global__ void __launch_bounds__(256) conv_wgrad_kernel(WgradParams P) {
-    __shared__ __align__(16) float zs[32][64];
-    __shared__ __align__(16) float xs[32 + KW - 1][64];
+    constexpr int TY = CO_T / 4, TX = CI_T / 4, TPG = TY * TX, PG = 256 / TPG;
+    __shared__ __align__(16) float zs[32][CO_T];
+    __shared__ __align__(16) float xs[32 + KW - 1][CI_T];
     const int tid = threadIdx.x;
-    const int tx = tid & 15, ty = tid >> 4;             // 4 ci per tx, 4 co per ty
+    const int pg = tid / TPG, rr = tid % TPG;
+    const int tx = rr % TX, ty = rr / TX;               // 4 ci per tx, 4 co per ty
     const int ky = blockIdx.y;
     int z = blockIdx.z;
     const int cib = z % P.n_ci_blk; z /= P.n_ci_blk;
     const int cob = z % P.n_co_blk;
     const int g = z / P.n_co_blk;
     const int s = P.ci_blk_seg[cib], c0 = P.ci_blk_c0[cib];
-    const int co0 = cob * 64;
+    const int co0 = cob * CO_T;
     const int hw = P.H * P.W;
     const int u_begin = blockIdx.x * P.units_per_cta;
     const int u_end = min(u_begin + P.units_per_cta, P.units_g);
     const T* zin = reinterpret_cast<const T*>(P.dz);
     const T* xin = reinterpret_cast<const T*>(P.in[s]);
-    const int lp = tid >> 3, lc = (tid & 7) * 8;        // loader: pixel lp of the chunk, channels lc..lc+8
     const int dy = ky - P.kh / 2, pad = KW / 2;
 
     float acc[KW][4][4];
@@ -84,36 +88,40 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(WgradParams P) {
         const int y = rowi % P.H;
         const long long img = (long long)g * P.imgs_per_group + rowi / P.H;
         const int x0 = xc * 32;
-        float zv[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) zv[i] = 0.f;
-        if (x0 + lp < P.W && co0 + lc < P.dz_c) {
-            Ld8<T>::load(zin + (img * hw + (long long)y * P.W + x0 + lp) * P.dz_c + co0 + lc, zv);
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                if (co0 + lc + i >= P.cout) zv[i] = 0.f;
-        }
-        __syncthreads();
-        *reinterpret_cast<float4*>(&zs[lp][lc]) = make_float4(zv[0], zv[1], zv[2], zv[3]);
-        *reinterpret_cast<float4*>(&zs[lp][lc + 4]) = make_float4(zv[4], zv[5], zv[6], zv[7]);
         const int yy = y + dy;
-        for (int e = lp; e < 32 + KW - 1; e += 32) {     // extended strip: image columns x0 - pad + e
+        __syncthreads();
+        for (int i = tid; i < 32 * (CO_T / 8); i += 256) {          // dz chunk [32 px][CO_T]
+            const int lp = i / (CO_T / 8), lc = (i % (CO_T / 8)) * 8;
+            float zv[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) zv[e] = 0.f;
+            if (x0 + lp < P.W && co0 + lc < P.dz_c) {
+                Ld8<T>::load(zin + (img * hw + (long long)y * P.W + x0 + lp) * P.dz_c + co0 + lc, zv);
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    if (co0 + lc + e >= P.cout) zv[e] = 0.f;
+            }
+            *reinterpret_cast<float4*>(&zs[lp][lc]) = make_float4(zv[0], zv[1], zv[2], zv[3]);
+            *reinterpret_cast<float4*>(&zs[lp][lc + 4]) = make_float4(zv[4], zv[5], zv[6], zv[7]);
+        }
+        for (int i = tid; i < (32 + KW - 1) * (CI_T / 8); i += 256) {   // extended strip: image columns x0 - pad + e
+            const int ep = i / (CI_T / 8), lc = (i % (CI_T / 8)) * 8;
             float xv[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) xv[i] = 0.f;
-            const int xx = x0 - pad + e;
+            for (int e = 0; e < 8; ++e) xv[e] = 0.f;
+            const int xx = x0 - pad + ep;
             if (yy >= 0 && yy < P.H && xx >= 0 && xx < P.W && c0 + lc < P.in_c[s]) {
                 Ld8<T>::load(xin + (img * hw + (long long)yy * P.W + xx) * P.in_c[s] + c0 + lc, xv);
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    if (c0 + lc + i >= P.seg_c[s]) xv[i] = 0.f;
+                for (int e = 0; e < 8; ++e)
+                    if (c0 + lc + e >= P.seg_c[s]) xv[e] = 0.f;
             }
-            *reinterpret_cast<float4*>(&xs[e][lc]) = make_float4(xv[0], xv[1], xv[2], xv[3]);
-            *reinterpret_cast<float4*>(&xs[e][lc + 4]) = make_float4(xv[4], xv[5], xv[6], xv[7]);
+            *reinterpret_cast<float4*>(&xs[ep][lc]) = make_float4(xv[0], xv[1], xv[2], xv[3]);
+            *reinterpret_cast<float4*>(&xs[ep][lc + 4]) = make_float4(xv[4], xv[5], xv[6], xv[7]);
         }
         __syncthreads();
-#pragma unroll 4
-        for (int q = 0; q < 32; ++q) {
+#pragma unroll 2
+        for (int q = pg; q < 32; q += PG) {
             const float4 a = *reinterpret_cast<const float4*>(&zs[q][ty * 4]);
             const float av[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
@@ -300,13 +308,23 @@ int vsrb_conv2d_wgrad(const vsrb_conv_geom* g, const void* const* in, const int3
     // the FLOPs; a cout below 64 is zero-filled by the TMA box) run on the tensor cores; everything else on the
     // FFMA kernel
     const bool tc_ok = g->dtype == VSRB_BF16 && g->kh == 3 && g->kw == 3 && g->groups == 1 && dz_c >= g->cout &&
-                       !getenv("VSRB_WGRAD_SIMT");
+                       (reinterpret_cast<uintptr_t>(dz) & 15) == 0 && !getenv("VSRB_WGRAD_SIMT");
+    bool on_tc[4] = {false, false, false, false};
+    // (co, ci) tile of the FFMA kernel: as narrow as its segments allow (bf16 only; fp32 keeps 64 x 64)
+    int co_t = 64, ci_t = 64, cmax = 0;
+    for (int s = 0; s < g->n_seg; ++s) {
+        on_tc[s] = tc_ok && g->seg_c[s] % 64 == 0 && (reinterpret_cast<uintptr_t>(in[s]) & 15) == 0;
+        if (!on_tc[s] && g->seg_c[s] > cmax) cmax = g->seg_c[s];
+    }
+    if (g->dtype == VSRB_BF16) {
+        co_t = g->cout <= 16 ? 16 : (g->cout <= 32 ? 32 : 64);
+        ci_t = cmax <= 16 ? 16 : (cmax <= 32 ? 32 : 64);
+    }
     for (int s = 0; s < g->n_seg; ++s) {
         VSRB_CHECK_ARG(in[s] && in_c[s] % 8 == 0 && in_c[s] >= g->seg_c[s], "wgrad: bad input segment %d", s);
         VSRB_CHECK_ARG(g->seg_off[s] + g->seg_c[s] <= cin_total, "wgrad: segment %d exceeds cin_total", s);
         P.in[s] = in[s]; P.in_c[s] = in_c[s]; P.seg_c[s] = g->seg_c[s]; P.seg_off[s] = g->seg_off[s];
-        if (tc_ok && g->seg_c[s] % 64 == 0 && (reinterpret_cast<uintptr_t>(in[s]) & 15) == 0 &&
-            (reinterpret_cast<uintptr_t>(dz) & 15) == 0) {
+        if (on_tc[s]) {
             for (int c0 = 0; c0 < g->seg_c[s]; c0 += 64) {
                 int rc = launch_wgrad_tc(in[s], in_c[s], c0, g->seg_off[s] + c0, dz, dz_c, batch, h, w, g->cout, cin_total, dw,
                                          (cudaStream_t)stream);
@@ -314,8 +332,8 @@ int vsrb_conv2d_wgrad(const vsrb_conv_geom* g, const void* const* in, const int3
             }
             continue;
         }
-        for (int c0 = 0; c0 < g->seg_c[s]; c0 += 64) {
-            VSRB_CHECK_ARG(P.n_ci_blk < 8, "wgrad: more than 512 input channels");
+        for (int c0 = 0; c0 < g->seg_c[s]; c0 += ci_t) {
+            VSRB_CHECK_ARG(P.n_ci_blk < 8, "wgrad: too many input-channel blocks");
             P.ci_blk_seg[P.n_ci_blk] = s;
             P.ci_blk_c0[P.n_ci_blk] = c0;
             ++P.n_ci_blk;
@@ -330,7 +348,7 @@ int vsrb_conv2d_wgrad(const vsrb_conv_geom* g, const void* const* in, const int3
     P.dz = dz; P.dz_c = dz_c;
     P.kh = g->kh; P.kw = g->kw; P.H = h; P.W = w; P.imgs_per_group = imgs_per_group; P.groups = g->groups;
     P.cout = g->cout; P.cin_total = cin_total;
-    P.n_co_blk = ceil_div(g->cout, 64);
+    P.n_co_blk = ceil_div(g->cout, co_t);
     P.dw = dw;
     P.chunks_per_row = ceil_div(w, 32);
     const long long units_g = (long long)imgs_per_group * h * P.chunks_per_row;
@@ -344,16 +362,31 @@ int vsrb_conv2d_wgrad(const vsrb_conv_geom* g, const void* const* in, const int3
     P.units_per_cta = (int)per;
     dim3 grid((unsigned)((units_g + per - 1) / per), g->kh, P.n_co_blk * P.n_ci_blk * g->groups);
     cudaStream_t st = (cudaStream_t)stream;
-#define VSRB_WG_LAUNCH(T)                                                        \
-    do {                                                                          \
-        if (g->kw == 1) conv_wgrad_kernel<T, 1><<<grid, 256, 0, st>>>(P);         \
-        else if (g->kw == 3) conv_wgrad_kernel<T, 3><<<grid, 256, 0, st>>>(P);    \
-        else if (g->kw == 5) conv_wgrad_kernel<T, 5><<<grid, 256, 0, st>>>(P);    \
-        else conv_wgrad_kernel<T, 7><<<grid, 256, 0, st>>>(P);                    \
+#define VSRB_WG_KW(T, CO, CI)                                                              \
+    do {                                                                                    \
+        if (g->kw == 1) conv_wgrad_kernel<T, 1, CO, CI><<<grid, 256, 0, st>>>(P);           \
+        else if (g->kw == 3) conv_wgrad_kernel<T, 3, CO, CI><<<grid, 256, 0, st>>>(P);      \
+        else if (g->kw == 7) conv_wgrad_kernel<T, 7, CO, CI><<<grid, 256, 0, st>>>(P);      \
+        else {                                                                              \
+            set_error("wgrad: kernel width %d unsupported", g->kw);                         \
+            return VSRB_E_ARG;                                                              \
+        }                                                                                   \
     } while (0)
-    if (g->dtype == VSRB_BF16) VSRB_WG_LAUNCH(__nv_bfloat16);
-    else VSRB_WG_LAUNCH(float);
-#undef VSRB_WG_LAUNCH
+#define VSRB_WG_CI(T, CO)                                  \
+    do {                                                    \
+        if (ci_t == 16) VSRB_WG_KW(T, CO, 16);              \
+        else if (ci_t == 32) VSRB_WG_KW(T, CO, 32);         \
+        else VSRB_WG_KW(T, CO, 64);                         \
+    } while (0)
+    if (g->dtype == VSRB_BF16) {
+        if (co_t == 16) VSRB_WG_CI(__nv_bfloat16, 16);
+        else if (co_t == 32) VSRB_WG_CI(__nv_bfloat16, 32);
+        else VSRB_WG_CI(__nv_bfloat16, 64);
+    } else {
+        VSRB_WG_KW(float, 64, 64);
+    }
+#undef VSRB_WG_CI
+#undef VSRB_WG_KW
     VSRB_LAUNCH_CHECK();
     return VSRB_OK;
 }
