@@ -272,8 +272,15 @@ def main():
     torch.cuda.synchronize()
     prof, ops.PROFILE = ops.PROFILE, None
     fam, parts = {}, {}
+    shapes = {}
     for kind, ev0, ev1, work_units, tag in prof:
         sec = ev0.elapsed_time(ev1) * 1e-3
+        if "[" in kind:                                   # VSRB_PROFILE_SHAPES=1: per-shape table, family key without the shape
+            q = shapes.setdefault(tag + " " + kind, [0.0, 0.0, 0])
+            q[0] += sec
+            q[1] += work_units
+            q[2] += 1
+            kind = kind.split("[")[0]
         d = fam.setdefault(kind, [0.0, 0.0, 0])
         d[0] += sec
         d[1] += work_units
@@ -347,6 +354,9 @@ def main():
             "conv_by_part": {k: {"ms": round(v[0] * 1e3, 3), "tflops": round(v[1] / v[0] / 1e12, 1), "launches": v[2]}
                              for k, v in parts.items()},
         }
+        if shapes:
+            line["conv_by_shape"] = {k: {"ms": round(v[0] * 1e3, 3), "tflops": round(v[1] / v[0] / 1e12, 1), "launches": v[2]}
+                                     for k, v in sorted(shapes.items(), key=lambda kv: -kv[1][0])}
         if world == 1 and not a.no_cpu_baseline:
             cores = os.cpu_count() or 1
             v, dtc = oracle_sample(a.blocks, 3, cores)

@@ -12,7 +12,7 @@ import torch
 ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
 from vsrlab_b200 import ops  # noqa: E402
-from vsrlab_b200._lib import ACT_NONE, ACT_RELU, BF16  # noqa: E402
+from vsrlab_b200._lib import ACT_NONE, ACT_RELU, BF16, EPI_SR  # noqa: E402
 
 dev = torch.device("cuda:0")
 
@@ -32,11 +32,15 @@ CASES = {
     "sp_7x7_8_32": (8, 32, 7, 58, 192, 320, False, 0),
     "pt_1x1_128_64": (128, 64, 1, 6, 180, 320, False, 0),
     "stem_3_64": (3, 64, 3, 6, 180, 320, False, 0),
+    "stem_3_64_30f": (3, 64, 3, 30, 180, 320, False, 0),
+    "sr_64_3": (64, 3, 3, 8, 720, 1280, False, -1),     # conv_last: EPI_SR (fp32 NCHW out + bilinear x4 skip)
 }
 
 
 def run_case(name, reps=20):
     cin, cout, k, n, h, w, residual, ps = CASES[name]
+    sr = ps < 0
+    ps = max(ps, 0)
     cv = torch.nn.Conv2d(cin, cout, k, 1, k // 2).to(dev)
     pc = ops.PackedConv([cv], [(0, cin)], BF16, ps)
     ca = (cin + 15) // 16 * 16
@@ -47,7 +51,14 @@ def run_case(name, reps=20):
     res = torch.randn(n, h, w, oc, device=dev).to(torch.bfloat16) if residual else None
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
+    if sr:
+        sr_out = torch.empty(n, cout, h, w, device=dev)
+        lr = torch.randn(n, cout, h // 4, w // 4, device=dev)
+
     def call():
+        if sr:
+            ops.conv2d_fwd(pc, [x], [ca], n, h, w, act=ACT_NONE, epilogue=EPI_SR, f32_io=sr_out, f32_in=lr, aux_hw=(h // 4, w // 4))
+            return
         ops.conv2d_fwd(pc, [x], [ca], n, h, w, act=ACT_RELU if not residual else ACT_NONE, out=out, out_c=oc, residual=res,
                        res_c=oc if residual else 0)
     for _ in range(3):

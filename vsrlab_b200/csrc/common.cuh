@@ -191,6 +191,35 @@ __device__ __forceinline__ void epi_act16(const EpiParams& e, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], v[i] * k);
 }
 
+// EPI_SR in two halves so a caller can fetch the skip term before its accumulator is ready: the bilinear x(H/aux_h)
+// upsample of the fp32 NCHW LR frame at HR pixel (y, x) (ATen align_corners=False taps) ...
+__device__ __forceinline__ void epi_sr_up(const EpiParams& e, int b, int y, int x, float (&up)[3]) {
+    const int ih = e.aux_h, iw = e.aux_w;
+    const float sy = (float)ih / (float)e.H, sx = (float)iw / (float)e.W;
+    int y0, y1, x0, x1;
+    float ly, lx;
+    up_tap(y, sy, ih, y0, y1, ly);
+    up_tap(x, sx, iw, x0, x1, lx);
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    const size_t iplane = (size_t)ih * iw;
+    const float* lp = e.f32_in + (size_t)b * 3 * iplane;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float* cp = lp + c * iplane;
+        const float a00 = __ldg(cp + y0 * iw + x0), a01 = __ldg(cp + y0 * iw + x1);
+        const float a10 = __ldg(cp + y1 * iw + x0), a11 = __ldg(cp + y1 * iw + x1);
+        up[c] = hy * (hx * a00 + lx * a01) + ly * (hx * a10 + lx * a11);
+    }
+}
+// ... and the fp32 NCHW store of conv + skip
+template <int N>
+__device__ __forceinline__ void epi_sr_store(const EpiParams& e, int b, int y, int x, const float (&v)[N], const float (&up)[3]) {
+    const size_t oplane = (size_t)e.H * e.W;
+    float* op = e.f32_io + (size_t)b * 3 * oplane + (size_t)y * e.W + x;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) op[c * oplane] = v[c] + up[c];
+}
+
 // One pixel (b,y,x), 16 consecutive packed output channels starting at n0 (multiple of 16);
 // v = act(acc + bias) already applied by the caller.  `g` = weight group of image b.
 // kResDone: the caller has already added the residual.
@@ -265,24 +294,9 @@ __device__ __forceinline__ void epi_store16(const EpiParams& e, int g, int b, in
         reinterpret_cast<float2*>(e.f32_io)[pix] = make_float2(f.x + v[0], f.y + v[1]);
     } else {   // VSRB_EPI_SR
         if (n0 != 0) return;
-        int ih = e.aux_h, iw = e.aux_w;
-        float sy = (float)ih / (float)e.H, sx = (float)iw / (float)e.W;
-        int y0, y1, x0, x1;
-        float ly, lx;
-        up_tap(y, sy, ih, y0, y1, ly);
-        up_tap(x, sx, iw, x0, x1, lx);
-        float hy = 1.f - ly, hx = 1.f - lx;
-        size_t iplane = (size_t)ih * iw, oplane = (size_t)e.H * e.W;
-        const float* lp = e.f32_in + (size_t)b * 3 * iplane;
-        float* op = e.f32_io + (size_t)b * 3 * oplane + (size_t)y * e.W + x;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float* cp = lp + c * iplane;
-            float a00 = __ldg(cp + y0 * iw + x0), a01 = __ldg(cp + y0 * iw + x1);
-            float a10 = __ldg(cp + y1 * iw + x0), a11 = __ldg(cp + y1 * iw + x1);
-            float up = hy * (hx * a00 + lx * a01) + ly * (hx * a10 + lx * a11);
-            op[c * oplane] = v[c] + up;
-        }
+        float up[3];
+        epi_sr_up(e, b, y, x, up);
+        epi_sr_store(e, b, y, x, v, up);
     }
 }
 #endif  // __CUDACC__

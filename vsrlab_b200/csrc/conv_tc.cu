@@ -69,6 +69,7 @@ struct TcParams {
     uint32_t res_abytes;
     int n_store;           // channels per store block (<= 64)
     int stg_bytes;         // bytes of one staging buffer (two are allocated)
+    int epi_alt;           // narrow direct-store epilogues: the two warps of a lane quarter take alternate tiles
     int pdl;               // launched with programmatic stream serialization (weights already stable)
     int* dbg;
     int debug;             // VSRB_TC_DEBUG bits (timing experiments only): 1 = no loads, 2 = no stores, 4 = no MMA
@@ -119,6 +120,57 @@ __device__ __forceinline__ void stage_chunk(const EpiParams& e, const uint32_t (
     st_shared_v4(o1, pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
 }
 
+// Walks the tiles blockIdx.x, blockIdx.x + gridDim.x, ... of one group as (image, tile row, tile column) with
+// carries instead of two integer divisions per tile (the divisions were ~15 % of the epilogue's instructions).
+struct TileWalk {
+    int li, ty, tx, d_li, d_ty, d_tx, tiles_x, tiles_y;
+    __device__ __forceinline__ TileWalk(int first, int stride, int tiles_x_, int tiles_per_img) {
+        tiles_x = tiles_x_;
+        tiles_y = tiles_per_img / tiles_x_;
+        li = first / tiles_per_img;
+        int t = first - li * tiles_per_img;
+        ty = t / tiles_x;
+        tx = t - ty * tiles_x;
+        d_li = stride / tiles_per_img;
+        t = stride - d_li * tiles_per_img;
+        d_ty = t / tiles_x;
+        d_tx = t - d_ty * tiles_x;
+    }
+    __device__ __forceinline__ void next() {
+        tx += d_tx;
+        int c = tx >= tiles_x;
+        tx -= c ? tiles_x : 0;
+        ty += d_ty + c;
+        c = ty >= tiles_y;
+        ty -= c ? tiles_y : 0;
+        li += d_li + c;
+    }
+};
+
+// Stacked layout, NCH (16 or 4) output channels of one pixel row segment: gathers the kKW partial sums of every
+// channel from the neighbouring lanes, adds the bias, applies the activation (kAct: 0 none, 1 ReLU, 2 max(v, v*act_k)).
+template <int kKW, int kAct, int NCH = 16>
+__device__ __forceinline__ void stacked_chunk16(uint32_t taddr, int n_tile, const float* bias16, float act_k, int lane,
+                                                float (&v)[NCH]) {
+    constexpr int PAD = kKW / 2;
+    constexpr int CH = NCH < 16 ? NCH : (kKW == 3 ? 16 : 8);        // channels gathered per TMEM round trip
+#pragma unroll
+    for (int hh = 0; hh < NCH / CH; ++hh) {
+        uint32_t r[kKW][CH];
+#pragma unroll
+        for (int kx = 0; kx < kKW; ++kx) tmem_ld_n<CH>(taddr + kx * n_tile + hh * CH, r[kx]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+            float sacc = __uint_as_float(r[PAD][i]) + bias16[hh * CH + i];
+#pragma unroll
+            for (int kx = 0; kx < kKW; ++kx)
+                if (kx != PAD) sacc += __shfl_sync(0xffffffffu, __uint_as_float(r[kx][i]), (lane + kx - PAD) & 31);
+            v[hh * CH + i] = kAct == 0 ? sacc : (kAct == 1 ? fmaxf(sacc, 0.f) : fmaxf(sacc, sacc * act_k));
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // kStaged = true : EPI_NHWC through swizzled staging + per-warp TMA stores (the hot path)
 // kStaged = false: every other epilogue, direct per-thread stores (3-channel fp32 outputs etc.)
@@ -151,7 +203,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(tfull0 + 8 * i, 1);
-            mbar_init(tempty0 + 8 * i, 4 * kEpiPerQ);
+            mbar_init(tempty0 + 8 * i, P.epi_alt ? 4 : 4 * kEpiPerQ);
         }
         mbar_init(wbar, 1);
         fence_barrier_init();
@@ -186,11 +238,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         griddep_wait();        // activations (and the residual) come from the previous kernel(s)
         int slot = 0;
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < tiles_g; tile += gridDim.x) {
-            const int li = tile / P.tiles_per_img;
-            const int t = tile - li * P.tiles_per_img;
-            const int img = g * P.imgs_per_group + li;
-            const int ty = t / P.tiles_x, tx = t - ty * P.tiles_x;
+        TileWalk tw(blockIdx.x, gridDim.x, P.tiles_x, P.tiles_per_img);
+        for (int tile = blockIdx.x; tile < tiles_g; tile += gridDim.x, tw.next()) {
+            const int img = g * P.imgs_per_group + tw.li;
+            const int ty = tw.ty, tx = tw.tx;
             const int y0 = ty * rows_tile - P.kh / 2, x0 = tx * P.UW - P.kw / 2;
             for (int o = 0; o < P.n_ops; ++o) {
                 const int s = P.op_wseg[o];
@@ -307,33 +358,69 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         // a store block of n_store channels is split in 16-channel chunks over the kEpiPerQ warps of the quarter
         const int nsplit = min(kEpiPerQ, P.n_store / 16);
         const int cpw = P.n_store / nsplit;               // channels of a store block per working warp (16 or 32)
-        const bool works = eh < nsplit;
-        const int cbeg = works ? eh * cpw : 0;
+        // 16-channel direct-store epilogues (conv_last, the cleaner's image conv, SPyNet's flow conv) leave the second
+        // warp of a quarter without channels: there the two warps own one accumulator buffer each (alternate tiles)
+        const bool alt = kKW > 0 && !kStaged && P.epi_alt;
+        const bool works = alt || eh < nsplit;
+        const int cbeg = (works && !alt) ? eh * cpw : 0;
         // stacked layout (n_tile <= 64, one store block): this warp's bias values live in registers
         float bias_r[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) bias_r[i] = (kKW > 0 && i < cpw) ? bias_s[cbeg + i] : 0.f;
         const float act_k = P.epi.act_k;
         griddep_wait();        // this role reads/writes global memory other kernels on the stream own
-        for (int tile = blockIdx.x; tile < tiles_g; tile += gridDim.x) {
-            const int li = tile / P.tiles_per_img;
-            const int t = tile - li * P.tiles_per_img;
+        const int actm = act_k == 1.f ? 0 : (act_k == 0.f ? 1 : 2);
+        TileWalk tw(blockIdx.x, gridDim.x, P.tiles_x, P.tiles_per_img);
+        for (int tile = blockIdx.x; tile < tiles_g; tile += gridDim.x, tw.next()) {
+            if (alt && eh != acc) {                            // the twin warp's tile
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                continue;
+            }
+            const int li = tw.li, ty = tw.ty, tx = tw.tx;
             const int img = g * P.imgs_per_group + li;
-            const int ty = t / P.tiles_x, tx = t - ty * P.tiles_x;
             const int x = tx * P.TW + px;
+            // image epilogues (<= 3 real channels) of the stacked layout take a 4-channel path; EPI_SR fetches its
+            // bilinear skip term while the tile's MMAs are still running
+            const bool narrow = kKW > 0 && !kStaged && P.epi.mode != VSRB_EPI_NHWC;
+            float upv[2][3];
+            if (narrow && P.epi.mode == VSRB_EPI_SR) {
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                    const int y = ty * rows_tile + m * P.rows_sub + wq, xo = tx * P.UW + lane - kKW / 2;
+                    upv[m][0] = upv[m][1] = upv[m][2] = 0.f;
+                    if (m < P.MT && lane >= kKW / 2 && lane < 32 - kKW / 2 && y < P.H && xo < P.W) epi_sr_up(P.epi, img, y, xo, upv[m]);
+                }
+            }
             mbar_wait(tfull0 + 8 * acc, acc_phase, P.dbg, 5, dead);
             tc_fence_after();
             for (int m = 0; m < ((P.debug & 8) ? 0 : P.MT); ++m) {
                 const uint32_t t0 = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * P.acc_cols + m * P.ns;
-                if (kKW > 0) {
+                if constexpr (kKW > 0) {
                     // ---- stacked layout: the quarter is one image row, lane = box column; filter column kx
                     // sits in accumulator columns [kx*n_tile, (kx+1)*n_tile) and belongs to the output pixel
                     // kx - pad lanes to the left, so out[lane] = sum_kx D_kx[lane + kx - pad] (warp shuffles)
                     constexpr int PAD = kKW / 2;
-                    constexpr int CH = kKW == 3 ? 16 : 8;        // channels gathered per TMEM round trip
                     const int y = ty * rows_tile + m * P.rows_sub + wq;
                     const bool lane_ok = lane >= PAD && lane < 32 - PAD;
                     const int xo = tx * P.UW + lane - PAD;
+                    if (narrow) {
+                        if (works) {
+                            float v4[4];
+                            stacked_chunk16<kKW, 2, 4>(t0, P.n_tile, bias_r, act_k, lane, v4);
+                            if (lane_ok && y < P.H && xo < P.W && !(P.debug & 2)) {
+                                if (P.epi.mode == VSRB_EPI_SR) {
+                                    const float up[3] = {m ? upv[1][0] : upv[0][0], m ? upv[1][1] : upv[0][1], m ? upv[1][2] : upv[0][2]};
+                                    epi_sr_store(P.epi, img, y, xo, v4, up);
+                                } else {
+                                    float v[16];
+#pragma unroll
+                                    for (int i = 0; i < 16; ++i) v[i] = i < 4 ? v4[i] : 0.f;
+                                    epi_store16<__nv_bfloat16, false>(P.epi, g, img, y, xo, 0, v);
+                                }
+                            }
+                        }
+                        continue;
+                    }
                     for (int b0 = 0; b0 < P.n_tile; b0 += P.n_store) {
                         if (kStaged) {
                             if (eh == 0 && lane == 0) bulk_wait_read<1>();
@@ -346,22 +433,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                                 const int c0 = cbeg + cc * 16;
                                 if (cc * 16 < cpw) {
                                     float v[16];
-#pragma unroll
-                                    for (int hh = 0; hh < 16 / CH; ++hh) {
-                                        uint32_t r[kKW > 0 ? kKW : 1][CH];
-#pragma unroll
-                                        for (int kx = 0; kx < kKW; ++kx) tmem_ld_n<CH>(t0 + kx * P.n_tile + b0 + c0 + hh * CH, r[kx]);
-                                        tmem_ld_wait();
-#pragma unroll
-                                        for (int i = 0; i < CH; ++i) {
-                                            float sacc = __uint_as_float(r[PAD][i]) + bias_r[cc * 16 + hh * CH + i];
-#pragma unroll
-                                            for (int kx = 0; kx < kKW; ++kx)
-                                                if (kx != PAD)
-                                                    sacc += __shfl_sync(0xffffffffu, __uint_as_float(r[kx][i]), (lane + kx - PAD) & 31);
-                                            v[hh * CH + i] = fmaxf(sacc, sacc * act_k);
-                                        }
-                                    }
+                                    const uint32_t ta = t0 + b0 + c0;
+                                    if (actm == 0) stacked_chunk16<kKW, 0>(ta, P.n_tile, bias_r + cc * 16, act_k, lane, v);
+                                    else if (actm == 1) stacked_chunk16<kKW, 1>(ta, P.n_tile, bias_r + cc * 16, act_k, lane, v);
+                                    else stacked_chunk16<kKW, 2>(ta, P.n_tile, bias_r + cc * 16, act_k, lane, v);
                                     if (kStaged) {
                                         if (lane_ok) {
                                             uint32_t o0 = row_base + (uint32_t)c0 * 2u, o1 = o0 + 16u;
@@ -556,6 +631,7 @@ int launch_conv_tc(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t stre
     P.res_mma = staged && a->residual && a->act == VSRB_ACT_NONE && p.n_tile == 64 && p.n_blocks == 1 && a->res_c % 8 == 0 &&
                 (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0;
     if (a->residual && !P.res_mma) staged = false;
+    P.epi_alt = (!staged && p.stacked && P.n_store == 16 && kEpiPerQ == 2) ? 1 : 0;
     if (P.res_mma) P.epi.res = nullptr;
     const int ident_total = P.res_mma ? kIdentBytes : 0;
 

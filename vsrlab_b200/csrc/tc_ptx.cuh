@@ -31,15 +31,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 // Bounded wait: a mis-programmed pipeline raises the debug flag and lets the kernel run to
 // completion with garbage instead of hanging the GPU.  `dead` is sticky per thread.
-static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, int* dbg, int code, bool& dead) {
+static __device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity, int* dbg, int code) {
     long long t0 = clock64();
     for (uint32_t it = 0;; ++it) {
-        if (mbar_try_wait(bar, parity)) return;
+        if (mbar_try_wait(bar, parity)) return false;
         if ((it & 255u) == 255u) {
             if (clock64() - t0 > 4000000000LL || *reinterpret_cast<volatile int*>(dbg) != 0) {
                 atomicCAS(dbg, 0, code);
-                dead = true;
-                return;
+                return true;                                   // gave up: the caller's `dead` flag goes up
             }
         }
     }
@@ -47,7 +46,7 @@ static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* dbg, int code, bool& dead) {
     if (dead) return;
     if (mbar_try_wait(bar, parity)) return;
-    mbar_wait_slow(bar, parity, dbg, code, dead);
+    dead = mbar_wait_slow(bar, parity, dbg, code);          // by value: `dead` stays in a register
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -113,6 +112,12 @@ template <>
 __device__ __forceinline__ void tmem_ld_n<8>(uint32_t taddr, uint32_t (&r)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+template <>
+__device__ __forceinline__ void tmem_ld_n<4>(uint32_t taddr, uint32_t (&r)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
                  : "r"(taddr));
 }
 // the two epilogue warps of TMEM lane quarter `wq` (64 threads) meet on named barrier 1 + wq

@@ -150,7 +150,11 @@ def conv2d_fwd(pc: PackedConv, ins: Sequence, in_c: Sequence[int], batch: int, h
     pc.uses += 1
     g = pc.geom
     flops = 2.0 * batch * h * w * pc.cout * sum(c for _, c in pc.real_segs) * pc.kh * pc.kw   # algorithmic (not x3)
-    with _Timed(("conv_tc_x3" if pc.split else "conv_tc") if pc.dtype == BF16 else "conv_f32", flops):
+    kind = ("conv_tc_x3" if pc.split else "conv_tc") if pc.dtype == BF16 else "conv_f32"
+    if PROFILE_SHAPES and PROFILE is not None:
+        cin = "+".join(str(c) for _, c in pc.real_segs)
+        kind += f"[{pc.kh}x{pc.kw} {cin}->{pc.cout} n{batch} {h}x{w} g{g.groups} epi{epilogue}{' res' if residual is not None else ''}]"
+    with _Timed(kind, flops):
         L.check(L.load().vsrb_conv2d_fwd(C.byref(a), _stream()), "vsrb_conv2d_fwd")
 
 
