@@ -80,7 +80,7 @@ struct TcParams {
 //  [46,48) version=1 | [61,64) layout type (2 = 128B, 4 = 64B, 6 = 32B swizzle)
 // All MMAs of one pipeline stage: MT sub-tiles x KH filter rows x ksteps K=16 steps.  Descriptors
 // differ only in their 14-bit start-address field, so each MMA costs one add per operand.
-template <int KH>
+template <int KH, bool kPair = false>
 __device__ __forceinline__ void issue_stage(uint32_t d0, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
                                             int MT, int d_m, uint32_t a_m, uint32_t a_ky, uint32_t b_ky, int ksteps,
                                             bool first) {
@@ -92,7 +92,8 @@ __device__ __forceinline__ void issue_stage(uint32_t d0, uint32_t a_lo, uint32_t
                 if (k < ksteps) {
                     const uint64_t ad = ((uint64_t)desc_hi << 32) | (a_lo + m * a_m + ky * a_ky + k * 2);
                     const uint64_t bd = ((uint64_t)desc_hi << 32) | (b_lo + ky * b_ky + k * 2);
-                    umma_bf16(d0 + m * d_m, ad, bd, idesc, (first && ky == 0 && k == 0) ? 0u : 1u);
+                    if constexpr (kPair) umma_bf16_pair(d0 + m * d_m, ad, bd, idesc, (first && ky == 0 && k == 0) ? 0u : 1u);
+                    else umma_bf16(d0 + m * d_m, ad, bd, idesc, (first && ky == 0 && k == 0) ? 0u : 1u);
                 }
             }
         }
@@ -171,11 +172,52 @@ __device__ __forceinline__ void stacked_chunk16(uint32_t taddr, int n_tile, cons
     }
 }
 
+// 3-wide stacked layout, hot shape (a warp owns 32 channels = two 16-channel chunks): the second chunk's TMEM loads
+// are in flight while the first chunk is gathered, activated and written to the staging row.
+__device__ __forceinline__ void ld_taps3(uint32_t taddr, int n_tile, uint32_t (&r)[3][16]) {
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) tmem_ld16_nowait(taddr + kx * n_tile, r[kx]);
+}
+template <int kAct>
+__device__ __forceinline__ void combine3_store(const uint32_t (&r)[3][16], const float* bias16, float act_k, int lane, bool lane_ok,
+                                               uint32_t row_addr, uint32_t msk) {
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        float sacc = __uint_as_float(r[1][i]) + bias16[i];
+        sacc += __shfl_sync(0xffffffffu, __uint_as_float(r[0][i]), (lane - 1) & 31);
+        sacc += __shfl_sync(0xffffffffu, __uint_as_float(r[2][i]), (lane + 1) & 31);
+        v[i] = kAct == 0 ? sacc : (kAct == 1 ? fmaxf(sacc, 0.f) : fmaxf(sacc, sacc * act_k));
+    }
+    if (lane_ok) {
+        uint32_t o0 = row_addr, o1 = o0 + 16u;
+        o0 ^= ((o0 >> 7) & msk) << 4;
+        o1 ^= ((o1 >> 7) & msk) << 4;
+        st_shared_v4(o0, pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        st_shared_v4(o1, pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+    }
+}
+template <int kAct>
+__device__ __forceinline__ void stacked3_two_chunks(uint32_t (&ra)[3][16], uint32_t taddr, int n_tile, const float* bias32, float act_k,
+                                                    int lane, bool lane_ok, uint32_t row_addr, uint32_t msk) {
+    uint32_t rb[3][16];
+    tmem_ld_wait();                                   // chunk 0 (issued by the caller before its barrier) has landed
+    ld_taps3(taddr + 16, n_tile, rb);
+    combine3_store<kAct>(ra, bias32, act_k, lane, lane_ok, row_addr, msk);
+    tmem_ld_wait();
+    combine3_store<kAct>(rb, bias32 + 16, act_k, lane, lane_ok, row_addr + 32u, msk);
+}
+
 // ---------------------------------------------------------------------------------------
 // kStaged = true : EPI_NHWC through swizzled staging + per-warp TMA stores (the hot path)
 // kStaged = false: every other epilogue, direct per-thread stores (3-channel fp32 outputs etc.)
 // kKW = 0: classic layout (one stage per filter column); 3 / 7: stacked layout (see api.cu make_plan)
-template <bool kStaged, int kKW>
+// kPair: two CTAs of a cluster (adjacent blockIdx.x) run each MMA together as one M = 256 instruction (cta_group::2):
+// every CTA keeps its own pixel tile (A) and accumulator, but only HALF of the weight rows (B) - the tensor cores
+// exchange the halves - so the shared-memory operand fetch per MMA drops from 128 + N to 128 + N/2 rows.  The leader
+// (cluster rank 0) issues the MMAs; full/accumulator-empty barriers live in the leader, slot-empty/accumulator-full
+// barriers are signalled in both CTAs by multicast commits.  Only the hot resblock shape uses it (launch_conv_tc).
+template <bool kStaged, int kKW, bool kPair = false>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ TcParams P) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -183,7 +225,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     uint8_t* base_ptr = smem_raw + (base - raw);
     // control block: barriers, TMEM base, bias of this (group, n_block)
     const uint32_t full0 = base, empty0 = base + 8 * kMaxSlots, tfull0 = base + 16 * kMaxSlots,
-                   tempty0 = tfull0 + 16, wbar = tempty0 + 16;
+                   tempty0 = tfull0 + 16, wbar = tempty0 + 16, wready = wbar + 8;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + 16 * kMaxSlots + 48);
     float* bias_s = reinterpret_cast<float*>(base_ptr + 256);   // up to 128 floats
     const uint32_t wres = base + kCtrlBytes;
@@ -195,6 +237,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int g = blockIdx.y / P.n_blocks, qb = blockIdx.y - g * P.n_blocks;
     const int tiles_g = P.imgs_per_group * P.tiles_per_img;
     const int rows_tile = P.rows_sub * P.MT;
+    uint32_t crank = 0;                                         // rank in the CTA pair (0 = leader)
+    if constexpr (kPair) crank = cluster_ctarank();
 
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < P.num_slots; ++i) {
@@ -203,26 +247,48 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(tfull0 + 8 * i, 1);
-            mbar_init(tempty0 + 8 * i, P.epi_alt ? 4 : 4 * kEpiPerQ);
+            mbar_init(tempty0 + 8 * i, (P.epi_alt ? 4 : 4 * kEpiPerQ) * (kPair ? 2 : 1));
         }
         mbar_init(wbar, 1);
+        mbar_init(wready, 2);
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(smem_u32(tmem_slot), 512);
+    if (warp == 2) {
+        if constexpr (kPair) tmem_alloc_pair(smem_u32(tmem_slot), 512);
+        else tmem_alloc(smem_u32(tmem_slot), 512);
+    }
     if (warp == 3)
         for (int i = lane; i < P.n_tile; i += 32) bias_s[i] = __ldg(P.epi.bias + (size_t)g * P.epi.cout_pad + qb * P.n_tile + i);
     tc_fence_before();
-    __syncthreads();
+    if constexpr (kPair) cluster_sync_all();       // the peer's barriers must exist before anything is signalled across
+    else __syncthreads();
     tc_fence_after();
     griddep_launch();      // the next kernel on the stream may start its own prologue as SMs free up
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
     const uint8_t* wsrc = P.w + ((size_t)g * P.n_blocks + qb) * P.wblock_bytes;
     bool dead = false;
 
+    if (warp < 4) {
+    // pair kernel: registers move from the control warps to the epilogue warps (two chunks of accumulators in flight);
+    // 4*32*72 + 8*32*216 = the 384*168 registers the CTA was launched with
+    if constexpr (kPair) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
     if (warp == 0) {
         // =============================== TMA producer ===============================
         // the warp stays converged; one elected lane arms the barrier and issues the copies
-        if ((P.resident || P.res_mma) && elect_one()) {
+        if (kPair && elect_one()) {
+            // this CTA's half of every weight block: rows [crank * ns/2, +ns/2) of each filter row's N = ns rows
+            mbar_expect_tx(wbar, P.wblock_bytes / 2 + (P.res_mma ? (uint32_t)kIdentBytes / 2 : 0u));
+            uint32_t off = 0;
+            for (int s = 0; s < P.n_seg; ++s) {
+                const uint32_t hb = P.seg_bstage[s] / (2u * (uint32_t)P.kh);
+                for (int i = 0; i < P.seg_stages[s]; ++i) {
+                    for (int ky = 0; ky < P.kh; ++ky)
+                        bulk_load(wres + off / 2 + ky * hb, wsrc + off + (2 * ky + crank) * hb, hb, wbar);
+                    off += P.seg_bstage[s];
+                }
+            }
+            if (P.res_mma) bulk_load(wid, P.ident + crank * (kIdentBytes / 2), kIdentBytes / 2, wbar);
+        } else if (!kPair && (P.resident || P.res_mma) && elect_one()) {
             mbar_expect_tx(wbar, (P.resident ? P.wblock_bytes : 0u) + (P.res_mma ? (uint32_t)kIdentBytes : 0u));
             if (P.resident) {
                 uint32_t off = 0;
@@ -239,7 +305,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         int slot = 0;
         uint32_t phase = 0;
         TileWalk tw(blockIdx.x, gridDim.x, P.tiles_x, P.tiles_per_img);
-        for (int tile = blockIdx.x; tile < tiles_g; tile += gridDim.x, tw.next()) {
+        // pair: the loop runs while the LEADER's tile exists; an odd tile count leaves the peer one dummy tile whose
+        // loads fall outside the tensor (zero fill) and whose result is never stored
+        for (int tile = blockIdx.x; tile - (int)crank < tiles_g; tile += gridDim.x, tw.next()) {
             const int img = g * P.imgs_per_group + tw.li;
             const int ty = tw.ty, tx = tw.tx;
             const int y0 = ty * rows_tile - P.kh / 2, x0 = tx * P.UW - P.kw / 2;
@@ -252,7 +320,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                     const uint32_t sa = slots0 + slot * P.slot_bytes;
                     mbar_wait(empty0 + 8 * slot, phase ^ 1, P.dbg, 1, dead);
                     if (elect_one()) {
-                        if (P.debug & 1) {
+                        if constexpr (kPair) {                 // both tiles' bytes are counted on the leader's barrier
+                            if (P.debug & 1) {
+                                if (crank == 0) mbar_arrive(full0 + 8 * slot);
+                            } else {
+                                if (crank == 0) mbar_expect_tx(full0 + 8 * slot, 2 * abytes);
+                                tma_load_4d_pair(&P.tmap[o], mapa_rank(full0 + 8 * slot, 0), sa, P.op_c0[o] + chunk * P.seg_ck[s], x0 + kx,
+                                                 y0, img);
+                            }
+                        } else if (P.debug & 1) {
                             mbar_arrive(full0 + 8 * slot);
                         } else {
                             mbar_expect_tx(full0 + 8 * slot, abytes + (P.resident ? 0 : bbytes));
@@ -270,7 +346,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 const uint32_t sa = slots0 + slot * P.slot_bytes;
                 mbar_wait(empty0 + 8 * slot, phase ^ 1, P.dbg, 6, dead);
                 if (elect_one()) {
-                    if (P.debug & 1) {
+                    if constexpr (kPair) {
+                        if (P.debug & 1) {
+                            if (crank == 0) mbar_arrive(full0 + 8 * slot);
+                        } else {
+                            if (crank == 0) mbar_expect_tx(full0 + 8 * slot, 2 * P.res_abytes);
+                            tma_load_4d_pair(&P.rmap, mapa_rank(full0 + 8 * slot, 0), sa, qb * P.n_tile, tx * P.UW - P.res_xoff,
+                                             ty * rows_tile, img);
+                        }
+                    } else if (P.debug & 1) {
                         mbar_arrive(full0 + 8 * slot);
                     } else {
                         mbar_expect_tx(full0 + 8 * slot, P.res_abytes);
@@ -284,12 +368,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     } else if (warp == 1) {
         // =============================== MMA issuer =================================
         // instruction descriptor: D=f32, A=B=bf16, K-major both, N>>3 @17, M>>4 @24
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.ns >> 3) << 17) | (8u << 24);
-        const uint32_t idesc_res = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | (8u << 24);
-        if (P.resident || P.res_mma) mbar_wait(wbar, 0, P.dbg, 2, dead);
+        constexpr uint32_t kM = kPair ? 16u : 8u;               // M = 256 across the pair, 128 alone
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.ns >> 3) << 17) | (kM << 24);
+        const uint32_t idesc_res = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | (kM << 24);
+        if (kPair || P.resident || P.res_mma) mbar_wait(wbar, 0, P.dbg, 2, dead);
+        if constexpr (kPair) {                                  // both halves of the weights must be resident
+            if (elect_one()) mbar_arrive_cluster(mapa_rank(wready, 0));
+            __syncwarp();
+            if (crank == 0) mbar_wait(wready, 0, P.dbg, 8, dead);
+        }
         int slot = 0, acc = 0;
         uint32_t phase = 0, acc_phase = 0;
-        for (int tile = blockIdx.x; tile < tiles_g; tile += gridDim.x) {
+        for (int tile = blockIdx.x; tile < tiles_g && crank == 0; tile += gridDim.x) {
             mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1, P.dbg, 3, dead);
             tc_fence_after();
             const uint32_t d0 = tmem_base + acc * P.acc_cols;
@@ -299,21 +389,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 uint32_t boff = P.seg_woff[s];
                 const uint32_t rb = P.seg_rowbytes[s];
                 const uint32_t desc_hi = ((rb * 8u) >> 4) | (1u << 14) | ((uint32_t)P.seg_layout[s] << 29);
-                const uint32_t a_ky = (P.TW * rb) >> 4, b_ky = (P.ns * rb) >> 4, a_m = (P.rows_sub * P.TW * rb) >> 4;
+                const uint32_t a_ky = (P.TW * rb) >> 4, b_ky = ((kPair ? P.ns / 2 : P.ns) * rb) >> 4,
+                               a_m = (P.rows_sub * P.TW * rb) >> 4;
                 const int ksteps = P.seg_ck[s] >> 4;
                 for (int local = 0; local < P.seg_stages[s]; ++local) {
                     const uint32_t sa = slots0 + slot * P.slot_bytes;
-                    const uint32_t sb = P.resident ? (wres + boff) : (sa + P.seg_abytes[s]);
+                    const uint32_t sb = kPair ? (wres + boff / 2) : (P.resident ? (wres + boff) : (sa + P.seg_abytes[s]));
                     mbar_wait(full0 + 8 * slot, phase, P.dbg, 4, dead);
                     tc_fence_after();
                     if (elect_one()) {
                         const uint32_t a_lo = ((sa >> 4) & 0x3FFFu) | (1u << 16), b_lo = ((sb >> 4) & 0x3FFFu) | (1u << 16);
                         if (P.debug & 4) {
-                        } else if (P.kh == 3) issue_stage<3>(d0, a_lo, b_lo, desc_hi, idesc, P.MT, P.ns, a_m, a_ky, b_ky, ksteps, first);
+                        } else if (kPair || P.kh == 3)
+                            issue_stage<3, kPair>(d0, a_lo, b_lo, desc_hi, idesc, P.MT, P.ns, a_m, a_ky, b_ky, ksteps, first);
                         else if (P.kh == 7) issue_stage<7>(d0, a_lo, b_lo, desc_hi, idesc, P.MT, P.ns, a_m, a_ky, b_ky, ksteps, first);
                         else if (P.kh == 1) issue_stage<1>(d0, a_lo, b_lo, desc_hi, idesc, P.MT, P.ns, a_m, a_ky, b_ky, ksteps, first);
                         else issue_stage<5>(d0, a_lo, b_lo, desc_hi, idesc, P.MT, P.ns, a_m, a_ky, b_ky, ksteps, first);
-                        umma_commit(empty0 + 8 * slot);   // frees the slot when these MMAs retire
+                        // frees the slot (in both CTAs of a pair) when these MMAs retire
+                        if constexpr (kPair) umma_commit_pair(empty0 + 8 * slot);
+                        else umma_commit(empty0 + 8 * slot);
                     }
                     __syncwarp();
                     first = false;
@@ -329,18 +423,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                     const uint32_t a_lo = ((sa >> 4) & 0x3FFFu) | (1u << 16), b_lo = ((wid >> 4) & 0x3FFFu) | (1u << 16);
                     const uint32_t desc_hi = ((128u * 8u) >> 4) | (1u << 14) | (2u << 29);
                     if (!(P.debug & 4))
-                        issue_stage<1>(d0 + (kKW / 2) * P.n_tile, a_lo, b_lo, desc_hi, idesc_res, P.MT, P.ns, (P.rows_sub * P.TW * 128u) >> 4, 0,
-                                       0, 4, false);
-                    umma_commit(empty0 + 8 * slot);
+                        issue_stage<1, kPair>(d0 + (kKW / 2) * P.n_tile, a_lo, b_lo, desc_hi, idesc_res, P.MT, P.ns,
+                                              (P.rows_sub * P.TW * 128u) >> 4, 0, 0, 4, false);
+                    if constexpr (kPair) umma_commit_pair(empty0 + 8 * slot);
+                    else umma_commit(empty0 + 8 * slot);
                 }
                 __syncwarp();
                 if (++slot == P.num_slots) { slot = 0; phase ^= 1; }
             }
-            if (elect_one()) umma_commit(tfull0 + 8 * acc);   // accumulator complete -> epilogue
+            if (elect_one()) {                                 // accumulator complete -> epilogue (of both CTAs)
+                if constexpr (kPair) umma_commit_pair(tfull0 + 8 * acc);
+                else umma_commit(tfull0 + 8 * acc);
+            }
             __syncwarp();
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-    } else if (warp >= 4) {
+    }
+    } else {
+        if constexpr (kPair) asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
         // =============================== epilogue ===================================
         // kEpiPerQ warps per TMEM lane quarter (hardware rule: a warp reads lanes 32*(warp%4)..+31): the warps
         // (wq, eh=0..kEpiPerQ-1) share the 32 pixels of quarter wq and split their channels.
@@ -370,8 +470,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const float act_k = P.epi.act_k;
         griddep_wait();        // this role reads/writes global memory other kernels on the stream own
         const int actm = act_k == 1.f ? 0 : (act_k == 0.f ? 1 : 2);
+        const uint32_t tempty_lead = kPair ? mapa_rank(tempty0, 0) : 0u;
         TileWalk tw(blockIdx.x, gridDim.x, P.tiles_x, P.tiles_per_img);
-        for (int tile = blockIdx.x; tile < tiles_g; tile += gridDim.x, tw.next()) {
+        for (int tile = blockIdx.x; tile - (int)crank < tiles_g; tile += gridDim.x, tw.next()) {
+            const bool dummy = kPair && tile >= tiles_g;       // the pair's odd tile out: handshakes only
             if (alt && eh != acc) {                            // the twin warp's tile
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 continue;
@@ -393,7 +495,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             }
             mbar_wait(tfull0 + 8 * acc, acc_phase, P.dbg, 5, dead);
             tc_fence_after();
-            for (int m = 0; m < ((P.debug & 8) ? 0 : P.MT); ++m) {
+            for (int m = 0; m < (((P.debug & 8) || dummy) ? 0 : P.MT); ++m) {
                 const uint32_t t0 = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * P.acc_cols + m * P.ns;
                 if constexpr (kKW > 0) {
                     // ---- stacked layout: the quarter is one image row, lane = box column; filter column kx
@@ -422,11 +524,33 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                         continue;
                     }
                     for (int b0 = 0; b0 < P.n_tile; b0 += P.n_store) {
+                        const uint32_t row_base = stg0 + sbuf * P.stg_bytes + (uint32_t)(wq * 32 + lane - PAD) * rowb;
+                        if constexpr (kStaged && kKW == 3 && kPair) {
+                            if (cpw == 32) {                                   // hot shape: pipelined TMEM reads
+                                uint32_t ra[3][16];
+                                const uint32_t ta = t0 + b0 + cbeg;
+                                ld_taps3(ta, P.n_tile, ra);
+                                if (eh == 0 && lane == 0) bulk_wait_read<1>();
+                                pair_sync(wq, 32 * kEpiPerQ);
+                                const uint32_t ro = row_base + (uint32_t)cbeg * 2u;
+                                if (actm == 0) stacked3_two_chunks<0>(ra, ta, P.n_tile, bias_r, act_k, lane, lane_ok, ro, msk);
+                                else if (actm == 1) stacked3_two_chunks<1>(ra, ta, P.n_tile, bias_r, act_k, lane, lane_ok, ro, msk);
+                                else stacked3_two_chunks<2>(ra, ta, P.n_tile, bias_r, act_k, lane, lane_ok, ro, msk);
+                                fence_proxy_async();
+                                pair_sync(wq, 32 * kEpiPerQ);
+                                if (eh == 0 && lane == 0 && !(P.debug & 2)) {
+                                    tma_store_5d(&P.smap[0], stg0 + sbuf * P.stg_bytes + (uint32_t)(wq * 32) * rowb, qb * P.n_tile + b0,
+                                                 tx * P.UW, y, li, g);
+                                    bulk_commit();
+                                }
+                                sbuf ^= 1;
+                                continue;
+                            }
+                        }
                         if (kStaged) {
                             if (eh == 0 && lane == 0) bulk_wait_read<1>();
                             pair_sync(wq, 32 * kEpiPerQ);
                         }
-                        const uint32_t row_base = stg0 + sbuf * P.stg_bytes + (uint32_t)(wq * 32 + lane - PAD) * rowb;
                         if (works) {
 #pragma unroll
                             for (int cc = 0; cc < 2; ++cc) {
@@ -507,17 +631,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+            if (lane == 0) {
+                if constexpr (kPair) mbar_arrive_cluster(tempty_lead + 8 * acc);
+                else mbar_arrive(tempty0 + 8 * acc);
+            }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         if (kStaged && eh == 0 && lane == 0) bulk_wait_all();   // staged tiles must be read out before shared memory goes away
+        tc_fence_before();
+        if constexpr (kPair) cluster_sync_all();               // neither CTA may leave while its peer still signals it
+        else asm volatile("bar.sync 0;" ::: "memory");
+        return;
     }
-
     tc_fence_before();
-    __syncthreads();
+    if constexpr (kPair) cluster_sync_all();
+    else asm volatile("bar.sync 0;" ::: "memory");
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        if constexpr (kPair) tmem_dealloc_pair(tmem_base, 512);
+        else tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -578,6 +710,7 @@ int launch_conv_tc(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t stre
         VSRB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
         VSRB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
         VSRB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+        VSRB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
         void* ip = nullptr;
         VSRB_CUDA(cudaGetSymbolAddress(&ip, g_identity));
         g_ident_ptr[dev] = reinterpret_cast<const uint8_t*>(ip);
@@ -636,6 +769,10 @@ int launch_conv_tc(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t stre
     const int ident_total = P.res_mma ? kIdentBytes : 0;
 
     const int avail = kSmemMax - kCtrlBytes - 1024 - (staged ? stg_total : 0) - ident_total;
+    // CTA pairs (cta_group::2) for the hot resblock shape: staged NHWC 3x3, 64-wide stacked tile, resident weights
+    bool pair = staged && p.stacked && p.kh == 3 && p.kw == 3 && p.n_tile == 64 && p.ns == 192 && ctas_budget / units >= 2 &&
+                (long)a->imgs_per_group * ceil_div(a->h, P.rows_sub) * ceil_div(a->w, P.UW) >= 2 && !getenv("VSRB_TC_NO_PAIR");
+    for (int attempt = 0; attempt < 2; ++attempt) {
     int MT = (2 * 2 * p.ns <= 512) ? 2 : 1;
     if (MT == 2) {
         long tiles2 = (long)a->imgs_per_group * ceil_div(a->h, 2 * P.rows_sub) * ceil_div(a->w, P.UW) * units;
@@ -657,7 +794,7 @@ int launch_conv_tc(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t stre
             abmax = abmax > (int)P.res_abytes ? abmax : (int)P.res_abytes;
         }
         const int slot_res = (int)round_up(amax, 1024), slot_str = (int)round_up(abmax, 1024);
-        const int wres = (int)round_up(p.wblock_bytes, 1024);
+        const int wres = (int)round_up(pair ? p.wblock_bytes / 2 : p.wblock_bytes, 1024);
         if (P.box_rows <= 256 && wres + 3 * slot_res <= avail) {
             P.resident = 1; P.wres_bytes = wres; P.slot_bytes = slot_res;
             P.num_slots = (avail - wres) / slot_res;
@@ -671,6 +808,9 @@ int launch_conv_tc(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t stre
             set_error("conv tile does not fit shared memory (kh=%d n_tile=%d)", p.kh, p.n_tile);
             return VSRB_E_SMEM;
         }
+    }
+    if (!pair || (P.resident && P.MT == 1)) break;
+    pair = false;                                   // the pair kernel only exists for resident weights
     }
     P.acc_cols = P.MT * p.ns;
     P.tiles_x = ceil_div(a->w, P.UW);
@@ -742,12 +882,18 @@ int launch_conv_tc(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t stre
     int ctas_x = ctas_budget / units;
     if (ctas_x < 1) ctas_x = 1;
     if (ctas_x > tiles_g) ctas_x = tiles_g;
+    if (pair) {                                     // whole pairs; an odd tile count leaves one dummy tile
+        const int want = (int)round_up((size_t)tiles_g, 2);
+        ctas_x = (ctas_budget / units) & ~1;
+        if (ctas_x > want) ctas_x = want;
+    }
     const int smem = kCtrlBytes + 1024 + (int)P.wres_bytes + ident_total + P.num_slots * P.slot_bytes + (staged ? stg_total : 0);
     dim3 grid(ctas_x, units);
     const int kkw = p.stacked ? p.kw : 0;
     P.pdl = (a->flags & VSRB_CONV_PDL) ? 1 : 0;
     void (*kern)(TcParams) = nullptr;
-    if (staged) kern = kkw == 3 ? conv_tc_kernel<true, 3> : (kkw == 7 ? conv_tc_kernel<true, 7> : conv_tc_kernel<true, 0>);
+    if (pair) kern = conv_tc_kernel<true, 3, true>;
+    else if (staged) kern = kkw == 3 ? conv_tc_kernel<true, 3> : (kkw == 7 ? conv_tc_kernel<true, 7> : conv_tc_kernel<true, 0>);
     else kern = kkw == 3 ? conv_tc_kernel<false, 3> : (kkw == 7 ? conv_tc_kernel<false, 7> : conv_tc_kernel<false, 0>);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -755,11 +901,22 @@ int launch_conv_tc(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t stre
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (P.pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    if (pair) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 2;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = P.pdl ? 1 : 0;
+    cfg.numAttrs = na;
     VSRB_CUDA(cudaLaunchKernelEx(&cfg, kern, P));
     VSRB_LAUNCH_CHECK();
     return VSRB_OK;

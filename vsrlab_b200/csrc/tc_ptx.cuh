@@ -30,23 +30,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     return ok != 0;
 }
 // Bounded wait: a mis-programmed pipeline raises the debug flag and lets the kernel run to
-// completion with garbage instead of hanging the GPU.  `dead` is sticky per thread.
-static __device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity, int* dbg, int code) {
-    long long t0 = clock64();
-    for (uint32_t it = 0;; ++it) {
-        if (mbar_try_wait(bar, parity)) return false;
-        if ((it & 255u) == 255u) {
-            if (clock64() - t0 > 4000000000LL || *reinterpret_cast<volatile int*>(dbg) != 0) {
-                atomicCAS(dbg, 0, code);
-                return true;                                   // gave up: the caller's `dead` flag goes up
-            }
-        }
-    }
-}
+// completion with garbage instead of hanging the GPU.  `dead` is sticky per thread.  Everything is inline (no call:
+// ptxas cannot allocate registers for a call inside a setmaxnreg region); try_wait itself suspends the thread for a
+// hardware time slice, so 2^22 failed polls are seconds.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* dbg, int code, bool& dead) {
     if (dead) return;
-    if (mbar_try_wait(bar, parity)) return;
-    dead = mbar_wait_slow(bar, parity, dbg, code);          // by value: `dead` stays in a register
+    uint32_t polls = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        ++polls;
+        if ((polls & 1023u) == 0u && (polls > (1u << 22) || *reinterpret_cast<volatile int*>(dbg) != 0)) {
+            atomicCAS(dbg, 0, code);
+            dead = true;
+            return;
+        }
+    }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -95,6 +92,53 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// ---- CTA-pair (cta_group::2) forms: two CTAs of a cluster run one M=256 MMA; the leader (cluster rank 0) issues it ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA's layout) inside CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA tile load whose completion bytes are counted on a barrier of the pair's leader CTA
+__device__ __forceinline__ void tma_load_4d_pair(const CUtensorMap* map, uint32_t bar_cluster, uint32_t dst, int c0, int c1, int c2,
+                                                 int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t cols) {      // the same warp of BOTH CTAs
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+// arrives on the barrier at the same shared-memory offset in both CTAs of the pair when the MMAs issued so far retire
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
 }
 // 32 lanes x 16 consecutive fp32 columns; the caller waits with tmem_ld_wait()
 __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
