@@ -539,7 +539,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                                 fence_proxy_async();
                                 pair_sync(wq, 32 * kEpiPerQ);
                                 if (eh == 0 && lane == 0 && !(P.debug & 2)) {
-                                    tma_store_5d(&P.smap[0], stg0 + sbuf * P.stg_bytes + (uint32_t)(wq * 32) * rowb, qb * P.n_tile + b0,
+                                    const int n0 = qb * P.n_tile + b0;         // PixelShuffle: one output map per sub-pixel
+                                    const int q = P.epi.pixshuf ? n0 / P.epi.cq : 0;
+                                    tma_store_5d(&P.smap[q], stg0 + sbuf * P.stg_bytes + (uint32_t)(wq * 32) * rowb, n0 - q * P.epi.cq,
                                                  tx * P.UW, y, li, g);
                                     bulk_commit();
                                 }
@@ -581,7 +583,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                             fence_proxy_async();
                             pair_sync(wq, 32 * kEpiPerQ);
                             if (eh == 0 && lane == 0 && !(P.debug & 2)) {
-                                tma_store_5d(&P.smap[0], stg0 + sbuf * P.stg_bytes + (uint32_t)(wq * 32) * rowb, qb * P.n_tile + b0,
+                                const int n0 = qb * P.n_tile + b0;
+                                const int q = P.epi.pixshuf ? n0 / P.epi.cq : 0;
+                                tma_store_5d(&P.smap[q], stg0 + sbuf * P.stg_bytes + (uint32_t)(wq * 32) * rowb, n0 - q * P.epi.cq,
                                              tx * P.UW, y, li, g);
                                 bulk_commit();
                             }
