@@ -59,15 +59,31 @@ int make_plan(const vsrb_conv_geom* g, ConvPlan* p) {
         // per cycle for 64/128-byte rows and one per cycle for 32-byte rows; the stacked epilogue costs
         // n_tile*(4*(kw-1)+24) cycles per 128 pixels; a stacked tile only yields (33-kw)/32 useful columns.
         auto rows_cost = [](int ck) { return ck >= 32 ? 0.5 : 1.0; };
-        auto mma_cost = [&](int n_tile, int n, int cap, int stages_kx) {
+        auto mma_cost = [&](int n_tile, int n, int cap, int stages_kx, bool pair = false) {
             double c = 0;
             for (int s = 0; s < g->n_seg; ++s) {
                 const int cpad = (int)round_up(g->seg_c[s], 16);
                 int ck = (cpad % 64 == 0) ? 64 : (cpad % 32 == 0 ? 32 : 16);
                 if (ck > cap) ck = cap;
-                c += (double)(cpad / 16) * p->kh * stages_kx * (128 + n) * rows_cost(ck);
+                c += (double)(cpad / 16) * p->kh * stages_kx * (128 + (pair ? n / 2 : n)) * rows_cost(ck);
             }
             return c * (p->cout_pad / n_tile);
+        };
+        // CTA pairs (conv_tc.cu, cta_group::2): every CTA holds half of the weight rows, resident.  A stacked plan whose
+        // stages are too large to stream (7x7 with 32/64-channel chunks) is still fine when half of the whole weight block
+        // plus two activation slots fit next to the staging buffers; launch_conv_tc then always runs it in pairs.
+        auto pair_fits = [&](int n_tile, int cap) {
+            if (p->kh != p->kw || (p->kw * n_tile / 2) % 8 != 0 || (p->kw * n_tile) % 16 != 0) return false;
+            size_t total = 0, amax = 0;
+            for (int s = 0; s < g->n_seg; ++s) {
+                const size_t cpad = round_up(g->seg_c[s], 16);
+                size_t ck = (cpad % 64 == 0) ? 64 : (cpad % 32 == 0 ? 32 : 16);
+                if (ck > (size_t)cap) ck = cap;
+                total += (size_t)p->kh * p->kw * n_tile * cpad * 2;
+                const size_t ab = (size_t)(4 + p->kh - 1) * 32 * ck * 2;
+                amax = amax > ab ? amax : ab;
+            }
+            return round_up(total / 2, 1024) + 3 * round_up(amax, 1024) <= (size_t)160 * 1024;
         };
         double best = mma_cost(p->n_tile, p->n_tile, 64, p->kw);
         const double classic_epi = 10.0 * p->cout_pad;
@@ -76,8 +92,9 @@ int make_plan(const vsrb_conv_geom* g, ConvPlan* p) {
         for (int i = 0; i < 3; ++i) {
             if (p->cout_pad % cands[i] != 0 || p->kw * cands[i] > 256) continue;
             for (int j = 0; j < 3; ++j) {
-                if (p->kh * p->kw * cands[i] * cands[j] * 2 > 76 * 1024) continue;
-                double c = mma_cost(cands[i], p->kw * cands[i], cands[j], 1);
+                const bool pf = pair_fits(cands[i], cands[j]);
+                if (p->kh * p->kw * cands[i] * cands[j] * 2 > 76 * 1024 && !pf) continue;
+                double c = mma_cost(cands[i], p->kw * cands[i], cands[j], 1, pf);
                 const double epi = (double)p->cout_pad * (4 * (p->kw - 1) + 24);
                 if (c < epi) c = epi;
                 c *= 32.0 / (33 - p->kw);

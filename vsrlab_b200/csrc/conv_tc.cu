@@ -400,10 +400,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                     if (elect_one()) {
                         const uint32_t a_lo = ((sa >> 4) & 0x3FFFu) | (1u << 16), b_lo = ((sb >> 4) & 0x3FFFu) | (1u << 16);
                         if (P.debug & 4) {
-                        } else if (kPair || P.kh == 3)
-                            issue_stage<3, kPair>(d0, a_lo, b_lo, desc_hi, idesc, P.MT, P.ns, a_m, a_ky, b_ky, ksteps, first);
-                        else if (P.kh == 7) issue_stage<7>(d0, a_lo, b_lo, desc_hi, idesc, P.MT, P.ns, a_m, a_ky, b_ky, ksteps, first);
-                        else if (P.kh == 1) issue_stage<1>(d0, a_lo, b_lo, desc_hi, idesc, P.MT, P.ns, a_m, a_ky, b_ky, ksteps, first);
+                        } else if (P.kh == 3) issue_stage<3, kPair>(d0, a_lo, b_lo, desc_hi, idesc, P.MT, P.ns, a_m, a_ky, b_ky, ksteps, first);
+                        else if (P.kh == 7) issue_stage<7, kPair>(d0, a_lo, b_lo, desc_hi, idesc, P.MT, P.ns, a_m, a_ky, b_ky, ksteps, first);
+                        else if (kPair) {
+                        } else if (P.kh == 1) issue_stage<1>(d0, a_lo, b_lo, desc_hi, idesc, P.MT, P.ns, a_m, a_ky, b_ky, ksteps, first);
                         else issue_stage<5>(d0, a_lo, b_lo, desc_hi, idesc, P.MT, P.ns, a_m, a_ky, b_ky, ksteps, first);
                         // frees the slot (in both CTAs of a pair) when these MMAs retire
                         if constexpr (kPair) umma_commit_pair(empty0 + 8 * slot);
@@ -485,7 +485,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             // bilinear skip term while the tile's MMAs are still running
             const bool narrow = kKW > 0 && !kStaged && P.epi.mode != VSRB_EPI_NHWC;
             float upv[2][3];
-            if (narrow && P.epi.mode == VSRB_EPI_SR) {
+            if (narrow && P.epi.mode == VSRB_EPI_SR && !dummy) {
 #pragma unroll
                 for (int m = 0; m < 2; ++m) {
                     const int y = ty * rows_tile + m * P.rows_sub + wq, xo = tx * P.UW + lane - kKW / 2;
@@ -715,6 +715,9 @@ int launch_conv_tc(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t stre
         VSRB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
         VSRB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
         VSRB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+        VSRB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, 7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+        VSRB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+        VSRB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, 7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
         void* ip = nullptr;
         VSRB_CUDA(cudaGetSymbolAddress(&ip, g_identity));
         g_ident_ptr[dev] = reinterpret_cast<const uint8_t*>(ip);
@@ -773,9 +776,11 @@ int launch_conv_tc(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t stre
     const int ident_total = P.res_mma ? kIdentBytes : 0;
 
     const int avail = kSmemMax - kCtrlBytes - 1024 - (staged ? stg_total : 0) - ident_total;
-    // CTA pairs (cta_group::2) for the hot resblock shape: staged NHWC 3x3, 64-wide stacked tile, resident weights
-    bool pair = staged && p.stacked && p.kh == 3 && p.kw == 3 && p.n_tile == 64 && p.ns == 192 && ctas_budget / units >= 2 &&
-                (long)a->imgs_per_group * ceil_div(a->h, P.rows_sub) * ceil_div(a->w, P.UW) >= 2 && !getenv("VSRB_TC_NO_PAIR");
+    // CTA pairs (cta_group::2) for staged NHWC stacked 3x3 / 7x7 convs whose half weight block stays resident (every CTA
+    // holds ns/2 rows of each filter row: whole 8-row swizzle atoms; N of an M=256 MMA is a multiple of 16)
+    // (narrow tiles, N < 96, are bound by the A fetch and the per-tile handshake, which is longer across two CTAs: no pairs)
+    bool pair = p.stacked && (p.kw == 3 || p.kw == 7) && p.kh == p.kw && (p.ns / 2) % 8 == 0 && p.ns % 16 == 0 && p.ns >= 96 &&
+                !getenv("VSRB_TC_NO_PAIR");
     for (int attempt = 0; attempt < 2; ++attempt) {
     int MT = (2 * 2 * p.ns <= 512) ? 2 : 1;
     if (MT == 2) {
@@ -799,7 +804,7 @@ int launch_conv_tc(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t stre
         }
         const int slot_res = (int)round_up(amax, 1024), slot_str = (int)round_up(abmax, 1024);
         const int wres = (int)round_up(pair ? p.wblock_bytes / 2 : p.wblock_bytes, 1024);
-        if (P.box_rows <= 256 && wres + 3 * slot_res <= avail) {
+        if (P.box_rows <= 256 && wres + (pair ? 2 : 3) * slot_res <= avail) {
             P.resident = 1; P.wres_bytes = wres; P.slot_bytes = slot_res;
             P.num_slots = (avail - wres) / slot_res;
         } else {
@@ -813,7 +818,7 @@ int launch_conv_tc(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t stre
             return VSRB_E_SMEM;
         }
     }
-    if (!pair || (P.resident && P.MT == 1)) break;
+    if (!pair || P.resident) break;
     pair = false;                                   // the pair kernel only exists for resident weights
     }
     P.acc_cols = P.MT * p.ns;
@@ -889,6 +894,7 @@ int launch_conv_tc(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t stre
     if (pair) {                                     // whole pairs; an odd tile count leaves one dummy tile
         const int want = (int)round_up((size_t)tiles_g, 2);
         ctas_x = (ctas_budget / units) & ~1;
+        if (ctas_x < 2) ctas_x = 2;
         if (ctas_x > want) ctas_x = want;
     }
     const int smem = kCtrlBytes + 1024 + (int)P.wres_bytes + ident_total + P.num_slots * P.slot_bytes + (staged ? stg_total : 0);
@@ -896,7 +902,8 @@ int launch_conv_tc(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t stre
     const int kkw = p.stacked ? p.kw : 0;
     P.pdl = (a->flags & VSRB_CONV_PDL) ? 1 : 0;
     void (*kern)(TcParams) = nullptr;
-    if (pair) kern = conv_tc_kernel<true, 3, true>;
+    if (pair && staged) kern = kkw == 3 ? conv_tc_kernel<true, 3, true> : conv_tc_kernel<true, 7, true>;
+    else if (pair) kern = kkw == 3 ? conv_tc_kernel<false, 3, true> : conv_tc_kernel<false, 7, true>;
     else if (staged) kern = kkw == 3 ? conv_tc_kernel<true, 3> : (kkw == 7 ? conv_tc_kernel<true, 7> : conv_tc_kernel<true, 0>);
     else kern = kkw == 3 ? conv_tc_kernel<false, 3> : (kkw == 7 ? conv_tc_kernel<false, 7> : conv_tc_kernel<false, 0>);
     cudaLaunchConfig_t cfg;
