@@ -59,6 +59,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index, self.stop_flag, self.sm, self.reasons, self.max_mhz = index, False, [], set(), None
+        self.power_w, self.power_limit_w = [], None
 
     def run(self):
         try:
@@ -68,8 +69,16 @@ class ClockSampler(threading.Thread):
             self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
             names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
                      0x80: "hw_power_brake_slowdown"}
+            try:
+                self.power_limit_w = nv.nvmlDeviceGetEnforcedPowerLimit(h) / 1000.0
+            except Exception:  # noqa: BLE001
+                pass
             while not self.stop_flag:
                 self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    self.power_w.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                except Exception:  # noqa: BLE001
+                    pass
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
                 for bit, nm in names.items():
                     if r & bit:
@@ -80,7 +89,9 @@ class ClockSampler(threading.Thread):
 
     def summary(self):
         sm = sorted(self.sm)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        pw = sorted(self.power_w)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "power_w": pw[len(pw) // 2] if pw else None, "power_limit_w": self.power_limit_w}
 
 
 def oracle_sample(blocks: int, frames: int, threads: int):

@@ -718,6 +718,8 @@ int launch_conv_tc(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t stre
         VSRB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, 7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
         VSRB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
         VSRB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, 7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+        VSRB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+        VSRB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
         void* ip = nullptr;
         VSRB_CUDA(cudaGetSymbolAddress(&ip, g_identity));
         g_ident_ptr[dev] = reinterpret_cast<const uint8_t*>(ip);
@@ -779,8 +781,9 @@ int launch_conv_tc(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t stre
     // CTA pairs (cta_group::2) for staged NHWC stacked 3x3 / 7x7 convs whose half weight block stays resident (every CTA
     // holds ns/2 rows of each filter row: whole 8-row swizzle atoms; N of an M=256 MMA is a multiple of 16)
     // (narrow tiles, N < 96, are bound by the A fetch and the per-tile handshake, which is longer across two CTAs: no pairs)
-    bool pair = p.stacked && (p.kw == 3 || p.kw == 7) && p.kh == p.kw && (p.ns / 2) % 8 == 0 && p.ns % 16 == 0 && p.ns >= 96 &&
-                !getenv("VSRB_TC_NO_PAIR");
+    // Classic-layout convs with wide tiles (the 64->256 upsampling conv, N = 128) pair the same way.
+    bool pair = ((p.stacked && (p.kw == 3 || p.kw == 7) && p.kh == p.kw) || (!p.stacked && p.kh == 3 && p.n_tile >= 128)) &&
+                (p.ns / 2) % 8 == 0 && p.ns % 16 == 0 && p.ns >= 96 && !getenv("VSRB_TC_NO_PAIR");
     for (int attempt = 0; attempt < 2; ++attempt) {
     int MT = (2 * 2 * p.ns <= 512) ? 2 : 1;
     if (MT == 2) {
@@ -902,8 +905,10 @@ int launch_conv_tc(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t stre
     const int kkw = p.stacked ? p.kw : 0;
     P.pdl = (a->flags & VSRB_CONV_PDL) ? 1 : 0;
     void (*kern)(TcParams) = nullptr;
-    if (pair && staged) kern = kkw == 3 ? conv_tc_kernel<true, 3, true> : conv_tc_kernel<true, 7, true>;
-    else if (pair) kern = kkw == 3 ? conv_tc_kernel<false, 3, true> : conv_tc_kernel<false, 7, true>;
+    if (pair && staged)
+        kern = kkw == 3 ? conv_tc_kernel<true, 3, true> : (kkw == 7 ? conv_tc_kernel<true, 7, true> : conv_tc_kernel<true, 0, true>);
+    else if (pair)
+        kern = kkw == 3 ? conv_tc_kernel<false, 3, true> : (kkw == 7 ? conv_tc_kernel<false, 7, true> : conv_tc_kernel<false, 0, true>);
     else if (staged) kern = kkw == 3 ? conv_tc_kernel<true, 3> : (kkw == 7 ? conv_tc_kernel<true, 7> : conv_tc_kernel<true, 0>);
     else kern = kkw == 3 ? conv_tc_kernel<false, 3> : (kkw == 7 ? conv_tc_kernel<false, 7> : conv_tc_kernel<false, 0>);
     cudaLaunchConfig_t cfg;
