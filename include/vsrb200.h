@@ -127,6 +127,10 @@ int         vsrb_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_m
 int64_t     vsrb_launch_count(void);
 /* 0 if no kernel reported a pipeline time-out since the last call (debug aid) */
 int         vsrb_debug_status(void* stream);
+/* debug aid: with VSRB_TC_DEBUG bit 64 set, every CTA of a tensor-core conv records %globaltimer stamps (ns) of its
+ * pipeline milestones (8 per CTA: entry, prologue done, weights resident, first tile loaded, first accumulator ready,
+ * last tile stored, stores drained, exit); copies the first `n_ctas` CTAs' stamps of the last launch to `out[n_ctas*8]` */
+int         vsrb_debug_trace(uint64_t* out, int32_t n_ctas);
 
 /* ---- convolution: replaces nn.Conv2d -> F.conv2d (+ the pointwise op that follows it) --
  * reference: conv.py:89-92,101-103 (ResidualConv/ResidualBlock), conv.py:21 (ConvReLU),

@@ -121,6 +121,18 @@ __device__ __forceinline__ void stage_chunk(const EpiParams& e, const uint32_t (
     st_shared_v4(o1, pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
 }
 
+// VSRB_TC_DEBUG bit 64: per-CTA %globaltimer stamps of the pipeline milestones (vsrb_debug_trace)
+static constexpr int kTraceCtas = 512;
+__device__ unsigned long long g_trace[kTraceCtas * 8];
+__device__ __forceinline__ void trace_stamp(int debug, int slot) {
+    if (debug & 64) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        const int cta = blockIdx.y * gridDim.x + blockIdx.x;
+        if (cta < kTraceCtas) g_trace[cta * 8 + slot] = t;
+    }
+}
+
 // Walks the tiles blockIdx.x, blockIdx.x + gridDim.x, ... of one group as (image, tile row, tile column) with
 // carries instead of two integer divisions per tile (the divisions were ~15 % of the epilogue's instructions).
 struct TileWalk {
@@ -234,6 +246,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const uint32_t stg0 = slots0 + P.num_slots * P.slot_bytes;   // two staging buffers for the TMA store
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) trace_stamp(P.debug, 0);
     const int g = blockIdx.y / P.n_blocks, qb = blockIdx.y - g * P.n_blocks;
     const int tiles_g = P.imgs_per_group * P.tiles_per_img;
     const int rows_tile = P.rows_sub * P.MT;
@@ -263,6 +276,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     if constexpr (kPair) cluster_sync_all();       // the peer's barriers must exist before anything is signalled across
     else __syncthreads();
     tc_fence_after();
+    if (threadIdx.x == 0) trace_stamp(P.debug, 1);
     griddep_launch();      // the next kernel on the stream may start its own prologue as SMs free up
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
     const uint8_t* wsrc = P.w + ((size_t)g * P.n_blocks + qb) * P.wblock_bytes;
@@ -377,8 +391,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             __syncwarp();
             if (crank == 0) mbar_wait(wready, 0, P.dbg, 8, dead);
         }
+        if (lane == 0) trace_stamp(P.debug, 2);
         int slot = 0, acc = 0;
         uint32_t phase = 0, acc_phase = 0;
+        bool first_stage = true;
         for (int tile = blockIdx.x; tile < tiles_g && crank == 0; tile += gridDim.x) {
             mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1, P.dbg, 3, dead);
             tc_fence_after();
@@ -397,6 +413,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                     const uint32_t sb = kPair ? (wres + boff / 2) : (P.resident ? (wres + boff) : (sa + P.seg_abytes[s]));
                     mbar_wait(full0 + 8 * slot, phase, P.dbg, 4, dead);
                     tc_fence_after();
+                    if (first_stage && lane == 0) trace_stamp(P.debug, 3);
+                    first_stage = false;
                     if (elect_one()) {
                         const uint32_t a_lo = ((sa >> 4) & 0x3FFFu) | (1u << 16), b_lo = ((sb >> 4) & 0x3FFFu) | (1u << 16);
                         if (P.debug & 4) {
@@ -495,6 +513,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             }
             mbar_wait(tfull0 + 8 * acc, acc_phase, P.dbg, 5, dead);
             tc_fence_after();
+            if (tile == (int)blockIdx.x && warp == 4 && lane == 0) trace_stamp(P.debug, 4);
             for (int m = 0; m < (((P.debug & 8) || dummy) ? 0 : P.MT); ++m) {
                 const uint32_t t0 = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * P.acc_cols + m * P.ns;
                 if constexpr (kKW > 0) {
@@ -641,7 +660,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (warp == 4 && lane == 0) trace_stamp(P.debug, 5);
         if (kStaged && eh == 0 && lane == 0) bulk_wait_all();   // staged tiles must be read out before shared memory goes away
+        if (warp == 4 && lane == 0) trace_stamp(P.debug, 6);
         tc_fence_before();
         if constexpr (kPair) cluster_sync_all();               // neither CTA may leave while its peer still signals it
         else asm volatile("bar.sync 0;" ::: "memory");
@@ -654,6 +675,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         tc_fence_after();
         if constexpr (kPair) tmem_dealloc_pair(tmem_base, 512);
         else tmem_dealloc(tmem_base, 512);
+        if (lane == 0) trace_stamp(P.debug, 7);
     }
 }
 
@@ -939,3 +961,11 @@ int launch_conv_tc(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t stre
 }
 
 }  // namespace vsrb
+
+extern "C" int vsrb_debug_trace(uint64_t* out, int32_t n_ctas) {
+    using namespace vsrb;
+    VSRB_CHECK_ARG(out && n_ctas >= 1 && n_ctas <= kTraceCtas, "debug_trace: 1..%d CTAs", kTraceCtas);
+    VSRB_CUDA(cudaDeviceSynchronize());
+    VSRB_CUDA(cudaMemcpyFromSymbol(out, g_trace, sizeof(unsigned long long) * 8 * (size_t)n_ctas));
+    return VSRB_OK;
+}
