@@ -41,11 +41,86 @@ def _packed_transposed(conv) -> ops.PackedConvT:
     return pc
 
 
+def _wgrad_geom(conv, segs):
+    g = L.ConvGeom()
+    g.kh, g.kw, g.n_seg = conv.kernel_size[0], conv.kernel_size[1], len(segs)
+    for i, (off, c) in enumerate(segs):
+        g.seg_off[i], g.seg_c[i] = off, c
+    g.cout, g.pixshuf, g.groups, g.dtype, g.transpose = conv.out_channels, 0, 1, BF16, 0
+    return g
+
+
+# Weight gradients of a recurrent layer: the propagation resblocks apply the same conv at every time step on a small
+# batch (N images), so a weight-gradient launch per use runs on a handful of CTAs (measured: 64 us each on 16 CTAs, 330
+# launches = 17 % of the cfg4 step).  Inside `batched_wgrad()` every conv of a forward pass gets ONE `_WeightNode`: the
+# uses' backward passes only park (inputs, dz) in its box, and the node's own backward - which autograd runs after the
+# last use - concatenates them along the batch dimension and launches the weight/bias gradient once.  The parameter
+# still receives its gradient from a single autograd node, so hooks (DDP's reducer) see nothing unusual.
+_WGRAD_SCOPE: Optional[dict] = None
+_BATCH_PIXELS = 1 << 18      # uses with fewer pixels than this are batched; larger ones already fill the GPU
+
+
+class batched_wgrad:
+    def __enter__(self):
+        global _WGRAD_SCOPE
+        self.prev, _WGRAD_SCOPE = _WGRAD_SCOPE, {}
+        return self
+
+    def __exit__(self, *exc):
+        global _WGRAD_SCOPE
+        _WGRAD_SCOPE = self.prev
+        return False
+
+
+class _WeightNode(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, weight, bias, conv, segs, box):
+        ctx.conv, ctx.segs, ctx.box, ctx.has_bias = conv, segs, box, bias is not None
+        ctx.shape, ctx.device = weight.shape, weight.device
+        return weight.new_zeros(1)
+
+    @staticmethod
+    def backward(ctx, _dtoken):
+        conv, segs, box = ctx.conv, ctx.segs, ctx.box
+        dw = torch.zeros(ctx.shape, dtype=torch.float32, device=ctx.device)
+        db = torch.zeros(conv.out_channels, dtype=torch.float32, device=ctx.device) if ctx.has_bias else None
+        g = _wgrad_geom(conv, segs)
+        groups = {}
+        for ins, dz in box:
+            key = (tuple(ins[0].shape[2:]), tuple(t.shape[1] for t in ins), dz.shape[1])
+            groups.setdefault(key, []).append((ins, dz))
+        box.clear()
+        for (hw, in_c, dz_c), items in groups.items():
+            h, w = hw
+            small = [it for it in items if it[1].shape[0] * h * w < _BATCH_PIXELS]
+            big = [it for it in items if it[1].shape[0] * h * w >= _BATCH_PIXELS]
+            if len(small) > 1:
+                ins = [torch.cat([it[0][i] for it in small], 0) for i in range(len(in_c))]
+                big.append((ins, torch.cat([it[1] for it in small], 0)))
+            else:
+                big += small
+            for ins, dz in big:
+                ops.conv2d_wgrad(g, ins, list(in_c), dz, dz_c, dz.shape[0], h, w, conv.in_channels, dw, db)
+        return dw, db, None, None, None
+
+
+def _weight_token(mod, segs):
+    """(token, box) of `mod` in the current batched_wgrad scope, or (None, None) outside one / for frozen weights."""
+    if _WGRAD_SCOPE is None or not mod.weight.requires_grad:
+        return None, None
+    ent = _WGRAD_SCOPE.get(id(mod))
+    if ent is None or ent[2] is not mod or ent[3] != tuple(segs):
+        box: list = []
+        ent = (_WeightNode.apply(mod.weight, mod.bias, mod, tuple(segs), box), box, mod, tuple(segs))
+        _WGRAD_SCOPE[id(mod)] = ent
+    return ent[0], ent[1]
+
+
 class ConvFn(torch.autograd.Function):
     """act(conv(cat(inputs))) [+ residual] [pixel-shuffled], bf16 channels_last in and out."""
 
     @staticmethod
-    def forward(ctx, weight, bias, conv, segs, act, slope, pixshuf, residual, *inputs):
+    def forward(ctx, weight, bias, token, box, conv, segs, act, slope, pixshuf, residual, *inputs):
         from .functional import packed
         pc = packed([conv], segs, BF16, pixshuf)
         ins = [_cl(t) for t in inputs]
@@ -59,7 +134,7 @@ class ConvFn(torch.autograd.Function):
             raise VsrbError("ConvFn: a fused residual needs act='none' (reference conv.py:89-92)")
         ops.conv2d_fwd(pc, ins, [t.shape[1] for t in ins], b, h, w, act=_ACT[act], slope=slope, out=out, out_c=oc,
                        residual=res, res_c=0 if res is None else res.shape[1])
-        ctx.conv, ctx.segs, ctx.act, ctx.slope, ctx.pixshuf = conv, segs, act, slope, pixshuf
+        ctx.conv, ctx.segs, ctx.act, ctx.slope, ctx.pixshuf, ctx.box = conv, segs, act, slope, pixshuf, box
         ctx.has_res = res is not None
         ctx.save_for_backward(weight, out if act != "none" else None, *ins)
         return out
@@ -82,32 +157,31 @@ class ConvFn(torch.autograd.Function):
         dz = _cl(dz)
         dz_c = dz.shape[1]
         b, _, h, w = ins[0].shape
-        # weight / bias gradient
-        g = L.ConvGeom()
-        g.kh, g.kw, g.n_seg = conv.kernel_size[0], conv.kernel_size[1], len(segs)
-        for i, (off, c) in enumerate(segs):
-            g.seg_off[i], g.seg_c[i] = off, c
-        g.cout, g.pixshuf, g.groups, g.dtype, g.transpose = cout, 0, 1, BF16, 0
+        # weight / bias gradient: parked for the conv's _WeightNode inside batched_wgrad(), else computed here
         dw = db = None
-        if ctx.needs_input_grad[0]:
+        if ctx.box is not None:
+            ctx.box.append((ins, dz))
+        elif ctx.needs_input_grad[0]:
+            g = _wgrad_geom(conv, segs)
             dw = torch.zeros_like(weight, dtype=torch.float32)
             db = torch.zeros(cout, dtype=torch.float32, device=weight.device) if conv.bias is not None else None
             ops.conv2d_wgrad(g, ins, [t.shape[1] for t in ins], dz, dz_c, b, h, w, conv.in_channels, dw, db)
         # input gradient: the forward kernel on dz with transposed + flipped weights
         d_ins: List[Optional[torch.Tensor]] = [None] * len(ins)
-        if any(ctx.needs_input_grad[8 + i] for i in range(len(ins))):
+        if any(ctx.needs_input_grad[10 + i] for i in range(len(ins))):
             pt = _packed_transposed(conv)
             dx = torch.empty((b, pt.cout_pad, h, w), dtype=torch.bfloat16, device=dz.device, memory_format=CL)
             ops.conv2d_fwd(pt, [dz], [dz_c], b, h, w, act=ACT_NONE, out=dx, out_c=pt.cout_pad)
             for i, (off, c) in enumerate(segs):
-                if not ctx.needs_input_grad[8 + i]:
+                if not ctx.needs_input_grad[10 + i]:
                     continue
                 ca = ins[i].shape[1]
                 if len(segs) == 1 and ca == pt.cout_pad:
                     d_ins[i] = dx
                 else:
                     d_ins[i] = F.pad(dx[:, off:off + c], (0, 0, 0, 0, 0, ca - c))
-        return (dw, db if (conv.bias is not None and ctx.needs_input_grad[1]) else None, None, None, None, None, None, d_res, *d_ins)
+        return (dw, db if (conv.bias is not None and ctx.needs_input_grad[1]) else None, None, None, None, None, None, None, None, d_res,
+                *d_ins)
 
 
 class WarpFn(torch.autograd.Function):
@@ -141,7 +215,11 @@ class WarpFn(torch.autograd.Function):
 # the modules, differentiable
 # --------------------------------------------------------------------------------------
 def conv(mod, inputs: Sequence[torch.Tensor], segs, act="none", slope=0.1, pixshuf=0, residual=None) -> torch.Tensor:
-    return ConvFn.apply(mod.weight, mod.bias, mod, tuple(segs), act, slope, pixshuf, residual, *inputs)
+    token, box = _weight_token(mod, segs)
+    if token is not None:      # the weight's gradient flows through the token's node; this use sees the weight as a constant
+        return ConvFn.apply(mod.weight.detach(), None if mod.bias is None else mod.bias.detach(), token, box, mod, tuple(segs), act, slope,
+                            pixshuf, residual, *inputs)
+    return ConvFn.apply(mod.weight, mod.bias, None, None, mod, tuple(segs), act, slope, pixshuf, residual, *inputs)
 
 
 def to_cl16(x: torch.Tensor) -> torch.Tensor:
@@ -250,8 +328,9 @@ def realbasicvsr(model, lr: torch.Tensor):
     """(sr, lq) with gradients.  The cleaned clip is also written back into the caller's `lr`, which is what the
     reference's in-place refinement leaves there (realbasicvsr.py:26-29)."""
     n, t, c, h, w = lr.shape
-    lq = cleaner(model.cleaner, lr.reshape(n * t, c, h, w).float()).view(n, t, c, h, w)
-    sr = basicvsr(model.basicvsr, lq)
+    with batched_wgrad():
+        lq = cleaner(model.cleaner, lr.reshape(n * t, c, h, w).float()).view(n, t, c, h, w)
+        sr = basicvsr(model.basicvsr, lq)
     with torch.no_grad():
         lr.copy_(lq)
     return sr, lq

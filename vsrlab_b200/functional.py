@@ -464,7 +464,8 @@ def basicvsr_forward(bv, lrs: torch.Tensor) -> torch.Tensor:
     if _wants_grad(bv):
         from . import autograd as AG
         ops.require_cuda(lrs, "lrs")
-        return AG.basicvsr(bv, lrs.float())
+        with AG.batched_wgrad():
+            return AG.basicvsr(bv, lrs.float())
     lrs = _check_input(lrs, "lrs").contiguous()
     return _basicvsr_run(bv, lrs, current_dtype())
 
