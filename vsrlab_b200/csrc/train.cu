@@ -152,6 +152,148 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(WgradParams P) {
 }
 
 // ---------------------------------------------------------------------------------------
+// bf16 weight gradient on the warp-level tensor-core path (mma.sync m16n8k16) for the shapes wgrad_tc_kernel does not
+// take (SPyNet's 7x7 layers, 1x1, 3-channel segments).  Same decomposition as conv_wgrad_kernel - one filter row ky and
+// one CO_T x CI_T tile per CTA, 32-pixel row chunks - but the chunk is staged as bf16 and each filter column kx is the
+// GEMM  D_kx[co][ci] += sum_q dz[q][co] * x[q + kx][ci]  (K = 32 pixels = two k16 steps).  Both operands sit pixel-major
+// in shared memory, i.e. transposed for the MMA, and are fetched with ldmatrix.trans; the kx shift is just a row offset
+// of the B fetch, so dz fragments are loaded once per k-step and reused by all kw columns.  (tcgen05 needs the pixel
+// shift in whole swizzle atoms - wgrad_tc.cu pays three halo copies for kw = 3; seven would not fit.)
+// Rows are padded by 16 bytes so the eight 16-byte rows of an ldmatrix land in different banks.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t (&r)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// keeps the first `valid` (0..8) bf16 of a 16-byte vector, zeroes the rest
+__device__ __forceinline__ uint4 keep_bf16(uint4 u, int valid) {
+    uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int left = valid - 2 * i;
+        w[i] = left >= 2 ? w[i] : (left == 1 ? (w[i] & 0xFFFFu) : 0u);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+template <int KW, int CO_T, int CI_T>
+__global__ void __launch_bounds__(256) conv_wgrad_mma_kernel(WgradParams P) {
+    constexpr int ZP = CO_T * 2 + 16, XP = CI_T * 2 + 16;             // padded row pitch in bytes
+    constexpr int WT = (CO_T / 16) * (CI_T / 16);                     // 16 x 16 warp tiles of the CTA tile
+    constexpr int TPW = WT >= 8 ? WT / 8 : 1;                         // tiles per warp
+    constexpr int KS = WT >= 8 ? 1 : (WT <= 4 ? 2 : 1);               // warps sharing a tile split the two k16 steps
+    __shared__ __align__(16) uint8_t zs[32 * ZP];
+    __shared__ __align__(16) uint8_t xs[(32 + KW - 1) * XP];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ky = blockIdx.y;
+    int z = blockIdx.z;
+    const int cib = z % P.n_ci_blk; z /= P.n_ci_blk;
+    const int cob = z % P.n_co_blk;
+    const int g = z / P.n_co_blk;
+    const int s = P.ci_blk_seg[cib], c0 = P.ci_blk_c0[cib];
+    const int co0 = cob * CO_T;
+    const int hw = P.H * P.W;
+    const int u_begin = blockIdx.x * P.units_per_cta;
+    const int u_end = min(u_begin + P.units_per_cta, P.units_g);
+    const __nv_bfloat16* zin = reinterpret_cast<const __nv_bfloat16*>(P.dz);
+    const __nv_bfloat16* xin = reinterpret_cast<const __nv_bfloat16*>(P.in[s]);
+    const int dy = ky - P.kh / 2, pad = KW / 2;
+
+    // this warp's tiles and k-steps
+    const int t_first = WT >= 8 ? warp * TPW : warp % WT;
+    const int ks_own = WT >= 8 ? -1 : warp / WT;                       // -1: both k16 steps
+    const bool active = WT >= 8 || ks_own < KS;
+    float acc[TPW][KW][2][4];
+#pragma unroll
+    for (int t = 0; t < TPW; ++t)
+#pragma unroll
+        for (int k = 0; k < KW; ++k)
+#pragma unroll
+            for (int n = 0; n < 2; ++n)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[t][k][n][i] = 0.f;
+    const uint32_t zs0 = (uint32_t)__cvta_generic_to_shared(zs), xs0 = (uint32_t)__cvta_generic_to_shared(xs);
+    const int lj = lane >> 3, lr = lane & 7;                            // ldmatrix: matrix index and row of this lane's address
+
+    for (int u = u_begin; u < u_end; ++u) {
+        const int xc = u % P.chunks_per_row;
+        const int rowi = u / P.chunks_per_row;
+        const int y = rowi % P.H;
+        const long long img = (long long)g * P.imgs_per_group + rowi / P.H;
+        const int x0 = xc * 32;
+        const int yy = y + dy;
+        __syncthreads();
+        for (int i = tid; i < 32 * (CO_T / 8); i += 256) {            // dz chunk [32 px][CO_T] bf16
+            const int lp = i / (CO_T / 8), lc = (i % (CO_T / 8)) * 8;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (x0 + lp < P.W && co0 + lc < P.dz_c) {
+                v = __ldg(reinterpret_cast<const uint4*>(zin + (img * hw + (long long)y * P.W + x0 + lp) * P.dz_c + co0 + lc));
+                v = keep_bf16(v, P.cout - (co0 + lc));
+            }
+            *reinterpret_cast<uint4*>(zs + lp * ZP + lc * 2) = v;
+        }
+        for (int i = tid; i < (32 + KW - 1) * (CI_T / 8); i += 256) { // extended strip: image columns x0 - pad + e
+            const int ep = i / (CI_T / 8), lc = (i % (CI_T / 8)) * 8;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            const int xx = x0 - pad + ep;
+            if (yy >= 0 && yy < P.H && xx >= 0 && xx < P.W && c0 + lc < P.in_c[s]) {
+                v = __ldg(reinterpret_cast<const uint4*>(xin + (img * hw + (long long)yy * P.W + xx) * P.in_c[s] + c0 + lc));
+                v = keep_bf16(v, P.seg_c[s] - (c0 + lc));
+            }
+            *reinterpret_cast<uint4*>(xs + ep * XP + lc * 2) = v;
+        }
+        __syncthreads();
+        if (active) {
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                if (ks_own >= 0 && ks != ks_own) continue;
+                const int q0 = ks * 16;
+#pragma unroll
+                for (int t = 0; t < TPW; ++t) {
+                    const int tile = t_first + t;
+                    const int co_off = (tile / (CI_T / 16)) * 16, ci_off = (tile % (CI_T / 16)) * 16;
+                    uint32_t a[4];
+                    ldsm_x4_t(zs0 + (uint32_t)((q0 + (lj >> 1) * 8 + lr) * ZP + (co_off + (lj & 1) * 8) * 2), a);
+#pragma unroll
+                    for (int k = 0; k < KW; ++k) {
+                        uint32_t b[4];
+                        ldsm_x4_t(xs0 + (uint32_t)((q0 + k + (lj & 1) * 8 + lr) * XP + (ci_off + (lj >> 1) * 8) * 2), b);
+                        mma_bf16_16816(acc[t][k][0], a, b[0], b[1]);
+                        mma_bf16_16816(acc[t][k][1], a, b[2], b[3]);
+                    }
+                }
+            }
+        }
+    }
+    if (!active) return;
+    const int taps = P.kh * KW;
+    const int gq = lane >> 2, tq = lane & 3;
+#pragma unroll
+    for (int t = 0; t < TPW; ++t) {
+        const int tile = t_first + t;
+        const int co_off = (tile / (CI_T / 16)) * 16, ci_off = (tile % (CI_T / 16)) * 16;
+#pragma unroll
+        for (int k = 0; k < KW; ++k)
+#pragma unroll
+            for (int n = 0; n < 2; ++n)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int co = co0 + co_off + gq + (i >> 1) * 8;
+                    const int ci = c0 + ci_off + n * 8 + tq * 2 + (i & 1);
+                    if (co < P.cout && ci < P.seg_c[s])
+                        atomicAdd(P.dw + (((size_t)g * P.cout + co) * P.cin_total + P.seg_off[s] + ci) * taps + ky * KW + k,
+                                  acc[t][k][n][i]);
+                }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // flow_warp backward.  C/8 (bf16) or C/4 (fp32) threads per pixel as in the forward kernel; dx is an fp32
 // buffer (zeroed by the caller) updated with atomics; dflow gets the channel-reduced tap derivative.
 // ---------------------------------------------------------------------------------------
@@ -310,13 +452,13 @@ int vsrb_conv2d_wgrad(const vsrb_conv_geom* g, const void* const* in, const int3
     const bool tc_ok = g->dtype == VSRB_BF16 && g->kh == 3 && g->kw == 3 && g->groups == 1 && dz_c >= g->cout &&
                        (reinterpret_cast<uintptr_t>(dz) & 15) == 0 && !getenv("VSRB_WGRAD_SIMT");
     bool on_tc[4] = {false, false, false, false};
-    // (co, ci) tile of the FFMA kernel: as narrow as its segments allow (bf16 only; fp32 keeps 64 x 64)
+    // (co, ci) tile of the mma.sync kernel: as narrow as its segments allow (the FFMA kernels keep 64 x 64)
     int co_t = 64, ci_t = 64, cmax = 0;
     for (int s = 0; s < g->n_seg; ++s) {
         on_tc[s] = tc_ok && g->seg_c[s] % 64 == 0 && (reinterpret_cast<uintptr_t>(in[s]) & 15) == 0;
         if (!on_tc[s] && g->seg_c[s] > cmax) cmax = g->seg_c[s];
     }
-    if (g->dtype == VSRB_BF16) {
+    if (g->dtype == VSRB_BF16 && !getenv("VSRB_WGRAD_FFMA")) {
         co_t = g->cout <= 16 ? 16 : (g->cout <= 32 ? 32 : 64);
         ci_t = cmax <= 16 ? 16 : (cmax <= 32 ? 32 : 64);
     }
@@ -362,29 +504,37 @@ int vsrb_conv2d_wgrad(const vsrb_conv_geom* g, const void* const* in, const int3
     P.units_per_cta = (int)per;
     dim3 grid((unsigned)((units_g + per - 1) / per), g->kh, P.n_co_blk * P.n_ci_blk * g->groups);
     cudaStream_t st = (cudaStream_t)stream;
-#define VSRB_WG_KW(T, CO, CI)                                                              \
-    do {                                                                                    \
-        if (g->kw == 1) conv_wgrad_kernel<T, 1, CO, CI><<<grid, 256, 0, st>>>(P);           \
-        else if (g->kw == 3) conv_wgrad_kernel<T, 3, CO, CI><<<grid, 256, 0, st>>>(P);      \
-        else if (g->kw == 7) conv_wgrad_kernel<T, 7, CO, CI><<<grid, 256, 0, st>>>(P);      \
-        else {                                                                              \
-            set_error("wgrad: kernel width %d unsupported", g->kw);                         \
-            return VSRB_E_ARG;                                                              \
-        }                                                                                   \
+#define VSRB_WG_KW(KERN, CO, CI)                                                       \
+    do {                                                                                \
+        if (g->kw == 1) KERN(1, CO, CI)<<<grid, 256, 0, st>>>(P);                       \
+        else if (g->kw == 3) KERN(3, CO, CI)<<<grid, 256, 0, st>>>(P);                  \
+        else if (g->kw == 7) KERN(7, CO, CI)<<<grid, 256, 0, st>>>(P);                  \
+        else {                                                                          \
+            set_error("wgrad: kernel width %d unsupported", g->kw);                     \
+            return VSRB_E_ARG;                                                          \
+        }                                                                               \
     } while (0)
-#define VSRB_WG_CI(T, CO)                                  \
+#define VSRB_WG_CI(KERN, CO)                               \
     do {                                                    \
-        if (ci_t == 16) VSRB_WG_KW(T, CO, 16);              \
-        else if (ci_t == 32) VSRB_WG_KW(T, CO, 32);         \
-        else VSRB_WG_KW(T, CO, 64);                         \
+        if (ci_t == 16) VSRB_WG_KW(KERN, CO, 16);           \
+        else if (ci_t == 32) VSRB_WG_KW(KERN, CO, 32);      \
+        else VSRB_WG_KW(KERN, CO, 64);                      \
     } while (0)
-    if (g->dtype == VSRB_BF16) {
-        if (co_t == 16) VSRB_WG_CI(__nv_bfloat16, 16);
-        else if (co_t == 32) VSRB_WG_CI(__nv_bfloat16, 32);
-        else VSRB_WG_CI(__nv_bfloat16, 64);
+#define VSRB_K_MMA(KW, CO, CI) conv_wgrad_mma_kernel<KW, CO, CI>
+#define VSRB_K_F32(KW, CO, CI) conv_wgrad_kernel<float, KW, CO, CI>
+#define VSRB_K_FFMA16(KW, CO, CI) conv_wgrad_kernel<__nv_bfloat16, KW, CO, CI>
+    if (g->dtype == VSRB_BF16 && !getenv("VSRB_WGRAD_FFMA")) {
+        if (co_t == 16) VSRB_WG_CI(VSRB_K_MMA, 16);
+        else if (co_t == 32) VSRB_WG_CI(VSRB_K_MMA, 32);
+        else VSRB_WG_CI(VSRB_K_MMA, 64);
+    } else if (g->dtype == VSRB_BF16) {                    // cross-check path: the FFMA kernel on bf16 data, 64 x 64 tiles
+        VSRB_WG_KW(VSRB_K_FFMA16, 64, 64);
     } else {
-        VSRB_WG_KW(float, 64, 64);
+        VSRB_WG_KW(VSRB_K_F32, 64, 64);
     }
+#undef VSRB_K_FFMA16
+#undef VSRB_K_F32
+#undef VSRB_K_MMA
 #undef VSRB_WG_CI
 #undef VSRB_WG_KW
     VSRB_LAUNCH_CHECK();
