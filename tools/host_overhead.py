@@ -43,6 +43,17 @@ for _ in range(300):
     o = AG.conv(cv, [xx], [(0, 64)], "relu"); o.backward(g)
 t1 = time.perf_counter(); torch.cuda.synchronize(); t2 = time.perf_counter()
 print(f"autograd conv fwd+bwd: {(t1-t0)/300*1e6:.1f} us per call host, {(t2-t0)/300*1e6:.1f} us incl. GPU drain")
+for rep in range(2):
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(300):
+        o = AG.conv(cv, [xx], [(0, 64)], "relu"); o.backward(g)
+    t1 = time.perf_counter(); torch.cuda.synchronize(); t2 = time.perf_counter()
+    print(f"repeat {rep}: fwd+bwd {(t1-t0)/300*1e6:.1f} us host, {(t2-t0)/300*1e6:.1f} us incl. GPU drain")
+torch.cuda.synchronize(); t0 = time.perf_counter()
+for _ in range(300):
+    o = AG.conv(cv, [xx], [(0, 64)], "relu"); o.backward(g); xx.grad = None; cv.weight.grad = None; cv.bias.grad = None
+t1 = time.perf_counter(); torch.cuda.synchronize(); t2 = time.perf_counter()
+print(f"grads reset each iteration: fwd+bwd {(t1-t0)/300*1e6:.1f} us host, {(t2-t0)/300*1e6:.1f} us incl. GPU drain")
 import cProfile, pstats
 pr = cProfile.Profile(); pr.enable()
 for _ in range(20):

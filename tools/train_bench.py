@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--frames", type=int, default=15)
     ap.add_argument("--blocks", type=int, default=5)
     ap.add_argument("--train-flow", type=int, default=1)
+    ap.add_argument("--host-profile", action="store_true", help="cProfile one step on the host (stderr)")
     a = ap.parse_args()
     import torch.distributed as dist
     from vsrlab.vsr.models.RealBasicVSR.realbasicvsr import RealBasicVSR
@@ -71,6 +72,18 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.steps
+    if a.host_profile and rank == 0:
+        import cProfile
+        import pstats
+        pr = cProfile.Profile()
+        t0 = time.perf_counter()
+        pr.enable()
+        step()
+        pr.disable()
+        t1 = time.perf_counter()
+        torch.cuda.synchronize()
+        print(f"host time of one step {1e3 * (t1 - t0):.1f} ms (profiler on), +{1e3 * (time.perf_counter() - t1):.1f} ms GPU drain", file=sys.stderr)
+        pstats.Stats(pr, stream=sys.stderr).sort_stats("tottime").print_stats(28)
     ops.PROFILE = []
     step()
     torch.cuda.synchronize()

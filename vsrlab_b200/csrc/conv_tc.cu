@@ -253,6 +253,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     uint32_t crank = 0;                                         // rank in the CTA pair (0 = leader)
     if constexpr (kPair) crank = cluster_ctarank();
 
+    // Prologue in two steps so the first loads leave as early as possible: (1) barriers exist (CTA- or pair-wide sync),
+    // after which the producer warp starts; (2) the other eleven warps meet once more for the TMEM address and the bias.
+    if (warp == 0 && lane == 0) {
+        for (int o = 0; o < P.n_ops; ++o) prefetch_tensormap(&P.tmap[o]);
+        if (P.res_mma) prefetch_tensormap(&P.rmap);
+        if (kStaged) prefetch_tensormap(&P.smap[0]);
+    }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < P.num_slots; ++i) {
             mbar_init(full0 + 8 * i, 1);
@@ -266,19 +273,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         mbar_init(wready, 2);
         fence_barrier_init();
     }
-    if (warp == 2) {
-        if constexpr (kPair) tmem_alloc_pair(smem_u32(tmem_slot), 512);
-        else tmem_alloc(smem_u32(tmem_slot), 512);
-    }
-    if (warp == 3)
-        for (int i = lane; i < P.n_tile; i += 32) bias_s[i] = __ldg(P.epi.bias + (size_t)g * P.epi.cout_pad + qb * P.n_tile + i);
-    tc_fence_before();
     if constexpr (kPair) cluster_sync_all();       // the peer's barriers must exist before anything is signalled across
     else __syncthreads();
-    tc_fence_after();
-    if (threadIdx.x == 0) trace_stamp(P.debug, 1);
     griddep_launch();      // the next kernel on the stream may start its own prologue as SMs free up
-    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+    uint32_t tmem_base = 0;
+    if (warp >= 1) {
+        if (warp == 2) {
+            if constexpr (kPair) tmem_alloc_pair(smem_u32(tmem_slot), 512);
+            else tmem_alloc(smem_u32(tmem_slot), 512);
+        }
+        if (warp == 3)
+            for (int i = lane; i < P.n_tile; i += 32) bias_s[i] = __ldg(P.epi.bias + (size_t)g * P.epi.cout_pad + qb * P.n_tile + i);
+        tc_fence_before();
+        asm volatile("bar.sync 5, %0;" ::"n"(kThreads - 32) : "memory");
+        tc_fence_after();
+        tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+    }
+    if (threadIdx.x == 32) trace_stamp(P.debug, 1);
     const uint8_t* wsrc = P.w + ((size_t)g * P.n_blocks + qb) * P.wblock_bytes;
     bool dead = false;
 

@@ -62,6 +62,9 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
 __device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
     asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
                      reinterpret_cast<uint64_t>(map)),
