@@ -134,6 +134,67 @@ def test_conv_kernels(dev, mode, case):
         assert out[..., co:].abs().max().item() == 0
 
 
+PAIR_CASES = [
+    # cin, cout, k, n, h, w, residual, pixshuf : shapes that take the CTA-pair (cta_group::2) kernels, with odd tile
+    # counts (a dummy tile in the last pair), a single tile, ragged borders, and every kernel variant
+    (64, 64, 3, 1, 4, 30, False, 0),        # exactly one tile: the peer CTA only has the dummy
+    (64, 64, 3, 1, 12, 31, True, 0),        # 3 x 2 tiles, residual through the identity MMA
+    (64, 64, 3, 3, 37, 52, False, 0),       # odd tile count, 3 images
+    (32, 32, 3, 2, 20, 33, False, 0),       # 32-wide stacked tile (N = 96, two sub-tiles per stage)
+    (64, 256, 3, 1, 17, 23, False, 2),      # classic layout, N = 128, pixel-shuffle store
+    (64, 32, 7, 2, 13, 29, False, 0),       # 7x7, 64-byte K rows, half of 200 KB of weights resident per CTA
+    (32, 64, 7, 1, 9, 27, False, 0),        # 7x7, two N blocks
+    (32, 16, 7, 2, 6, 10, False, 0),
+]
+
+
+@pytest.mark.parametrize("case", PAIR_CASES, ids=lambda c: f"k{c[2]}_{c[0]}to{c[1]}_{c[4]}x{c[5]}")
+def test_cta_pair_kernels_match_single_cta(dev, case, monkeypatch):
+    """The pair kernels issue the same MMAs in the same order on the same operands as the single-CTA kernels, only as
+    M = 256 instructions across two SMs: outputs must be bit-identical (and both must match the oracle conv)."""
+    from vsrlab_b200 import ops
+    from vsrlab_b200._lib import ACT_NONE, ACT_RELU, BF16, VsrbError
+    cin, cout, k, n, h, w, residual, pixshuf = case
+    g = torch.Generator().manual_seed(cin * 131 + cout + h)
+    cv = torch.nn.Conv2d(cin, cout, k, 1, k // 2)
+    with torch.no_grad():
+        cv.weight.copy_(torch.randn(cv.weight.shape, generator=g) / (cin * k * k) ** 0.5)
+        cv.bias.copy_(torch.randn(cv.bias.shape, generator=g) * 0.1)
+    x = torch.randn(n, cin, h, w, generator=g)
+    res = torch.randn(n, cout, h, w, generator=g) if residual else None
+    pc = ops.PackedConv([cv.to(dev)], [(0, cin)], BF16, pixshuf)
+    xt, ca = to_dev_nhwc(x, BF16, dev)
+    r = pixshuf or 1
+    co = cout // (r * r)
+    oc = (co + 15) // 16 * 16
+    rt, rc = (None, 0) if res is None else to_dev_nhwc(res, BF16, dev)
+    outs = []
+    for no_pair in ("", "1"):
+        if no_pair:
+            monkeypatch.setenv("VSRB_TC_NO_PAIR", "1")
+        else:
+            monkeypatch.delenv("VSRB_TC_NO_PAIR", raising=False)
+        out = torch.full((n, h * r, w * r, oc), 7.0, dtype=torch.bfloat16, device=dev)
+        try:
+            ops.conv2d_fwd(pc, [xt], [ca], n, h, w, act=ACT_NONE if residual else ACT_RELU, out=out, out_c=oc, residual=rt, res_c=rc)
+        except VsrbError as e:
+            # plans that keep half of a large weight block resident per CTA (7x7 with >= 32-channel K rows) only exist
+            # as pairs: without them the library must refuse loudly, not fall back
+            assert no_pair and k == 7 and "does not fit" in str(e)
+            continue
+        torch.cuda.synchronize()
+        assert ops.debug_status() == 0
+        outs.append(out)
+    if len(outs) == 2:
+        assert torch.equal(outs[0], outs[1])
+    y = F.conv2d(bf16r(x), bf16r(cv.weight.detach().cpu()), cv.bias.detach().cpu(), padding=k // 2)
+    y = y + bf16r(res) if residual else O.relu(y)
+    if pixshuf:
+        y = O.pixel_shuffle(y, 2)
+    got = from_dev_nhwc(outs[0], co, BF16)
+    assert (got - y).abs().max().item() <= 2.0 ** -8 * max(y.abs().max().item(), 1.0)
+
+
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
 @pytest.mark.parametrize("pad", ["zeros", "border"])
 def test_flow_warp_golden_and_adversarial(dev, golden, mode, pad):

@@ -147,3 +147,80 @@ def test_realbasicvsr_training_step_gradients(dev, train_flow):
         assert cos(p.grad.cpu(), ref) > (0.90 if "spynet" in name else 0.97), (name, cos(p.grad.cpu(), ref))
     assert cos(torch.cat(got), torch.cat(want)) > 0.99
     assert rel(torch.cat(got), torch.cat(want)) < 0.1
+
+
+@pytest.mark.parametrize("case", [
+    # (segs, cout, k, h, w): shapes of the mma.sync weight-gradient kernel (7x7, 1x1, narrow segments, ragged widths)
+    ([(0, 8)], 32, 7, 13, 37),
+    ([(0, 32)], 64, 7, 9, 40),
+    ([(0, 64)], 32, 7, 12, 33),
+    ([(0, 16)], 2, 7, 6, 10),
+    ([(0, 64), (64, 64)], 64, 1, 10, 35),
+    ([(0, 3)], 64, 3, 11, 31),
+    ([(0, 64)], 3, 3, 11, 31),
+], ids=lambda c: f"k{c[2]}_{c[0]}_{c[1]}")
+def test_wgrad_mma_matches_ffma_and_fp32(dev, case, monkeypatch):
+    """dW / db of the warp-MMA kernel against the FFMA kernel on the same bf16 data (only the summation order differs)
+    and against fp32 autograd."""
+    from vsrlab_b200 import autograd as AG, ops
+    segs, cout, k, h, w = case
+    g = torch.Generator().manual_seed(5)
+    cin = sum(c for _, c in segs)
+    B = 3
+    x = bf16r(torch.randn(B, cin, h, w, generator=g))
+    dz = bf16r(torch.randn(B, cout, h, w, generator=g))
+    cv = torch.nn.Conv2d(cin, cout, k, 1, k // 2)
+    geom = AG._wgrad_geom(cv, tuple(segs))
+    ins = [AG.to_cl16(x[:, off:off + c].to(dev)) for off, c in segs]
+    dzd = AG.to_cl16(dz.to(dev))
+    res = []
+    for ffma in ("", "1"):
+        if ffma:
+            monkeypatch.setenv("VSRB_WGRAD_FFMA", "1")
+        else:
+            monkeypatch.delenv("VSRB_WGRAD_FFMA", raising=False)
+        dw = torch.zeros(cout, cin, k, k, device=dev)
+        db = torch.zeros(cout, device=dev)
+        ops.conv2d_wgrad(geom, ins, [t.shape[1] for t in ins], dzd, dzd.shape[1], B, h, w, cin, dw, db)
+        torch.cuda.synchronize()
+        res.append((dw.cpu(), db.cpu()))
+    wr = torch.zeros(cout, cin, k, k, requires_grad=True)
+    (F.conv2d(x, wr, None, padding=k // 2) * dz).sum().backward()
+    scale = wr.grad.abs().max().item()
+    assert (res[0][0] - res[1][0]).abs().max().item() <= 1e-4 * scale
+    assert (res[0][0] - wr.grad).abs().max().item() <= 1e-4 * scale
+    assert (res[0][1] - dz.sum((0, 2, 3))).abs().max().item() <= 1e-3 * dz.sum((0, 2, 3)).abs().max().item()
+
+
+def test_batched_wgrad_equals_per_use(dev):
+    """Inside batched_wgrad() a conv used several times gets ONE weight-gradient launch from its _WeightNode; the
+    parameter gradients must equal those of the per-use path, and hooks on the parameter must fire exactly once."""
+    from vsrlab_b200 import autograd as AG
+    torch.manual_seed(2)
+    cv = torch.nn.Conv2d(64, 64, 3, 1, 1).to(dev)
+    xs = [AG.to_cl16(bf16r(torch.randn(2, 64, 12, 20)).to(dev)).requires_grad_(True) for _ in range(3)]
+    fired = []
+    cv.weight.register_hook(lambda g_: fired.append(1))
+
+    def run(batched):
+        for t in xs:
+            t.grad = None
+        cv.zero_grad(set_to_none=True)
+        fired.clear()
+        y = 0
+        if batched:
+            with AG.batched_wgrad():
+                for i, t in enumerate(xs):
+                    y = y + AG.conv(cv, [t], [(0, 64)], "relu").float().mul(i + 1.0).sum()
+        else:
+            for i, t in enumerate(xs):
+                y = y + AG.conv(cv, [t], [(0, 64)], "relu").float().mul(i + 1.0).sum()
+        y.backward()
+        return cv.weight.grad.clone(), cv.bias.grad.clone(), [t.grad.clone() for t in xs], len(fired)
+
+    w0, b0, g0, n0 = run(False)
+    w1, b1, g1, n1 = run(True)
+    assert n1 == 1
+    assert rel(w1, w0) < 1e-5 and rel(b1, b0) < 1e-5
+    for a, b in zip(g1, g0):
+        assert torch.equal(a, b)
