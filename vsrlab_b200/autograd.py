@@ -232,9 +232,96 @@ def to_cl16(x: torch.Tensor) -> torch.Tensor:
     return _cl(x)
 
 
+class ResBlockFn(torch.autograd.Function):
+    """A whole ResidualBlock (conv.py:94-103: stem conv + LeakyReLU, then B x [conv, ReLU, conv, + identity]) as ONE autograd
+    node.  The recurrent propagation calls it 2T times per clip on small batches, where the per-node cost of torch autograd
+    and of `Function.apply` (~50 us per conv, forward + backward) exceeded the kernels' run time; here the 1 + 2B forward
+    launches and the backward (input-gradient convs with the skip connection fused as their residual, ReLU masks as one
+    threshold_backward each, weight gradients parked for the convs' _WeightNodes) are plain loops."""
+
+    @staticmethod
+    def forward(ctx, rb, segs, n_in, boxes, *tensors):
+        from .functional import packed
+        ins = [_cl(t) for t in tensors[:n_in]]
+        convs = [rb.conv[0]] + [c for blk in rb.res_block for c in (blk.conv1, blk.conv2)]
+        mid = convs[0].out_channels
+        b, _, h, w = ins[0].shape
+        dev = ins[0].device
+
+        def new():
+            return torch.empty((b, mid, h, w), dtype=torch.bfloat16, device=dev, memory_format=CL)
+        x = new()
+        ops.conv2d_fwd(packed([convs[0]], segs, BF16, 0), ins, [t.shape[1] for t in ins], b, h, w, act=ACT_LRELU, slope=0.1, out=x,
+                       out_c=mid)
+        saved = [x]
+        one = ((0, mid),)
+        for blk in rb.res_block:
+            t = new()
+            ops.conv2d_fwd(packed([blk.conv1], one, BF16, 0), [x], [mid], b, h, w, act=ACT_RELU, out=t, out_c=mid)
+            y = new()
+            ops.conv2d_fwd(packed([blk.conv2], one, BF16, 0), [t], [mid], b, h, w, act=ACT_NONE, out=y, out_c=mid, residual=x, res_c=mid)
+            saved += [t, y]
+            x = y
+        ctx.rb, ctx.segs, ctx.n_in, ctx.convs = rb, segs, n_in, convs
+        ctx.boxes = boxes
+        ctx.save_for_backward(*ins, *saved[:-1])
+        return x
+
+    @staticmethod
+    def backward(ctx, dy):
+        n_in, convs, segs = ctx.n_in, ctx.convs, ctx.segs
+        ins = list(ctx.saved_tensors[:n_in])
+        acts = list(ctx.saved_tensors[n_in:])          # x0, t1, x1, t2, x2, ... (the last block's output is not needed)
+        mid = convs[0].out_channels
+        b, _, h, w = ins[0].shape
+        boxes = ctx.boxes
+        one = ((0, mid),)
+
+        def park(i, xs, dz):
+            if boxes is not None and boxes[i] is not None:
+                boxes[i].append((xs, dz))
+
+        def dgrad(cv, dz, residual=None):
+            pt = _packed_transposed(cv)
+            dx = torch.empty((b, pt.cout_pad, h, w), dtype=torch.bfloat16, device=dz.device, memory_format=CL)
+            ops.conv2d_fwd(pt, [dz], [dz.shape[1]], b, h, w, act=ACT_NONE, out=dx, out_c=pt.cout_pad, residual=residual,
+                           res_c=0 if residual is None else residual.shape[1])
+            return dx
+        g = _cl(dy)
+        nb = (len(convs) - 1) // 2
+        for i in range(nb - 1, -1, -1):
+            x_in, t = acts[2 * i], acts[2 * i + 1]
+            park(2 + 2 * i, [t], g)                                   # conv2: no activation, dz = g
+            dt = dgrad(convs[2 + 2 * i], g)
+            dz1 = torch.ops.aten.threshold_backward(dt, t, 0)        # ReLU mask of conv1's output
+            park(1 + 2 * i, [x_in], dz1)
+            g = dgrad(convs[1 + 2 * i], dz1, residual=g)              # + the skip connection's gradient, fused
+        x0 = acts[0]
+        dz0 = torch.where(x0 > 0, g, g * 0.1)
+        park(0, ins, dz0)
+        d_ins: List[Optional[torch.Tensor]] = [None] * n_in
+        if any(ctx.needs_input_grad[4 + i] for i in range(n_in)):
+            dx = dgrad(convs[0], dz0)
+            for i, (off, c) in enumerate(segs):
+                if ctx.needs_input_grad[4 + i]:
+                    ca = ins[i].shape[1]
+                    d_ins[i] = dx if (n_in == 1 and ca == dx.shape[1]) else F.pad(dx[:, off:off + c], (0, 0, 0, 0, 0, ca - c))
+        return (None, None, None, None, *d_ins, *([None] * (len(ctx.needs_input_grad) - 4 - n_in)))
+
+
 def resblock(rb, inputs, segs) -> torch.Tensor:
     """ResidualBlock.forward (conv.py:101-103) on bf16 channels_last tensors."""
     mid = rb.conv[0].out_channels
+    convs = [rb.conv[0]] + [c for blk in rb.res_block for c in (blk.conv1, blk.conv2)]
+    if _WGRAD_SCOPE is not None and all(c.kernel_size == (3, 3) for c in convs):
+        # fused node; the weights' gradients flow through the convs' tokens (inputs of the node), parked per use
+        toks, boxes = [], []
+        for i, c in enumerate(convs):
+            tok, box = _weight_token(c, tuple(segs) if i == 0 else ((0, mid),))
+            boxes.append(box)
+            if tok is not None:
+                toks.append(tok)
+        return ResBlockFn.apply(rb, tuple(segs), len(inputs), boxes, *inputs, *toks)
     x = conv(rb.conv[0], inputs, segs, "lrelu")
     for blk in rb.res_block:
         t = conv(blk.conv1, [x], [(0, mid)], "relu")
