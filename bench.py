@@ -219,7 +219,7 @@ def main():
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    l0 = ops.launch_count()
+    l0, r0 = ops.launch_count(), VF.replayed_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -228,7 +228,7 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = ops.launch_count() - l0
+    launches = ops.launch_count() - l0 + VF.replayed_launches() - r0      # direct launches + kernel nodes of graph replays
     sampler.stop_flag = True
     sampler.join(timeout=2)
 

@@ -495,6 +495,13 @@ def realbasicvsr_forward(model, lr: torch.Tensor):
 GRAPHS = os.environ.get("VSRB_GRAPHS", "1") == "1"      # VSRB_GRAPHS=0: launch every kernel eagerly
 MAX_GRAPHS = 4                                          # captured (model, shape, precision) combinations kept alive
 _graphs: Dict[tuple, tuple] = {}
+# kernels of libvsrb200.so launched through graph replays (vsrb_launch_count only sees direct launches; a replay
+# launches every kernel node recorded at capture time)
+_replayed_launches = 0
+
+
+def replayed_launches() -> int:
+    return _replayed_launches
 
 
 def _weights_stamp(model) -> tuple:
@@ -520,16 +527,19 @@ def _graphed_forward(model, lr: torch.Tensor, dt: int):
         torch.cuda.current_stream(lr.device).wait_stream(side)
         torch.cuda.synchronize(lr.device)
         graph = torch.cuda.CUDAGraph()
+        k0 = ops.launch_count()
         with torch.cuda.graph(graph, stream=side):
             x_nhwc = _cleaner_run(model.cleaner, static_in.view(n * t, c, h, w), dt)
             static_sr = _basicvsr_run(model.basicvsr, static_in, dt, x_nhwc)
-        entry = (stamp, graph, static_in, static_sr, weakref.ref(model))
+        entry = (stamp, graph, static_in, static_sr, weakref.ref(model), ops.launch_count() - k0)
         _graphs.pop(key, None)
         while len(_graphs) >= MAX_GRAPHS:          # dicts keep insertion order: drop the oldest capture
             _graphs.pop(next(iter(_graphs)))
         _graphs[key] = entry
-    _, graph, static_in, static_sr, _ = entry
+    global _replayed_launches
+    _, graph, static_in, static_sr, _, n_kernels = entry
     static_in.copy_(lr)
     graph.replay()
+    _replayed_launches += n_kernels
     lr.copy_(static_in)
     return static_sr.clone(), lr
