@@ -352,11 +352,14 @@ def main():
             "clocks": sampler.summary(),
             "roofline": {"kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, all launches of a step)", "bound": "tensor",
                          "achieved": conv[1] / conv[0] / 1e12, "peak": pk["tf_sust"], "unit": "TFLOP/s",
-                         "frac": conv[1] / conv[0] / 1e12 / pk["tf_sust"], "traffic": traffic.get("conv_tc"),
+                         "frac": conv[1] / conv[0] / 1e12 / pk["tf_sust"],
+                         "traffic": (traffic.get("conv_tc") or {}).get("dram_bytes_per_launch"),
+                         "traffic_source": traffic.get("conv_tc"),
                          "peak_source": pk["src"] + " (sustained)",
                          "launches_per_step": conv[2], "share_of_step": conv[0] / max(step_s_prof, 1e-9)},
             "roofline_warp": {"kernel": "flow_warp_kernel", "bound": "hbm", "achieved": warp[1] / warp[0] / 1e9, "peak": pk["hbm"],
-                              "unit": "GB/s", "frac": warp[1] / warp[0] / 1e9 / pk["hbm"], "traffic": traffic.get("flow_warp"),
+                              "unit": "GB/s", "frac": warp[1] / warp[0] / 1e9 / pk["hbm"],
+                              "traffic": (traffic.get("flow_warp") or {}).get("dram_bytes_per_launch"), "traffic_source": traffic.get("flow_warp"),
                               "launches_per_step": warp[2], "share_of_step": warp[0] / max(step_s_prof, 1e-9),
                               "note": "in-step calls move 30 MB each (L2 resident, launch-latency bound); `standalone` is the "
                                       "same kernel on 256 feature maps (3.9 GB moved, L2 flushed)",
