@@ -220,6 +220,37 @@ __device__ __forceinline__ void epi_sr_store(const EpiParams& e, int b, int y, i
     for (int c = 0; c < 3; ++c) op[c * oplane] = v[c] + up[c];
 }
 
+// EPI_CLEAN / EPI_FLOW in two halves as well: the fp32 value the conv result is added to ...
+__device__ __forceinline__ void epi_clean_fetch(const EpiParams& e, int b, int y, int x, float (&pre)[3]) {
+    const size_t plane = (size_t)e.H * e.W;
+    const float* xp = e.f32_io + (size_t)b * 3 * plane + (size_t)y * e.W + x;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) pre[c] = xp[c * plane];
+}
+__device__ __forceinline__ void epi_flow_fetch(const EpiParams& e, int b, int y, int x, float (&pre)[3]) {
+    const float2 f = __ldg(reinterpret_cast<const float2*>(e.f32_in) + ((size_t)b * e.H + y) * e.W + x);
+    pre[0] = f.x; pre[1] = f.y; pre[2] = 0.f;
+}
+// ... and the stores (EPI_CLEAN: fp32 NCHW frame in place + its bf16 NHWC-16 shadow; EPI_FLOW: flow_up + relu(conv))
+template <typename T>
+__device__ __forceinline__ void epi_clean_store(const EpiParams& e, int b, int y, int x, const float (&v)[4], const float (&pre)[3]) {
+    const size_t plane = (size_t)e.H * e.W;
+    float* xp = e.f32_io + (size_t)b * 3 * plane + (size_t)y * e.W + x;
+    float nv[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) nv[i] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        nv[c] = pre[c] + v[c];
+        xp[c * plane] = nv[c];
+    }
+    T* op = reinterpret_cast<T*>(e.out) + (((size_t)b * e.H + y) * e.W + x) * e.out_c;
+    Act<T>::store16(op, nv);
+}
+__device__ __forceinline__ void epi_flow_store(const EpiParams& e, int b, int y, int x, const float (&v)[4], const float (&pre)[3]) {
+    reinterpret_cast<float2*>(e.f32_io)[((size_t)b * e.H + y) * e.W + x] = make_float2(pre[0] + v[0], pre[1] + v[1]);
+}
+
 // One pixel (b,y,x), 16 consecutive packed output channels starting at n0 (multiple of 16);
 // v = act(acc + bias) already applied by the caller.  `g` = weight group of image b.
 // kResDone: the caller has already added the residual.

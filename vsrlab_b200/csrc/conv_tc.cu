@@ -513,13 +513,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             // image epilogues (<= 3 real channels) of the stacked layout take a 4-channel path; EPI_SR fetches its
             // bilinear skip term while the tile's MMAs are still running
             const bool narrow = kKW > 0 && !kStaged && P.epi.mode != VSRB_EPI_NHWC;
+            // (EPI_CLEAN / EPI_FLOW likewise fetch the fp32 value they add to; plain layouts only - the split-bf16 mode
+            // keeps the generic store)
             float upv[2][3];
-            if (narrow && P.epi.mode == VSRB_EPI_SR && !dummy) {
+            const bool prefetch = narrow && !dummy && !P.epi.split && (P.epi.mode != VSRB_EPI_CLEAN || P.epi.out_c >= 16);
+            if (prefetch) {
 #pragma unroll
                 for (int m = 0; m < 2; ++m) {
                     const int y = ty * rows_tile + m * P.rows_sub + wq, xo = tx * P.UW + lane - kKW / 2;
                     upv[m][0] = upv[m][1] = upv[m][2] = 0.f;
-                    if (m < P.MT && lane >= kKW / 2 && lane < 32 - kKW / 2 && y < P.H && xo < P.W) epi_sr_up(P.epi, img, y, xo, upv[m]);
+                    if (m < P.MT && lane >= kKW / 2 && lane < 32 - kKW / 2 && y < P.H && xo < P.W) {
+                        if (P.epi.mode == VSRB_EPI_SR) epi_sr_up(P.epi, img, y, xo, upv[m]);
+                        else if (P.epi.mode == VSRB_EPI_CLEAN) epi_clean_fetch(P.epi, img, y, xo, upv[m]);
+                        else epi_flow_fetch(P.epi, img, y, xo, upv[m]);
+                    }
                 }
             }
             mbar_wait(tfull0 + 8 * acc, acc_phase, P.dbg, 5, dead);
@@ -540,9 +547,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                             float v4[4];
                             stacked_chunk16<kKW, 2, 4>(t0, P.n_tile, bias_r, act_k, lane, v4);
                             if (lane_ok && y < P.H && xo < P.W && !(P.debug & 2)) {
-                                if (P.epi.mode == VSRB_EPI_SR) {
+                                if (prefetch) {
                                     const float up[3] = {m ? upv[1][0] : upv[0][0], m ? upv[1][1] : upv[0][1], m ? upv[1][2] : upv[0][2]};
-                                    epi_sr_store(P.epi, img, y, xo, v4, up);
+                                    if (P.epi.mode == VSRB_EPI_SR) epi_sr_store(P.epi, img, y, xo, v4, up);
+                                    else if (P.epi.mode == VSRB_EPI_CLEAN) epi_clean_store<__nv_bfloat16>(P.epi, img, y, xo, v4, up);
+                                    else epi_flow_store(P.epi, img, y, xo, v4, up);
                                 } else {
                                     float v[16];
 #pragma unroll
