@@ -32,11 +32,13 @@ def _cl(t: torch.Tensor) -> torch.Tensor:
 
 
 def _packed_transposed(conv) -> ops.PackedConvT:
-    key = id(conv)
+    """`conv`: one module, or a tuple of same-shaped modules (weight groups)."""
+    convs = tuple(conv) if isinstance(conv, (list, tuple)) else (conv,)
+    key = tuple(id(c) for c in convs)
     pc = _packed_t.get(key)
-    if pc is None or pc.stamp != ops.PackedConv.stamp_of([conv]) or pc.owner() is not conv:   # ids are recycled
-        pc = ops.PackedConvT(conv, BF16)
-        pc.owner = weakref.ref(conv)
+    if pc is None or pc.stamp != ops.PackedConv.stamp_of(convs) or any(r() is not c for r, c in zip(pc.owners_t, convs)):
+        pc = ops.PackedConvT(convs, BF16)                       # (ids are recycled: the owners must be the same live modules)
+        pc.owners_t = [weakref.ref(c) for c in convs]
         _packed_t[key] = pc
     return pc
 
@@ -240,68 +242,71 @@ class ResBlockFn(torch.autograd.Function):
     threshold_backward each, weight gradients parked for the convs' _WeightNodes) are plain loops."""
 
     @staticmethod
-    def forward(ctx, rb, segs, n_in, boxes, *tensors):
+    def forward(ctx, rbs, segs, n_in, boxes, *tensors):
+        """`rbs`: tuple of G same-shaped ResidualBlocks = weight groups; images [g*B/G, (g+1)*B/G) belong to group g (the two
+        propagation directions run as one launch per layer).  `boxes[layer][g]`: where that conv's (inputs, dz) are parked."""
         from .functional import packed
         ins = [_cl(t) for t in tensors[:n_in]]
-        convs = [rb.conv[0]] + [c for blk in rb.res_block for c in (blk.conv1, blk.conv2)]
-        mid = convs[0].out_channels
+        per_g = [[rb.conv[0]] + [c for blk in rb.res_block for c in (blk.conv1, blk.conv2)] for rb in rbs]
+        layers = [tuple(cg[j] for cg in per_g) for j in range(len(per_g[0]))]          # layer j = its conv in every group
+        mid = layers[0][0].out_channels
         b, _, h, w = ins[0].shape
         dev = ins[0].device
 
         def new():
             return torch.empty((b, mid, h, w), dtype=torch.bfloat16, device=dev, memory_format=CL)
         x = new()
-        ops.conv2d_fwd(packed([convs[0]], segs, BF16, 0), ins, [t.shape[1] for t in ins], b, h, w, act=ACT_LRELU, slope=0.1, out=x,
+        ops.conv2d_fwd(packed(list(layers[0]), segs, BF16, 0), ins, [t.shape[1] for t in ins], b, h, w, act=ACT_LRELU, slope=0.1, out=x,
                        out_c=mid)
         saved = [x]
         one = ((0, mid),)
-        for blk in rb.res_block:
+        for j in range(1, len(layers), 2):
             t = new()
-            ops.conv2d_fwd(packed([blk.conv1], one, BF16, 0), [x], [mid], b, h, w, act=ACT_RELU, out=t, out_c=mid)
+            ops.conv2d_fwd(packed(list(layers[j]), one, BF16, 0), [x], [mid], b, h, w, act=ACT_RELU, out=t, out_c=mid)
             y = new()
-            ops.conv2d_fwd(packed([blk.conv2], one, BF16, 0), [t], [mid], b, h, w, act=ACT_NONE, out=y, out_c=mid, residual=x, res_c=mid)
+            ops.conv2d_fwd(packed(list(layers[j + 1]), one, BF16, 0), [t], [mid], b, h, w, act=ACT_NONE, out=y, out_c=mid, residual=x,
+                           res_c=mid)
             saved += [t, y]
             x = y
-        ctx.rb, ctx.segs, ctx.n_in, ctx.convs = rb, segs, n_in, convs
-        ctx.boxes = boxes
+        ctx.segs, ctx.n_in, ctx.layers, ctx.boxes = segs, n_in, layers, boxes
         ctx.save_for_backward(*ins, *saved[:-1])
         return x
 
     @staticmethod
     def backward(ctx, dy):
-        n_in, convs, segs = ctx.n_in, ctx.convs, ctx.segs
+        n_in, layers, segs, boxes = ctx.n_in, ctx.layers, ctx.segs, ctx.boxes
         ins = list(ctx.saved_tensors[:n_in])
         acts = list(ctx.saved_tensors[n_in:])          # x0, t1, x1, t2, x2, ... (the last block's output is not needed)
-        mid = convs[0].out_channels
         b, _, h, w = ins[0].shape
-        boxes = ctx.boxes
-        one = ((0, mid),)
+        G = len(layers[0])
+        n = b // G
 
-        def park(i, xs, dz):
-            if boxes is not None and boxes[i] is not None:
-                boxes[i].append((xs, dz))
+        def park(j, xs, dz):
+            for gi in range(G):
+                if boxes[j][gi] is not None:
+                    boxes[j][gi].append(([t[gi * n:(gi + 1) * n] for t in xs], dz[gi * n:(gi + 1) * n]))
 
-        def dgrad(cv, dz, residual=None):
-            pt = _packed_transposed(cv)
+        def dgrad(j, dz, residual=None):
+            pt = _packed_transposed(layers[j])
             dx = torch.empty((b, pt.cout_pad, h, w), dtype=torch.bfloat16, device=dz.device, memory_format=CL)
             ops.conv2d_fwd(pt, [dz], [dz.shape[1]], b, h, w, act=ACT_NONE, out=dx, out_c=pt.cout_pad, residual=residual,
                            res_c=0 if residual is None else residual.shape[1])
             return dx
         g = _cl(dy)
-        nb = (len(convs) - 1) // 2
+        nb = (len(layers) - 1) // 2
         for i in range(nb - 1, -1, -1):
             x_in, t = acts[2 * i], acts[2 * i + 1]
             park(2 + 2 * i, [t], g)                                   # conv2: no activation, dz = g
-            dt = dgrad(convs[2 + 2 * i], g)
+            dt = dgrad(2 + 2 * i, g)
             dz1 = torch.ops.aten.threshold_backward(dt, t, 0)        # ReLU mask of conv1's output
             park(1 + 2 * i, [x_in], dz1)
-            g = dgrad(convs[1 + 2 * i], dz1, residual=g)              # + the skip connection's gradient, fused
+            g = dgrad(1 + 2 * i, dz1, residual=g)                     # + the skip connection's gradient, fused
         x0 = acts[0]
         dz0 = torch.where(x0 > 0, g, g * 0.1)
         park(0, ins, dz0)
         d_ins: List[Optional[torch.Tensor]] = [None] * n_in
         if any(ctx.needs_input_grad[4 + i] for i in range(n_in)):
-            dx = dgrad(convs[0], dz0)
+            dx = dgrad(0, dz0)
             for i, (off, c) in enumerate(segs):
                 if ctx.needs_input_grad[4 + i]:
                     ca = ins[i].shape[1]
@@ -310,18 +315,26 @@ class ResBlockFn(torch.autograd.Function):
 
 
 def resblock(rb, inputs, segs) -> torch.Tensor:
-    """ResidualBlock.forward (conv.py:101-103) on bf16 channels_last tensors."""
-    mid = rb.conv[0].out_channels
-    convs = [rb.conv[0]] + [c for blk in rb.res_block for c in (blk.conv1, blk.conv2)]
-    if _WGRAD_SCOPE is not None and all(c.kernel_size == (3, 3) for c in convs):
+    """ResidualBlock.forward (conv.py:101-103) on bf16 channels_last tensors.  `rb` may be a tuple of same-shaped blocks:
+    weight groups over equal slices of the batch (needs a batched_wgrad scope)."""
+    rbs = tuple(rb) if isinstance(rb, (list, tuple)) else (rb,)
+    mid = rbs[0].conv[0].out_channels
+    per_g = [[r.conv[0]] + [c for blk in r.res_block for c in (blk.conv1, blk.conv2)] for r in rbs]
+    if _WGRAD_SCOPE is not None and all(c.kernel_size == (3, 3) for cg in per_g for c in cg):
         # fused node; the weights' gradients flow through the convs' tokens (inputs of the node), parked per use
         toks, boxes = [], []
-        for i, c in enumerate(convs):
-            tok, box = _weight_token(c, tuple(segs) if i == 0 else ((0, mid),))
-            boxes.append(box)
-            if tok is not None:
-                toks.append(tok)
-        return ResBlockFn.apply(rb, tuple(segs), len(inputs), boxes, *inputs, *toks)
+        for j in range(len(per_g[0])):
+            row = []
+            for cg in per_g:
+                tok, box = _weight_token(cg[j], tuple(segs) if j == 0 else ((0, mid),))
+                row.append(box)
+                if tok is not None:
+                    toks.append(tok)
+            boxes.append(row)
+        return ResBlockFn.apply(rbs, tuple(segs), len(inputs), boxes, *inputs, *toks)
+    if len(rbs) != 1:
+        raise VsrbError("grouped residual blocks need a batched_wgrad() scope and 3x3 convs")
+    rb = rbs[0]
     x = conv(rb.conv[0], inputs, segs, "lrelu")
     for blk in rb.res_block:
         t = conv(blk.conv1, [x], [(0, mid)], "relu")
@@ -384,20 +397,18 @@ def basicvsr(bv, lrs: torch.Tensor) -> torch.Tensor:
             fb, ff = fl[:m].view(n, t - 1, h, w, 2), fl[m:].view(n, t - 1, h, w, 2)
     lr16 = to_cl16(lrs.reshape(n * t, c, h, w)).view(n, t, 16, h, w)
     segs = [(3, mid), (0, 3)]
+    # both directions advance together: step k runs frame t-1-k of the backward chain and frame k of the forward chain as
+    # the two weight groups of one launch per layer (images [0, n) backward, [n, 2n) forward)
     back: List[Optional[torch.Tensor]] = [None] * t
-    feat = torch.zeros((n, mid, h, w), dtype=torch.bfloat16, device=lrs.device).contiguous(memory_format=CL)
-    for i in range(t - 1, -1, -1):
-        if i < t - 1:
-            feat = WarpFn.apply(feat, fb[:, i], False)
-        feat = resblock(bv.backward_resblocks, [feat, _cl(lr16[:, i])], segs)
-        back[i] = feat
-    fwd: List[torch.Tensor] = []
-    feat = torch.zeros_like(feat)
-    for i in range(t):
-        if i > 0:
-            feat = WarpFn.apply(feat, ff[:, i - 1], False)
-        feat = resblock(bv.forward_resblocks, [feat, _cl(lr16[:, i])], segs)
-        fwd.append(feat)
+    fwd: List[Optional[torch.Tensor]] = [None] * t
+    feat = torch.zeros((2 * n, mid, h, w), dtype=torch.bfloat16, device=lrs.device).contiguous(memory_format=CL)
+    for k in range(t):
+        ib, jf = t - 1 - k, k
+        if k > 0:
+            feat = WarpFn.apply(feat, torch.cat([fb[:, ib], ff[:, jf - 1]], 0), False)
+        lr_k = _cl(torch.cat([lr16[:, ib], lr16[:, jf]], 0))
+        feat = resblock((bv.backward_resblocks, bv.forward_resblocks), [feat, lr_k], segs)
+        back[ib], fwd[jf] = feat[:n], feat[n:]
     # fusion + reconstruction, batched over frames (frame order (n, t) like the output)
     bk = _cl(torch.stack(back, 1).flatten(0, 1))
     fw = _cl(torch.stack(fwd, 1).flatten(0, 1))

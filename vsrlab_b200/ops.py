@@ -220,26 +220,28 @@ def device_info() -> Tuple[int, int, int]:
 # training kernels
 # --------------------------------------------------------------------------------------
 class PackedConvT(PackedConv):
-    """Weights packed for the INPUT-GRADIENT convolution (transposed + flipped, geom.transpose = 1)."""
+    """Weights packed for the INPUT-GRADIENT convolution (transposed + flipped, geom.transpose = 1).  A list of convs of
+    one shape packs as weight groups (the two propagation directions run as one launch)."""
 
-    def __init__(self, conv: torch.nn.Conv2d, dtype: int):
+    def __init__(self, conv, dtype: int):
         lib = L.load()
-        w0 = conv.weight
+        convs = list(conv) if isinstance(conv, (list, tuple)) else [conv]
+        w0 = convs[0].weight
         require_cuda(w0, "conv weight")
         cout, cin, kh, kw = w0.shape
         g = L.ConvGeom()
         g.kh, g.kw, g.n_seg = kh, kw, 1
         g.seg_off[0], g.seg_c[0] = 0, cout
-        g.cout, g.pixshuf, g.groups, g.dtype, g.transpose = cin, 0, 1, dtype, 1
+        g.cout, g.pixshuf, g.groups, g.dtype, g.transpose = cin, 0, len(convs), dtype, 1
         self.geom = g
         self.cout, self.cin, self.kh, self.kw = cin, cout, kh, kw      # of the gradient conv
         self.cout_pad = (cin + 15) // 16 * 16
         self.dtype = dtype
-        self.stamp = self.stamp_of([conv])
+        self.stamp = self.stamp_of(convs)
         self.uses = 0
         self.split = False
         self.real_segs = ((0, cout),)
-        w = w0.detach().to(torch.float32).contiguous()
+        w = torch.stack([c.weight.detach().to(torch.float32) for c in convs]).contiguous()
         nbytes = lib.vsrb_packed_weight_bytes(C.byref(g))
         if nbytes == 0:
             raise L.VsrbError(f"unsupported conv geometry: {lib.vsrb_last_error().decode()}")
