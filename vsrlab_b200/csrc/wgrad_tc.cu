@@ -3,7 +3,7 @@
 //   dW[tap][ci][co] = sum over pixels p of  x[p + tap][ci] * dz[p][co]
 //
 // is a GEMM whose K dimension is the pixel index.  Both operands are "MN-major" for UMMA: a TMA box of
-// 128 pixels x 64 channels lands in shared memory as 128 rows of 128 bytes (128B swizzle) = K rows of 64
+// pixels x 64 channels lands in shared memory as rows of 128 bytes (128B swizzle) = K rows of 64
 // contiguous M (resp. N) elements, which is exactly the canonical MN-major layout, so no transpose is needed:
 //   A (M side) = the activation x, shifted by the filter tap: the same three kx-shifted halo copies the forward
 //                conv uses; a tap (ky,kx) is copy kx starting ky*16 rows further down.  Two taps are issued as ONE
@@ -14,17 +14,22 @@
 //                persistent CTA; K advances 16 pixels (2048 bytes) per MMA.
 // Every pixel tile is read once; at the end each CTA adds its partial dW into the fp32 OIHW gradient with atomics.
 // Replaces the wgrad half of autograd's ConvolutionBackward0 for the hot 64->64 / 64->256 3x3 layers.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
 namespace vsrb {
 
 static constexpr int kWgThreads = 256;
-static constexpr int kWgTW = 16, kWgRows = 8;                               // 128-pixel tiles
-static constexpr int kWgCopyBytes = (kWgRows + 2) * kWgTW * 128;            // one kx-shifted halo copy: 20 KiB
-static constexpr int kWgZBytes = kWgRows * kWgTW * 128;                     // dz tile: 16 KiB
-static constexpr int kWgStageBytes = 3 * kWgCopyBytes + kWgZBytes;          // 76 KiB
-static constexpr int kWgStages = 2;
+static constexpr int kWgTW = 16, kWgRows = 4;                               // 64-pixel tiles: four K=16 steps
+static constexpr int kWgCopyBytes = (kWgRows + 2) * kWgTW * 128;            // one kx-shifted halo copy: 12 KiB
+static constexpr int kWgZBytes = kWgRows * kWgTW * 128;                     // dz tile: 8 KiB
+static constexpr int kWgStageBytes = 3 * kWgCopyBytes + kWgZBytes;          // 44 KiB
+// The kernel is bound by its TMA loads (measured: loads alone 97 us of 112 for 120 x 64 x 64 images, ~3.7 TB/s of mostly
+// L2-resident boxes, the same with two 76 KiB stages of 128 pixels): the three shifted copies cost 2.7x the unique bytes.
+// Building the kx copies on chip from one load is the known next step.
+static constexpr int kWgStages = 4;
 static constexpr int kWgSmem = 1024 + 1024 + kWgStages * kWgStageBytes;
 
 struct WgTcParams {
@@ -35,6 +40,7 @@ struct WgTcParams {
     int cout, cin_total, ci_off;   // OIHW geometry of dw; ci_off = first input channel of this block on the OIHW axis
     float* dw;
     int* dbg;
+    int debug;                  // VSRB_WG_DEBUG: 1 / 2 / 4 = skip the final atomics / the MMAs / the loads (timing decomposition only)
 };
 
 // MN-major, 128B-swizzled operand descriptor: start>>4 | LBO>>4 @16 | SBO>>4 @32 (8 K-rows = 1024 B) | version 1 @46 | layout 2 @61
@@ -80,7 +86,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
             const int ty = t / P.tiles_x, tx = t - ty * P.tiles_x;
             const uint32_t sa = stage0 + slot * kWgStageBytes;
             mbar_wait(empty0 + 8 * slot, phase ^ 1, P.dbg, 11, dead);
-            if (elect_one()) {
+            if (elect_one() && (P.debug & 4)) {
+                mbar_arrive(full0 + 8 * slot);                // timing decomposition: no loads
+            } else if (elect_one()) {
                 mbar_expect_tx(full0 + 8 * slot, kWgStageBytes);
                 for (int kx = 0; kx < 3; ++kx)
                     tma_load_4d(&P.xmap, full0 + 8 * slot, sa + kx * kWgCopyBytes, P.c0, tx * kWgTW + kx - 1, ty * kWgRows - 1, img);
@@ -90,7 +98,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
             if (++slot == kWgStages) { slot = 0; phase ^= 1; }
         }
     } else if (warp == 1) {
-        // ---- MMA issuer: D_pair[128 x 64] += X_pair^T[128 x 16] * dZ[16 x 64] for 8 K steps x 5 tap pairs ----
+        // ---- MMA issuer: D_pair[128 x 64] += X_pair^T[128 x 16] * dZ[16 x 64] for kWgRows K steps x 5 tap pairs ----
         // instruction descriptor: D=f32, A=B=bf16, A and B MN-major (bits 15, 16), N=64, M=128
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | (8u << 24);
         int slot = 0;
@@ -103,7 +111,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
             if (elect_one()) {
                 const uint32_t zb = sa + 3 * kWgCopyBytes;
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks) {
+                for (int ks = 0; ks < ((P.debug & 2) ? 0 : kWgRows); ++ks) {
                     const uint64_t bd = mn_desc(zb + ks * 2048u, 0u);
                     const uint32_t acc = (first && ks == 0) ? 0u : 1u;
                     // pairs (ky,0)&(ky,1): second tile lives one halo copy further
@@ -124,7 +132,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
         if (elect_one()) umma_commit(done);
         __syncwarp();
     } else if (warp >= 4) {
-        // ---- epilogue (once): TMEM -> atomics into dw[co][ci][tap] ----
+        // ---- epilogue (once), part 1: TMEM -> shared memory in the OIHW order of the 64(co) x 64(ci) x 9 block.  Lanes
+        // differ in ci, i.e. by 9 floats: conflict-free.  The pipeline stages are free once `done` has fired. ----
         const int wq = warp - 4;
         mbar_wait(done, 0, P.dbg, 13, dead);
         tc_fence_after();
@@ -133,6 +142,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
             const int ci = (wq & 1) * 32 + lane;
             // tap = ky*3 + kx of (pair, half)
             const int tapA[5] = {0, 3, 6, 2, 8}, tapB[5] = {1, 4, 7, 5, -1};
+            float* stg = reinterpret_cast<float*>(base_ptr + 1024);
             for (int pr = 0; pr < 5; ++pr) {
                 const int tap = half ? tapB[pr] : tapA[pr];
                 for (int c0 = 0; c0 < 64; c0 += 16) {
@@ -141,14 +151,21 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
                     tmem_ld_wait();
                     if (tap >= 0) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const int co = P.n0 + c0 + j;
-                            if (co < P.cout)
-                                atomicAdd(P.dw + ((size_t)co * P.cin_total + P.ci_off + ci) * 9 + tap, __uint_as_float(r[j]));
-                        }
+                        for (int j = 0; j < 16; ++j) stg[((c0 + j) * 64 + ci) * 9 + tap] = __uint_as_float(r[j]);
                     }
                 }
             }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    // ---- epilogue part 2 (all warps): the block leaves with coalesced atomics - consecutive lanes add consecutive floats
+    // of dw[co][ci_off .. ci_off+63][0..8], 8x fewer L2 sector operations than one scattered atomic per (ci, tap) ----
+    if (my_tiles > 0 && !(P.debug & 1)) {
+        const float* stg = reinterpret_cast<const float*>(base_ptr + 1024);
+        for (int co = 0; co < 64 && P.n0 + co < P.cout; ++co) {
+            float* dst = P.dw + ((size_t)(P.n0 + co) * P.cin_total + P.ci_off) * 9;
+            for (int i = threadIdx.x; i < 576; i += kWgThreads) atomicAdd(dst + i, stg[co * 576 + i]);
         }
     }
     tc_fence_before();
@@ -240,8 +257,14 @@ int launch_wgrad_tc(const void* x, int x_c, int c0, int ci_off, const void* dz, 
     const int n_blocks = ceil_div(cout, 64);
     // every CTA ends with 9*64*64 atomics, so small problems use fewer CTAs (>= 16 pixel tiles each)
     int ctas = sms / n_blocks;
-    if (ctas > P.total_tiles / 16) ctas = P.total_tiles / 16;
+    if (ctas > P.total_tiles / 32) ctas = P.total_tiles / 32;
     if (ctas < 1) ctas = 1;
+    {
+        const char* e = getenv("VSRB_WG_DEBUG");
+        P.debug = e ? atoi(e) : 0;
+        const char* c = getenv("VSRB_WG_CTAS");
+        if (c && atoi(c) > 0 && atoi(c) < ctas) ctas = atoi(c);
+    }
     for (int nb = 0; nb < n_blocks; ++nb) {          // one launch per 64-wide output block; they run concurrently-ish back to back
         P.n0 = nb * 64;
         wgrad_tc_kernel<<<ctas, kWgThreads, kWgSmem, stream>>>(P);
