@@ -177,18 +177,45 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
 }
 
 // bias gradient: db[co] += sum over pixels of dz[p][co]
+__device__ __forceinline__ void bias_ld8(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+__device__ __forceinline__ void bias_ld8(const float* p, float (&v)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+// db[c] += sum over pixels of dz[p][c].  HBM-bound (reads dz once): every thread owns 8 consecutive channels (one 16-byte
+// load per pixel for bf16) and a strided set of pixels; the pixel lanes of a CTA are reduced in shared memory, then one
+// atomic per channel and CTA.  blockDim = 256 = G channel groups (G = 8 for 64 channels) x 256/G pixel lanes.
 template <typename T>
-__global__ void bias_grad_kernel(const T* __restrict__ dz, int dz_c, long long pixels, int cout, float* __restrict__ db) {
-    // blockDim = (64 channels, 4 pixel lanes); grid.y = channel block
-    const int c = blockIdx.y * 64 + threadIdx.x;
-    float s = 0.f;
-    if (c < cout)
-        for (long long p = (long long)blockIdx.x * blockDim.y + threadIdx.y; p < pixels; p += (long long)gridDim.x * blockDim.y)
-            s += (float)dz[p * dz_c + c];
-    __shared__ float red[4][64];
-    red[threadIdx.y][threadIdx.x] = s;
+__global__ void __launch_bounds__(256) bias_grad_kernel(const T* __restrict__ dz, int dz_c, long long pixels, int cout, int G, float* __restrict__ db) {
+    __shared__ float red[256][9];                                  // [thread][8 channels] (+1: no bank conflicts)
+    const int grp = threadIdx.x % G, lane = threadIdx.x / G, lanes = 256 / G;
+    const int c0 = (blockIdx.y * G + grp) * 8;
+    float s[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = 0.f;
+    if (c0 < dz_c) {
+        for (long long p = (long long)blockIdx.x * lanes + lane; p < pixels; p += (long long)gridDim.x * lanes) {
+            float v[8];
+            bias_ld8(dz + p * dz_c + c0, v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s[i] += v[i];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[threadIdx.x][i] = s[i];
     __syncthreads();
-    if (threadIdx.y == 0 && c < cout) atomicAdd(db + c, red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x]);
+    if (threadIdx.x < G * 8) {                                     // thread = (group, channel of the group)
+        const int g2 = threadIdx.x / 8, ch = threadIdx.x % 8;
+        float t = 0.f;
+        for (int l = 0; l < lanes; ++l) t += red[l * G + g2][ch];
+        const int c = (blockIdx.y * G + g2) * 8 + ch;
+        if (c < cout) atomicAdd(db + c, t);
+    }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -196,9 +223,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 int launch_bias_grad(const void* dz, int dz_c, long long pixels, int cout, int dtype, float* db, cudaStream_t s) {
-    dim3 block(64, 4), grid(296, ceil_div(cout, 64));
-    if (dtype == VSRB_BF16) bias_grad_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dz), dz_c, pixels, cout, db);
-    else bias_grad_kernel<float><<<grid, block, 0, s>>>(reinterpret_cast<const float*>(dz), dz_c, pixels, cout, db);
+    const int groups = ceil_div(cout, 8);
+    int G = 1;
+    while (G < groups && G < 32) G *= 2;                            // channel groups per CTA: power of two <= 32
+    long long want = (pixels + 256 / G * 8 - 1) / (256 / G * 8);   // >= 8 pixels per thread
+    int gx = (int)(want < 1 ? 1 : (want > 148 * 4 ? 148 * 4 : want));
+    dim3 grid(gx, ceil_div(groups, G));
+    if (dtype == VSRB_BF16) bias_grad_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dz), dz_c, pixels, cout, G, db);
+    else bias_grad_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(dz), dz_c, pixels, cout, G, db);
     VSRB_LAUNCH_CHECK();
     return VSRB_OK;
 }
