@@ -174,6 +174,9 @@ int vsrb_nchw_to_nhwc(const float* src, void* dst, int32_t n, int32_t c, int32_t
                       int32_t c_dst, int32_t dtype, void* stream);   /* channels >= c are zeroed */
 int vsrb_nhwc_to_nchw(const void* src, float* dst, int32_t n, int32_t c, int32_t h, int32_t w,
                       int32_t c_src, int32_t dtype, void* stream);
+/* inverse of nn.PixelShuffle(2) (upsampling.py:10-12) on bf16 NHWC, for the backward pass of the upsampling convs:
+ * src [n, 2h, 2w, c] -> dst [n, h, w, 4c] with dst channel 4*cc + 2*i + j = src pixel (2y+i, 2x+j), channel cc */
+int vsrb_pixel_unshuffle2(const void* src, void* dst, int32_t n, int32_t h, int32_t w, int32_t c, void* stream);
 
 /* ---- SPyNet glue ------------------------------------------------------------------------
  * reference spynet.py:38-48 (normalise + 5x avg_pool2d), :71-80 (resize to /32),

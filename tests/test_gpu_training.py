@@ -224,3 +224,15 @@ def test_batched_wgrad_equals_per_use(dev):
     assert rel(w1, w0) < 1e-5 and rel(b1, b0) < 1e-5
     for a, b in zip(g1, g0):
         assert torch.equal(a, b)
+
+
+def test_pixel_unshuffle2_matches_torch(dev):
+    """vsrb_pixel_unshuffle2 (bf16 NHWC) against F.pixel_unshuffle: pure data movement, bit-exact."""
+    from vsrlab_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    for (n, h, w, c) in [(2, 5, 7, 64), (1, 3, 4, 8), (3, 16, 9, 32)]:
+        src = torch.randn(n, c, 2 * h, 2 * w, generator=g).to(torch.bfloat16).to(dev).contiguous(memory_format=torch.channels_last)
+        dst = torch.empty((n, 4 * c, h, w), dtype=torch.bfloat16, device=dev).contiguous(memory_format=torch.channels_last)
+        ops.pixel_unshuffle2(src, dst, n, h, w, c)
+        torch.cuda.synchronize()
+        assert torch.equal(dst, F.pixel_unshuffle(src, 2))

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--blocks", type=int, default=5)
     ap.add_argument("--train-flow", type=int, default=1)
     ap.add_argument("--host-profile", action="store_true", help="cProfile one step on the host (stderr)")
+    ap.add_argument("--kernel-profile", action="store_true", help="torch.profiler (CUPTI) table of every kernel of one step (stderr)")
     a = ap.parse_args()
     import torch.distributed as dist
     from vsrlab.vsr.models.RealBasicVSR.realbasicvsr import RealBasicVSR
@@ -72,6 +73,17 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.steps
+    if a.kernel_profile and rank == 0:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof_k:
+            step()
+            torch.cuda.synchronize()
+        print(prof_k.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=70), file=sys.stderr)
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof_o:
+            step()
+            torch.cuda.synchronize()
+        print(prof_o.key_averages(group_by_input_shape=True).table(sort_by="self_cuda_time_total", row_limit=30, max_name_column_width=40,
+                                                                    max_shapes_column_width=70), file=sys.stderr)
     if a.host_profile and rank == 0:
         import cProfile
         import pstats

@@ -71,6 +71,7 @@ SYMBOLS = {
     "vsrb_launch_count": (C.c_int64, []),
     "vsrb_debug_status": (C.c_int, [C.c_void_p]),
     "vsrb_debug_trace": (C.c_int, [C.c_void_p, C.c_int32]),
+    "vsrb_pixel_unshuffle2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "vsrb_packed_weight_bytes": (C.c_size_t, [C.POINTER(ConvGeom)]),
     "vsrb_pack_conv_weight": (C.c_int, [C.POINTER(ConvGeom), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vsrb_conv2d_fwd": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),

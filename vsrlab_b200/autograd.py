@@ -155,7 +155,15 @@ class ConvFn(torch.autograd.Function):
             dz = torch.where(out > 0, dy, dy * ctx.slope)
         cout = conv.out_channels
         if ctx.pixshuf:
-            dz = F.pixel_unshuffle(dz[:, :cout // (ctx.pixshuf ** 2)], ctx.pixshuf)
+            cq = cout // (ctx.pixshuf ** 2)
+            if ctx.pixshuf == 2 and dz.shape[1] == cq and cq % 8 == 0 and dz.dtype == torch.bfloat16:
+                # the library's un-shuffle: one HBM-bound pass instead of torch's reshape/permute/contiguous chain
+                src = _cl(dz)
+                bb, _, hh, ww = src.shape
+                dz = torch.empty((bb, cout, hh // 2, ww // 2), dtype=torch.bfloat16, device=src.device, memory_format=CL)
+                ops.pixel_unshuffle2(src, dz, bb, hh // 2, ww // 2, cq)
+            else:
+                dz = F.pixel_unshuffle(dz[:, :cq], ctx.pixshuf)
         dz = _cl(dz)
         dz_c = dz.shape[1]
         b, _, h, w = ins[0].shape
@@ -378,6 +386,18 @@ def spynet(sp, ref: torch.Tensor, supp: torch.Tensor) -> torch.Tensor:
     return flow * scale
 
 
+_gather_idx: dict = {}
+
+
+def _gather_indices(n: int, t: int, device):
+    key = (n, t, str(device))
+    if key not in _gather_idx:
+        ib = [(t - 1 - i) * 2 * n + nn for nn in range(n) for i in range(t)]
+        jf = [i * 2 * n + n + nn for nn in range(n) for i in range(t)]
+        _gather_idx[key] = (torch.tensor(ib, device=device), torch.tensor(jf, device=device))
+    return _gather_idx[key]
+
+
 def basicvsr(bv, lrs: torch.Tensor) -> torch.Tensor:
     """BasicVSR.forward with gradients (basicvsr.py:39-83)."""
     from . import functional as VF
@@ -399,8 +419,7 @@ def basicvsr(bv, lrs: torch.Tensor) -> torch.Tensor:
     segs = [(3, mid), (0, 3)]
     # both directions advance together: step k runs frame t-1-k of the backward chain and frame k of the forward chain as
     # the two weight groups of one launch per layer (images [0, n) backward, [n, 2n) forward)
-    back: List[Optional[torch.Tensor]] = [None] * t
-    fwd: List[Optional[torch.Tensor]] = [None] * t
+    feats: List[torch.Tensor] = []
     feat = torch.zeros((2 * n, mid, h, w), dtype=torch.bfloat16, device=lrs.device).contiguous(memory_format=CL)
     for k in range(t):
         ib, jf = t - 1 - k, k
@@ -408,10 +427,13 @@ def basicvsr(bv, lrs: torch.Tensor) -> torch.Tensor:
             feat = WarpFn.apply(feat, torch.cat([fb[:, ib], ff[:, jf - 1]], 0), False)
         lr_k = _cl(torch.cat([lr16[:, ib], lr16[:, jf]], 0))
         feat = resblock((bv.backward_resblocks, bv.forward_resblocks), [feat, lr_k], segs)
-        back[ib], fwd[jf] = feat[:n], feat[n:]
-    # fusion + reconstruction, batched over frames (frame order (n, t) like the output)
-    bk = _cl(torch.stack(back, 1).flatten(0, 1))
-    fw = _cl(torch.stack(fwd, 1).flatten(0, 1))
+        feats.append(feat)
+    # fusion + reconstruction, batched over frames in the output's (n, t) order: one gather per direction out of the
+    # concatenated steps (slicing every step's `feat` in two cost five slow strided kernels per step in the backward pass)
+    allf = torch.cat(feats, 0).permute(0, 2, 3, 1)                           # [t * 2n, h, w, C]: plain contiguous view
+    idx_b, idx_f = _gather_indices(n, t, lrs.device)
+    bk = allf.index_select(0, idx_b).permute(0, 3, 1, 2)                     # frame (nn, i) = step t-1-i, image nn
+    fw = allf.index_select(0, idx_f).permute(0, 3, 1, 2)                     # frame (nn, i) = step i, image n + nn
     x = conv(bv.point_conv[0], [bk, fw], [(0, mid), (mid, mid)], "lrelu")
     for up in bv.upsample:
         x = conv(up.upconv, [x], [(0, mid)], "none", pixshuf=2)

@@ -376,6 +376,40 @@ static inline int grid_for(long long total, int block) {
 
 using namespace vsrb;
 
+// Inverse of PixelShuffle(2) on bf16 NHWC (training: the gradient of an upsampling conv arrives in the shuffled layout):
+// dst[b][y][x][4c + 2i + j] = src[b][2y + i][2x + j][c].  A thread owns 8 consecutive source channels of one LR pixel:
+// four 16-byte loads (the 2 x 2 HR pixels), four 16-byte stores (32 consecutive destination channels).  HBM-bound.
+__global__ void pixel_unshuffle2_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, long long lr_pixels, int w, int c) {
+    const int groups = c / 8;
+    const long long total = lr_pixels * groups;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(i % groups);
+        const long long p = i / groups;                       // b * h * w + y * w + x
+        const int x = (int)(p % w);
+        const long long by = p / w;                           // b * h + y
+        uint32_t q[4][4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {                         // k = 2i + j
+            const long long sp = (2 * by + (k >> 1)) * (2LL * w) + 2 * x + (k & 1);
+            const uint4 v = __ldg(src + sp * groups + g);
+            q[k][0] = v.x; q[k][1] = v.y; q[k][2] = v.z; q[k][3] = v.w;
+        }
+        // source channel e (0..7) of sub-pixel k goes to destination channel 4 * (8g + e) + k
+        uint32_t o[16];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const uint32_t sh = (e & 1) * 16;
+            const uint32_t v0 = (q[0][e >> 1] >> sh) & 0xFFFFu, v1 = (q[1][e >> 1] >> sh) & 0xFFFFu;
+            const uint32_t v2 = (q[2][e >> 1] >> sh) & 0xFFFFu, v3 = (q[3][e >> 1] >> sh) & 0xFFFFu;
+            o[2 * e] = v0 | (v1 << 16);
+            o[2 * e + 1] = v2 | (v3 << 16);
+        }
+        uint4* d = dst + (p * (4LL * groups) + 4LL * g);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) d[k] = make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+    }
+}
+
 extern "C" {
 
 int vsrb_flow_warp(const void* x, int64_t x_img_stride, const float* flow, int64_t flow_img_stride, void* out, int32_t n,
@@ -498,6 +532,16 @@ int vsrb_flow_resize(const float* flow_in, float* flow_out, int32_t P, int32_t H
     const long long total = (long long)P * h * w;
     flow_resize_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const float2*>(flow_in), reinterpret_cast<float2*>(flow_out), P, Hp, Wp, h, w);
+    VSRB_LAUNCH_CHECK();
+    return VSRB_OK;
+}
+
+int vsrb_pixel_unshuffle2(const void* src, void* dst, int32_t n, int32_t h, int32_t w, int32_t c, void* stream) {
+    VSRB_CHECK_ARG(src && dst && n >= 1 && h >= 1 && w >= 1 && c >= 8 && c % 8 == 0, "pixel_unshuffle2: bad arguments (c %% 8 == 0)");
+    VSRB_CHECK_ARG(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0, "pixel_unshuffle2: 16-byte alignment");
+    const long long lr_pixels = (long long)n * h * w;
+    pixel_unshuffle2_kernel<<<grid_for(lr_pixels * (c / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), lr_pixels, w, c);
     VSRB_LAUNCH_CHECK();
     return VSRB_OK;
 }

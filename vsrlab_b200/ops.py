@@ -202,6 +202,11 @@ def flow_resize(fin, fout, P: int, Hp: int, Wp: int, h: int, w: int) -> None:
     L.check(L.load().vsrb_flow_resize(_p(fin), _p(fout), P, Hp, Wp, h, w, _stream()), "vsrb_flow_resize")
 
 
+def pixel_unshuffle2(src: torch.Tensor, dst: torch.Tensor, n: int, h: int, w: int, c: int) -> None:
+    """bf16 NHWC [n,2h,2w,c] -> [n,h,w,4c] (inverse PixelShuffle(2), PyTorch channel order)."""
+    L.check(L.load().vsrb_pixel_unshuffle2(_p(src), _p(dst), n, h, w, c, _stream()), "vsrb_pixel_unshuffle2")
+
+
 def launch_count() -> int:
     return int(L.load().vsrb_launch_count())
 
