@@ -27,6 +27,8 @@
 // basicvsr.py:75-82; realbasicvsr.py:28-29; spynet.py:16-21 (see include/vsrb200.h).
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -717,9 +719,12 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+static std::mutex g_init_mutex;            // one-time per-process / per-device initialisation (callers may be threads)
+
 static EncodeTiledFn get_encode() {
     static EncodeTiledFn fn = nullptr;
     static bool tried = false;
+    std::lock_guard<std::mutex> lock(g_init_mutex);
     if (!tried) {
         tried = true;
         void* p = nullptr;
@@ -748,6 +753,7 @@ int launch_conv_tc(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t stre
     int dev = 0;
     VSRB_CUDA(cudaGetDevice(&dev));
     VSRB_CHECK_ARG(dev >= 0 && dev < 64, "device ordinal %d out of range", dev);
+    std::unique_lock<std::mutex> init_lock(g_init_mutex);
     if (!g_dev_ready[dev]) {
         VSRB_CUDA(cudaDeviceGetAttribute(&g_sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
         VSRB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
@@ -775,6 +781,7 @@ int launch_conv_tc(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t stre
         }
         g_dev_ready[dev] = true;
     }
+    init_lock.unlock();
     TcParams P;
     memset(&P, 0, sizeof(P));
     P.n_seg = p.n_seg; P.kh = p.kh; P.kw = p.kw; P.H = a->h; P.W = a->w;

@@ -16,6 +16,8 @@
 // Replaces the wgrad half of autograd's ConvolutionBackward0 for the hot 64->64 / 64->256 3x3 layers.
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -239,26 +241,30 @@ int launch_bias_grad(const void* dz, int dz_c, long long pixels, int cout, int d
 int launch_wgrad_tc(const void* x, int x_c, int c0, int ci_off, const void* dz, int dz_c, int batch, int h, int w, int cout,
                     int cin_total, float* dw, cudaStream_t stream) {
     static EncodeTiledFn encode = nullptr;
-    static bool attr = false;
-    if (!encode) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
-            set_error("cuTensorMapEncodeTiled not available from the driver");
-            return VSRB_E_NODEVICE;
-        }
-        encode = reinterpret_cast<EncodeTiledFn>(p);
-    }
-    if (!attr) {
-        VSRB_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem));
-        attr = true;
-    }
-    int sms = 148;
+    static bool attr[64] = {false};                  // function attributes are per device
+    static int sm_count[64] = {0};
+    static std::mutex init_mutex;
+    int dev = 0;
+    VSRB_CUDA(cudaGetDevice(&dev));
+    VSRB_CHECK_ARG(dev >= 0 && dev < 64, "device ordinal %d out of range", dev);
     {
-        int dev = 0;
-        VSRB_CUDA(cudaGetDevice(&dev));
-        VSRB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        std::lock_guard<std::mutex> lock(init_mutex);
+        if (!encode) {
+            void* p = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+                set_error("cuTensorMapEncodeTiled not available from the driver");
+                return VSRB_E_NODEVICE;
+            }
+            encode = reinterpret_cast<EncodeTiledFn>(p);
+        }
+        if (!attr[dev]) {
+            VSRB_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem));
+            VSRB_CUDA(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
+            attr[dev] = true;
+        }
     }
+    const int sms = sm_count[dev];
     WgTcParams P;
     memset(&P, 0, sizeof(P));
     P.H = h; P.W = w; P.batch = batch;
