@@ -27,6 +27,9 @@ def main():
     ap.add_argument("--frames", type=int, default=15)
     ap.add_argument("--blocks", type=int, default=5)
     ap.add_argument("--train-flow", type=int, default=1)
+    ap.add_argument("--graph", action="store_true",
+                    help="additionally capture forward + backward + clip + Adam in ONE CUDA graph (torch whole-network capture, "
+                         "single GPU) and time its replay: what the step costs once the host is out of the loop")
     ap.add_argument("--host-profile", action="store_true", help="cProfile one step on the host (stderr)")
     ap.add_argument("--kernel-profile", action="store_true", help="torch.profiler (CUPTI) table of every kernel of one step (stderr)")
     a = ap.parse_args()
@@ -44,7 +47,7 @@ def main():
     model = RealBasicVSR(cleaning_blocks=a.blocks, mid_channels=64, upscale=4, res_blocks=a.blocks, pretrained_flow=False,
                          train_flow=bool(a.train_flow)).to(dev).train()
     net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local]) if world > 1 else model
-    opt = torch.optim.Adam(net.parameters(), lr=1e-4, betas=(0.9, 0.99))
+    opt = torch.optim.Adam(net.parameters(), lr=1e-4, betas=(0.9, 0.99), capturable=bool(a.graph and world == 1))
     g = torch.Generator().manual_seed(rank)
     lr = torch.rand(a.batch, a.frames, 3, 64, 64, generator=g).to(dev)
     hr = torch.rand(a.batch, a.frames, 3, 256, 256, generator=g).to(dev)
@@ -58,7 +61,7 @@ def main():
         loss.backward()
         torch.nn.utils.clip_grad_norm_(net.parameters(), 1.0)
         opt.step()
-        return loss
+        return loss.detach()      # (a live `loss` would keep the graph and the parameters' grad accumulators alive)
 
     losses = []
     for _ in range(a.warmup):
@@ -73,6 +76,41 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.steps
+    ms_graph = None
+    if a.graph and world == 1:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        opt.zero_grad(set_to_none=True)
+        graph = torch.cuda.CUDAGraph()
+
+        def graph_body():
+            x = lr.clone()
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                sr, lq = net(x)
+            loss = charbonnier(sr, hr) + charbonnier(lq, F.interpolate(hr.flatten(0, 1), size=(64, 64), mode="bilinear").view_as(lq))
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(net.parameters(), 1.0)
+            opt.step()
+            return loss
+        with torch.cuda.graph(graph, stream=side):     # same stream as the warm-up: the parameters' grad accumulators live on it
+            static_loss = graph_body()
+        torch.cuda.synchronize()
+        for _ in range(2):
+            graph.replay()
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(a.steps):
+            graph.replay()
+        g1.record()
+        torch.cuda.synchronize()
+        ms_graph = g0.elapsed_time(g1) / a.steps
+        print(f"graph replay: {ms_graph:.2f} ms per step, loss {float(static_loss):.5f}", file=sys.stderr)
     if a.kernel_profile and rank == 0:
         from torch.profiler import ProfilerActivity, profile
         with profile(activities=[ProfilerActivity.CUDA]) as prof_k:
@@ -119,7 +157,7 @@ def main():
     if rank == 0:
         print(json.dumps({
             "workload": f"cfg4 training step: batch {a.batch}/GPU x {a.frames} frames 64x64, {a.blocks}/{a.blocks} blocks, train_flow={a.train_flow}",
-            "n_gpus": world, "ms_per_step": t.item(), "clips_per_sec": world * a.batch / (t.item() * 1e-3),
+            "n_gpus": world, "ms_per_step": t.item(), "ms_per_step_cuda_graph": ms_graph, "clips_per_sec": world * a.batch / (t.item() * 1e-3),
             "loss_first": float(losses[0]), "loss_last": float(losses[-1]), "replicas_identical": same,
             "kernels_ms": {k: {"ms": round(v[0], 2), "launches": v[2], "tflops_or_gbs": round(v[1] / max(v[0], 1e-9) / 1e9, 1)}
                            for k, v in fam.items()},

@@ -382,8 +382,8 @@ def spynet(sp, ref: torch.Tensor, supp: torch.Tensor) -> torch.Tensor:
             x = conv(cv, [x], [(0, cv.in_channels)], "relu")
         flow = flow_up + x[:, :2].float()
     flow = F.interpolate(flow, size=(h, w), mode="bilinear", align_corners=False)
-    scale = flow.new_tensor([float(w) / float(wp), float(h) / float(hp)]).view(1, 2, 1, 1)
-    return flow * scale
+    # per-axis rescale without a host-built tensor (keeps the step capturable in a CUDA graph)
+    return torch.cat([flow[:, :1] * (float(w) / float(wp)), flow[:, 1:] * (float(h) / float(hp))], 1)
 
 
 _gather_idx: dict = {}
