@@ -22,7 +22,10 @@ ESIZE = {BF16: 2, F32: 4, BF16X2: 2}
 # entries are (kind, start_event, end_event, algorithmic work: FLOPs for convs, bytes otherwise)
 PROFILE = None
 PROFILE_SHAPES = os.environ.get("VSRB_PROFILE_SHAPES") == "1"
-PDL = os.environ.get("VSRB_PDL") == "1"   # programmatic dependent launch between consecutive convs (measured: no gain, off)
+# Programmatic dependent launch between consecutive convs: the next conv's grid is scheduled while the current one drains
+# (its producer and epilogue roles wait on griddepcontrol.wait before touching activations).  +2 % at cfg3 inside the
+# replayed graph (CUPTI shows ~6 us between kernels otherwise); VSRB_PDL=0 turns it off.
+PDL = os.environ.get("VSRB_PDL", "1") == "1"
 TAG = ""          # set by the scheduler so profile entries can be grouped by network part
 
 
