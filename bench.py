@@ -297,6 +297,11 @@ def main():
     ms_e2e = f0.elapsed_time(f1)
 
     # ---- per-kernel roofline: CUDA events around every launch of one more step --------------
+    # The timed region replays a CUDA graph, so the per-launch pass must not be paced by the host either: a spin kernel
+    # holds the stream while the step's launches and event records are queued, then the GPU runs them back to back and the
+    # events see device-side durations (kernel + the GPU's own launch latency), not waits for Python.
+    torch.cuda.synchronize()
+    torch.cuda._sleep(int(0.15 * 1.9e9))
     ops.PROFILE = []
     step()
     torch.cuda.synchronize()
