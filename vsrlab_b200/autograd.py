@@ -407,8 +407,11 @@ def basicvsr(bv, lrs: torch.Tensor) -> torch.Tensor:
     a = lrs[:, :-1].reshape(-1, c, h, w)
     b = lrs[:, 1:].reshape(-1, c, h, w)
     if train_flow:
-        fb = spynet(bv.spynet, a, b).view(n, t - 1, 2, h, w).permute(0, 1, 3, 4, 2)
-        ff = spynet(bv.spynet, b, a).view(n, t - 1, 2, h, w).permute(0, 1, 3, 4, 2)
+        # both directions as one batch (first the backward pairs, then the forward pairs), like the inference path
+        fl = spynet(bv.spynet, torch.cat([a, b], 0), torch.cat([b, a], 0))
+        m = n * (t - 1)
+        fb = fl[:m].view(n, t - 1, 2, h, w).permute(0, 1, 3, 4, 2)
+        ff = fl[m:].view(n, t - 1, 2, h, w).permute(0, 1, 3, 4, 2)
     else:
         with torch.no_grad():
             ref, supp = VF._pair_indices(n, t, lrs.device)
