@@ -378,3 +378,31 @@ def test_edge_shapes(dev, shape):
         sr16, _ = net(x.clone().to(dev))
     assert O.psnr(sr16.cpu(), sr_ref) > 40.0
     assert ops.debug_status() == 0
+
+
+def test_graph_replay_and_pdl_do_not_change_results(dev):
+    """Scheduling features must be invisible in the numbers: eager launches, programmatic dependent launch between convs
+    and CUDA-graph replay of the whole forward give bit-identical sr / lq (bf16 mode)."""
+    from vsrlab.vsr.models.RealBasicVSR.realbasicvsr import RealBasicVSR
+    from vsrlab_b200 import functional as VF, ops
+    torch.manual_seed(5)
+    model = RealBasicVSR(cleaning_blocks=2, mid_channels=64, upscale=4, res_blocks=2, pretrained_flow=False, train_flow=False)
+    model = model.to(dev).eval()
+    x = torch.rand(2, 4, 3, 40, 72, device=dev)
+    keep = (VF.GRAPHS, ops.PDL)
+    outs = []
+    try:
+        with VF.precision("bf16"), torch.no_grad():
+            for graphs, pdl in ((False, False), (False, True), (True, True), (True, True)):
+                VF.GRAPHS, ops.PDL = graphs, pdl
+                VF.clear_caches()
+                xi = x.clone()
+                sr, lq = model(xi)
+                torch.cuda.synchronize()
+                assert ops.debug_status() == 0
+                outs.append((sr.clone(), lq.clone()))
+    finally:
+        VF.GRAPHS, ops.PDL = keep
+        VF.clear_caches()
+    for sr, lq in outs[1:]:
+        assert torch.equal(sr, outs[0][0]) and torch.equal(lq, outs[0][1])
