@@ -155,6 +155,13 @@ int    vsrb_conv_plan_info(const vsrb_conv_geom* g, int32_t info[8]);
 int vsrb_conv2d_wgrad(const vsrb_conv_geom* g, const void* const* in, const int32_t* in_c, const void* dz,
                       int32_t dz_c, int32_t batch, int32_t h, int32_t w, int32_t imgs_per_group,
                       int32_t cin_total, float* dw, float* db, void* stream);
+/* the same gradient summed over n_chunks (x, dz) pairs of one shape - the uses of a recurrent conv at different time
+ * steps (basicvsr.py:46-73 applies the same resblocks at every frame) - in one launch per 64-channel block:
+ * in[k * n_seg + s] = input segment s of chunk k, dz[k] = its output gradient, `batch` images per chunk.
+ * bf16, 3x3, ungrouped, segments of a multiple of 64 channels (the tensor-core path); other shapes: concatenate. */
+int vsrb_conv2d_wgrad_multi(const vsrb_conv_geom* g, int32_t n_chunks, const void* const* in, const int32_t* in_c,
+                            const void* const* dz, int32_t dz_c, int32_t batch, int32_t h, int32_t w,
+                            int32_t cin_total, float* dw, float* db, void* stream);
 /* backward of vsrb_flow_warp: dx (fp32 [n,h,w,c], accumulated with atomics, zero it first; or
  * NULL) and dflow (fp32 [n,h,w,2], overwritten; or NULL; needs the forward input x).        */
 int vsrb_flow_warp_bwd(const void* x, const float* flow, const void* dout, float* dx, float* dflow,

@@ -76,6 +76,9 @@ SYMBOLS = {
     "vsrb_pack_conv_weight": (C.c_int, [C.POINTER(ConvGeom), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vsrb_conv2d_fwd": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
     "vsrb_conv_plan_info": (C.c_int, [C.POINTER(ConvGeom), C.POINTER(C.c_int32)]),
+    "vsrb_conv2d_wgrad_multi": (C.c_int, [C.POINTER(ConvGeom), C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int32),
+                                          C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                          C.c_void_p, C.c_void_p]),
     "vsrb_conv2d_wgrad": (C.c_int, [C.POINTER(ConvGeom), C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_void_p, C.c_int32,
                                     C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vsrb_flow_warp_bwd": (C.c_int, [C.c_void_p] * 5 + [C.c_int32] * 6 + [C.c_void_p]),

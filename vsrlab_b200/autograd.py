@@ -96,7 +96,12 @@ class _WeightNode(torch.autograd.Function):
             h, w = hw
             small = [it for it in items if it[1].shape[0] * h * w < _BATCH_PIXELS]
             big = [it for it in items if it[1].shape[0] * h * w >= _BATCH_PIXELS]
-            if len(small) > 1:
+            tc = (conv.kernel_size == (3, 3) and all(c % 64 == 0 for _, c in segs) and len({it[1].shape[0] for it in small}) == 1
+                  and all(t.is_contiguous(memory_format=CL) and t.data_ptr() % 16 == 0 for it in small for t in (*it[0], it[1])))
+            if len(small) > 1 and tc:
+                # tensor-core path: one launch walks the list of (inputs, dz) pairs, no concatenation
+                ops.conv2d_wgrad_multi(g, small, list(in_c), dz_c, small[0][1].shape[0], h, w, conv.in_channels, dw, db)
+            elif len(small) > 1:
                 ins = [torch.cat([it[0][i] for it in small], 0) for i in range(len(in_c))]
                 big.append((ins, torch.cat([it[1] for it in small], 0)))
             else:

@@ -425,12 +425,44 @@ static int launch_warp_bwd(const T* x, const float2* flow, const T* dout, float*
 int launch_wgrad_tc(const void* x, int x_c, int c0, int ci_off, const void* dz, int dz_c, int batch, int h, int w, int cout,
                     int cin_total, float* dw, cudaStream_t stream);
 int launch_bias_grad(const void* dz, int dz_c, long long pixels, int cout, int dtype, float* db, cudaStream_t s);
+int launch_wgrad_tc_multi(const void* const* xs, int x_c, int c0, int ci_off, const void* const* dzs, int dz_c, int n_chunks,
+                          int batch, int h, int w, int cout, int cin_total, float* dw, cudaStream_t stream);
 
 }  // namespace vsrb
 
 using namespace vsrb;
 
 extern "C" {
+
+int vsrb_conv2d_wgrad_multi(const vsrb_conv_geom* g, int32_t n_chunks, const void* const* in, const int32_t* in_c,
+                            const void* const* dz, int32_t dz_c, int32_t batch, int32_t h, int32_t w, int32_t cin_total,
+                            float* dw, float* db, void* stream) {
+    VSRB_CHECK_ARG(g && in && in_c && dz && dw && n_chunks >= 1, "wgrad_multi: null argument");
+    VSRB_CHECK_ARG(g->dtype == VSRB_BF16 && g->kh == 3 && g->kw == 3 && g->groups == 1 && !g->pixshuf && !g->transpose &&
+                       g->n_seg >= 1 && g->n_seg <= 2 && dz_c >= g->cout && dz_c % 8 == 0,
+                   "wgrad_multi: bf16 3x3 ungrouped convs only (tensor-core path)");
+    for (int s = 0; s < g->n_seg; ++s)
+        VSRB_CHECK_ARG(g->seg_c[s] % 64 == 0 && in_c[s] % 8 == 0 && in_c[s] >= g->seg_c[s] && g->seg_off[s] + g->seg_c[s] <= cin_total,
+                       "wgrad_multi: segment %d must have a multiple of 64 channels", s);
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int k0 = 0; k0 < n_chunks; k0 += 16) {
+        const int nk = n_chunks - k0 < 16 ? n_chunks - k0 : 16;
+        for (int s = 0; s < g->n_seg; ++s) {
+            const void* xs[16];
+            for (int k = 0; k < nk; ++k) xs[k] = in[(size_t)(k0 + k) * g->n_seg + s];
+            for (int c0 = 0; c0 < g->seg_c[s]; c0 += 64) {
+                int rc = launch_wgrad_tc_multi(xs, in_c[s], c0, g->seg_off[s] + c0, dz + k0, dz_c, nk, batch, h, w, g->cout, cin_total, dw, st);
+                if (rc != VSRB_OK) return rc;
+            }
+        }
+        if (db)
+            for (int k = 0; k < nk; ++k) {
+                int rc = launch_bias_grad(dz[k0 + k], dz_c, (long long)batch * h * w, g->cout, g->dtype, db, st);
+                if (rc != VSRB_OK) return rc;
+            }
+    }
+    return VSRB_OK;
+}
 
 int vsrb_conv2d_wgrad(const vsrb_conv_geom* g, const void* const* in, const int32_t* in_c, const void* dz, int32_t dz_c,
                       int32_t batch, int32_t h, int32_t w, int32_t imgs_per_group, int32_t cin_total, float* dw, float* db,

@@ -34,8 +34,12 @@ static constexpr int kWgStageBytes = 3 * kWgCopyBytes + kWgZBytes;          // 4
 static constexpr int kWgStages = 4;
 static constexpr int kWgSmem = 1024 + 1024 + kWgStages * kWgStageBytes;
 
+static constexpr int kWgMaxChunks = 16;
 struct WgTcParams {
-    CUtensorMap xmap, zmap;
+    // One launch may sum over up to 16 (x, dz) tensor pairs of one shape ("chunks": the uses of a recurrent conv at
+    // different time steps), so their weight gradient needs neither a launch per use nor a concatenation.
+    CUtensorMap xmap[kWgMaxChunks], zmap[kWgMaxChunks];
+    int tiles_per_chunk;
     int H, W, batch;
     int tiles_x, tiles_per_img, total_tiles;
     int c0, n0;                 // channel offsets inside x / dz
@@ -83,8 +87,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
         int slot = 0;
         uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-            const int img = tile / P.tiles_per_img;
-            const int t = tile - img * P.tiles_per_img;
+            const int chunk = tile / P.tiles_per_chunk;
+            const int tc = tile - chunk * P.tiles_per_chunk;
+            const int img = tc / P.tiles_per_img;                 // image inside its chunk
+            const int t = tc - img * P.tiles_per_img;
             const int ty = t / P.tiles_x, tx = t - ty * P.tiles_x;
             const uint32_t sa = stage0 + slot * kWgStageBytes;
             mbar_wait(empty0 + 8 * slot, phase ^ 1, P.dbg, 11, dead);
@@ -93,8 +99,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
             } else if (elect_one()) {
                 mbar_expect_tx(full0 + 8 * slot, kWgStageBytes);
                 for (int kx = 0; kx < 3; ++kx)
-                    tma_load_4d(&P.xmap, full0 + 8 * slot, sa + kx * kWgCopyBytes, P.c0, tx * kWgTW + kx - 1, ty * kWgRows - 1, img);
-                tma_load_4d(&P.zmap, full0 + 8 * slot, sa + 3 * kWgCopyBytes, P.n0, tx * kWgTW, ty * kWgRows, img);
+                    tma_load_4d(&P.xmap[chunk], full0 + 8 * slot, sa + kx * kWgCopyBytes, P.c0, tx * kWgTW + kx - 1, ty * kWgRows - 1, img);
+                tma_load_4d(&P.zmap[chunk], full0 + 8 * slot, sa + 3 * kWgCopyBytes, P.n0, tx * kWgTW, ty * kWgRows, img);
             }
             __syncwarp();
             if (++slot == kWgStages) { slot = 0; phase ^= 1; }
@@ -237,9 +243,10 @@ int launch_bias_grad(const void* dz, int dz_c, long long pixels, int cout, int d
     return VSRB_OK;
 }
 
-// one 64-input-channel block (x channels [c0, c0+64), OIHW offset ci_off) against all 64-wide output blocks
-int launch_wgrad_tc(const void* x, int x_c, int c0, int ci_off, const void* dz, int dz_c, int batch, int h, int w, int cout,
-                    int cin_total, float* dw, cudaStream_t stream) {
+// one 64-input-channel block (x channels [c0, c0+64), OIHW offset ci_off) against all 64-wide output blocks, summed over
+// `n_chunks` (x, dz) pairs of `batch` images each
+int launch_wgrad_tc_multi(const void* const* xs, int x_c, int c0, int ci_off, const void* const* dzs, int dz_c, int n_chunks,
+                          int batch, int h, int w, int cout, int cin_total, float* dw, cudaStream_t stream) {
     static EncodeTiledFn encode = nullptr;
     static bool attr[64] = {false};                  // function attributes are per device
     static int sm_count[64] = {0};
@@ -247,6 +254,7 @@ int launch_wgrad_tc(const void* x, int x_c, int c0, int ci_off, const void* dz, 
     int dev = 0;
     VSRB_CUDA(cudaGetDevice(&dev));
     VSRB_CHECK_ARG(dev >= 0 && dev < 64, "device ordinal %d out of range", dev);
+    VSRB_CHECK_ARG(n_chunks >= 1 && n_chunks <= kWgMaxChunks, "wgrad: 1..%d chunks per launch", kWgMaxChunks);
     {
         std::lock_guard<std::mutex> lock(init_mutex);
         if (!encode) {
@@ -270,30 +278,35 @@ int launch_wgrad_tc(const void* x, int x_c, int c0, int ci_off, const void* dz, 
     P.H = h; P.W = w; P.batch = batch;
     P.tiles_x = ceil_div(w, kWgTW);
     P.tiles_per_img = P.tiles_x * ceil_div(h, kWgRows);
-    P.total_tiles = P.tiles_per_img * batch;
+    P.tiles_per_chunk = P.tiles_per_img * batch;
+    P.total_tiles = P.tiles_per_chunk * n_chunks;
     P.c0 = c0; P.cout = cout; P.cin_total = cin_total; P.ci_off = ci_off; P.dw = dw;
     P.dbg = debug_flag();
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    {
-        cuuint64_t dims[4] = {(cuuint64_t)x_c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)batch};
-        cuuint64_t strides[3] = {(cuuint64_t)x_c * 2, (cuuint64_t)w * x_c * 2, (cuuint64_t)h * w * x_c * 2};
-        cuuint32_t box[4] = {64, kWgTW, kWgRows + 2, 1};
-        CUresult r = encode(&P.xmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) { set_error("wgrad: tensor map (x) failed with %d", (int)r); return VSRB_E_CUDA; }
-    }
-    {
-        cuuint64_t dims[4] = {(cuuint64_t)dz_c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)batch};
-        cuuint64_t strides[3] = {(cuuint64_t)dz_c * 2, (cuuint64_t)w * dz_c * 2, (cuuint64_t)h * w * dz_c * 2};
-        cuuint32_t box[4] = {64, kWgTW, kWgRows, 1};
-        CUresult r = encode(&P.zmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(dz), dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) { set_error("wgrad: tensor map (dz) failed with %d", (int)r); return VSRB_E_CUDA; }
+    for (int k = 0; k < n_chunks; ++k) {
+        VSRB_CHECK_ARG(xs[k] && dzs[k] && ((reinterpret_cast<uintptr_t>(xs[k]) | reinterpret_cast<uintptr_t>(dzs[k])) & 15) == 0,
+                       "wgrad: chunk %d: null or unaligned tensor", k);
+        {
+            cuuint64_t dims[4] = {(cuuint64_t)x_c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)batch};
+            cuuint64_t strides[3] = {(cuuint64_t)x_c * 2, (cuuint64_t)w * x_c * 2, (cuuint64_t)h * w * x_c * 2};
+            cuuint32_t box[4] = {64, kWgTW, kWgRows + 2, 1};
+            CUresult r = encode(&P.xmap[k], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(xs[k]), dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { set_error("wgrad: tensor map (x) failed with %d", (int)r); return VSRB_E_CUDA; }
+        }
+        {
+            cuuint64_t dims[4] = {(cuuint64_t)dz_c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)batch};
+            cuuint64_t strides[3] = {(cuuint64_t)dz_c * 2, (cuuint64_t)w * dz_c * 2, (cuuint64_t)h * w * dz_c * 2};
+            cuuint32_t box[4] = {64, kWgTW, kWgRows, 1};
+            CUresult r = encode(&P.zmap[k], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(dzs[k]), dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { set_error("wgrad: tensor map (dz) failed with %d", (int)r); return VSRB_E_CUDA; }
+        }
     }
     const int n_blocks = ceil_div(cout, 64);
-    // every CTA ends with 9*64*64 atomics, so small problems use fewer CTAs (>= 16 pixel tiles each)
+    // every CTA ends with 9*64*64 atomics, so small problems use fewer CTAs (>= 32 pixel tiles each)
     int ctas = sms / n_blocks;
     if (ctas > P.total_tiles / 32) ctas = P.total_tiles / 32;
     if (ctas < 1) ctas = 1;
@@ -309,6 +322,11 @@ int launch_wgrad_tc(const void* x, int x_c, int c0, int ci_off, const void* dz, 
         VSRB_LAUNCH_CHECK();
     }
     return VSRB_OK;
+}
+
+int launch_wgrad_tc(const void* x, int x_c, int c0, int ci_off, const void* dz, int dz_c, int batch, int h, int w, int cout,
+                    int cin_total, float* dw, cudaStream_t stream) {
+    return launch_wgrad_tc_multi(&x, x_c, c0, ci_off, &dz, dz_c, 1, batch, h, w, cout, cin_total, dw, stream);
 }
 
 }  // namespace vsrb

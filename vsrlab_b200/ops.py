@@ -270,6 +270,21 @@ def conv2d_wgrad(geom: "L.ConvGeom", ins: Sequence[torch.Tensor], in_c: Sequence
                                            _p(dw), _p(db), _stream()), "vsrb_conv2d_wgrad")
 
 
+def conv2d_wgrad_multi(geom: "L.ConvGeom", chunks: Sequence[Tuple[Sequence[torch.Tensor], torch.Tensor]], in_c: Sequence[int],
+                       dz_c: int, batch: int, h: int, w: int, cin_total: int, dw: torch.Tensor, db: Optional[torch.Tensor]) -> None:
+    """dw / db += the gradient summed over `chunks` = [(inputs of one use, its dz), ...] of one shape, without concatenating
+    them (tensor-core path: bf16 3x3 convs whose input segments have a multiple of 64 channels)."""
+    n, ns = len(chunks), geom.n_seg
+    ptrs = (C.c_void_p * (n * ns))(*[t.data_ptr() for ins, _ in chunks for t in ins])
+    dzs = (C.c_void_p * n)(*[dz.data_ptr() for _, dz in chunks])
+    cs = (C.c_int32 * ns)(*in_c)
+    cin = sum(geom.seg_c[i] for i in range(ns))
+    flops = 2.0 * n * batch * h * w * geom.cout * cin * geom.kh * geom.kw
+    with _Timed(f"conv_wgrad[{geom.kh}x{geom.kw} {cin}->{geom.cout} {h}x{w} x{n}]" if PROFILE_SHAPES else "conv_wgrad", flops):
+        L.check(L.load().vsrb_conv2d_wgrad_multi(C.byref(geom), n, ptrs, cs, dzs, dz_c, batch, h, w, cin_total, _p(dw), _p(db),
+                                                 _stream()), "vsrb_conv2d_wgrad_multi")
+
+
 def flow_warp_bwd(x, flow, dout, dx, dflow, n: int, h: int, w: int, c: int, dtype: int, padding: int = PAD_ZEROS) -> None:
     with _Timed("flow_warp_bwd", float(n) * h * w * (3 * c * ESIZE[dtype] + 4 * c * 4)):
         L.check(L.load().vsrb_flow_warp_bwd(_p(x), _p(flow), _p(dout), _p(dx), _p(dflow), n, h, w, c, dtype, padding, _stream()),
