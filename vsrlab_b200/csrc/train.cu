@@ -425,6 +425,8 @@ static int launch_warp_bwd(const T* x, const float2* flow, const T* dout, float*
 int launch_wgrad_tc(const void* x, int x_c, int c0, int ci_off, const void* dz, int dz_c, int batch, int h, int w, int cout,
                     int cin_total, float* dw, cudaStream_t stream);
 int launch_bias_grad(const void* dz, int dz_c, long long pixels, int cout, int dtype, float* db, cudaStream_t s);
+int launch_bias_grad_multi(const void* const* dzs, int n_chunks, int dz_c, long long pixels, int cout, int dtype, float* db,
+                           cudaStream_t s);
 int launch_wgrad_tc_multi(const void* const* xs, int x_c, int c0, int ci_off, const void* const* dzs, int dz_c, int n_chunks,
                           int batch, int h, int w, int cout, int cin_total, float* dw, cudaStream_t stream);
 
@@ -455,11 +457,10 @@ int vsrb_conv2d_wgrad_multi(const vsrb_conv_geom* g, int32_t n_chunks, const voi
                 if (rc != VSRB_OK) return rc;
             }
         }
-        if (db)
-            for (int k = 0; k < nk; ++k) {
-                int rc = launch_bias_grad(dz[k0 + k], dz_c, (long long)batch * h * w, g->cout, g->dtype, db, st);
-                if (rc != VSRB_OK) return rc;
-            }
+    }
+    if (db) {
+        int rc = launch_bias_grad_multi(dz, n_chunks, dz_c, (long long)batch * h * w, g->cout, g->dtype, db, st);
+        if (rc != VSRB_OK) return rc;
     }
     return VSRB_OK;
 }
