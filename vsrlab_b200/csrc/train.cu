@@ -182,14 +182,17 @@ __device__ __forceinline__ uint4 keep_bf16(uint4 u, int valid) {
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+static constexpr int kMmaPx = 64;      // pixels of a chunk: four k16 steps amortise the per-chunk address math and barriers
+
 template <int KW, int CO_T, int CI_T>
 __global__ void __launch_bounds__(256) conv_wgrad_mma_kernel(WgradParams P) {
+    constexpr int PX = kMmaPx, NKS = PX / 16;
     constexpr int ZP = CO_T * 2 + 16, XP = CI_T * 2 + 16;             // padded row pitch in bytes
     constexpr int WT = (CO_T / 16) * (CI_T / 16);                     // 16 x 16 warp tiles of the CTA tile
     constexpr int TPW = WT >= 8 ? WT / 8 : 1;                         // tiles per warp
-    constexpr int KS = WT >= 8 ? 1 : (WT <= 4 ? 2 : 1);               // warps sharing a tile split the two k16 steps
-    __shared__ __align__(16) uint8_t zs[32 * ZP];
-    __shared__ __align__(16) uint8_t xs[(32 + KW - 1) * XP];
+    constexpr int KS = WT >= 8 ? 1 : (8 / WT > NKS ? NKS : 8 / WT);   // warps sharing a tile split the k16 steps
+    __shared__ __align__(16) uint8_t zs[PX * ZP];
+    __shared__ __align__(16) uint8_t xs[(PX + KW - 1) * XP];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ky = blockIdx.y;
     int z = blockIdx.z;
@@ -207,7 +210,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_mma_kernel(WgradParams P) {
 
     // this warp's tiles and k-steps
     const int t_first = WT >= 8 ? warp * TPW : warp % WT;
-    const int ks_own = WT >= 8 ? -1 : warp / WT;                       // -1: both k16 steps
+    const int ks_own = WT >= 8 ? -1 : warp / WT;                       // -1: all k16 steps; else steps ks_own, ks_own + KS, ...
     const bool active = WT >= 8 || ks_own < KS;
     float acc[TPW][KW][2][4];
 #pragma unroll
@@ -221,38 +224,63 @@ __global__ void __launch_bounds__(256) conv_wgrad_mma_kernel(WgradParams P) {
     const uint32_t zs0 = (uint32_t)__cvta_generic_to_shared(zs), xs0 = (uint32_t)__cvta_generic_to_shared(xs);
     const int lj = lane >> 3, lr = lane & 7;                            // ldmatrix: matrix index and row of this lane's address
 
-    for (int u = u_begin; u < u_end; ++u) {
+    // Register double buffering: the next chunk's 16-byte global loads are issued before the current chunk's MMAs and only
+    // written to shared memory after them, so the global-memory latency hides behind the tensor-core work.
+    constexpr int ZI = PX * (CO_T / 8), XI = (PX + KW - 1) * (CI_T / 8);   // 16-byte items per chunk
+    constexpr int ZJ = (ZI + 255) / 256, XJ = (XI + 255) / 256;
+    uint4 zr[ZJ], xr[XJ];
+    auto fetch = [&](int u) {
         const int xc = u % P.chunks_per_row;
         const int rowi = u / P.chunks_per_row;
         const int y = rowi % P.H;
         const long long img = (long long)g * P.imgs_per_group + rowi / P.H;
-        const int x0 = xc * 32;
+        const int x0 = xc * PX;
         const int yy = y + dy;
-        __syncthreads();
-        for (int i = tid; i < 32 * (CO_T / 8); i += 256) {            // dz chunk [32 px][CO_T] bf16
-            const int lp = i / (CO_T / 8), lc = (i % (CO_T / 8)) * 8;
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (x0 + lp < P.W && co0 + lc < P.dz_c) {
-                v = __ldg(reinterpret_cast<const uint4*>(zin + (img * hw + (long long)y * P.W + x0 + lp) * P.dz_c + co0 + lc));
-                v = keep_bf16(v, P.cout - (co0 + lc));
+#pragma unroll
+        for (int j = 0; j < ZJ; ++j) {                              // dz chunk [PX px][CO_T] bf16
+            const int i = tid + j * 256;
+            zr[j] = make_uint4(0u, 0u, 0u, 0u);
+            if (i < ZI) {
+                const int lp = i / (CO_T / 8), lc = (i % (CO_T / 8)) * 8;
+                if (x0 + lp < P.W && co0 + lc < P.dz_c) {
+                    zr[j] = __ldg(reinterpret_cast<const uint4*>(zin + (img * hw + (long long)y * P.W + x0 + lp) * P.dz_c + co0 + lc));
+                    zr[j] = keep_bf16(zr[j], P.cout - (co0 + lc));
+                }
             }
-            *reinterpret_cast<uint4*>(zs + lp * ZP + lc * 2) = v;
         }
-        for (int i = tid; i < (32 + KW - 1) * (CI_T / 8); i += 256) { // extended strip: image columns x0 - pad + e
-            const int ep = i / (CI_T / 8), lc = (i % (CI_T / 8)) * 8;
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            const int xx = x0 - pad + ep;
-            if (yy >= 0 && yy < P.H && xx >= 0 && xx < P.W && c0 + lc < P.in_c[s]) {
-                v = __ldg(reinterpret_cast<const uint4*>(xin + (img * hw + (long long)yy * P.W + xx) * P.in_c[s] + c0 + lc));
-                v = keep_bf16(v, P.seg_c[s] - (c0 + lc));
+#pragma unroll
+        for (int j = 0; j < XJ; ++j) {                              // extended strip: image columns x0 - pad + e
+            const int i = tid + j * 256;
+            xr[j] = make_uint4(0u, 0u, 0u, 0u);
+            if (i < XI) {
+                const int ep = i / (CI_T / 8), lc = (i % (CI_T / 8)) * 8;
+                const int xx = x0 - pad + ep;
+                if (yy >= 0 && yy < P.H && xx >= 0 && xx < P.W && c0 + lc < P.in_c[s]) {
+                    xr[j] = __ldg(reinterpret_cast<const uint4*>(xin + (img * hw + (long long)yy * P.W + xx) * P.in_c[s] + c0 + lc));
+                    xr[j] = keep_bf16(xr[j], P.seg_c[s] - (c0 + lc));
+                }
             }
-            *reinterpret_cast<uint4*>(xs + ep * XP + lc * 2) = v;
+        }
+    };
+    if (u_begin < u_end) fetch(u_begin);
+    for (int u = u_begin; u < u_end; ++u) {
+        __syncthreads();                                            // the previous chunk's fragments have been read
+#pragma unroll
+        for (int j = 0; j < ZJ; ++j) {
+            const int i = tid + j * 256;
+            if (i < ZI) *reinterpret_cast<uint4*>(zs + (i / (CO_T / 8)) * ZP + (i % (CO_T / 8)) * 16) = zr[j];
+        }
+#pragma unroll
+        for (int j = 0; j < XJ; ++j) {
+            const int i = tid + j * 256;
+            if (i < XI) *reinterpret_cast<uint4*>(xs + (i / (CI_T / 8)) * XP + (i % (CI_T / 8)) * 16) = xr[j];
         }
         __syncthreads();
+        if (u + 1 < u_end) fetch(u + 1);
         if (active) {
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-                if (ks_own >= 0 && ks != ks_own) continue;
+            for (int ks = 0; ks < NKS; ++ks) {
+                if (ks_own >= 0 && (ks % KS) != ks_own) continue;
                 const int q0 = ks * 16;
 #pragma unroll
                 for (int t = 0; t < TPW; ++t) {
@@ -525,7 +553,8 @@ int vsrb_conv2d_wgrad(const vsrb_conv_geom* g, const void* const* in, const int3
     P.cout = g->cout; P.cin_total = cin_total;
     P.n_co_blk = ceil_div(g->cout, co_t);
     P.dw = dw;
-    P.chunks_per_row = ceil_div(w, 32);
+    const bool mma_path = g->dtype == VSRB_BF16 && !getenv("VSRB_WGRAD_FFMA");
+    P.chunks_per_row = ceil_div(w, mma_path ? kMmaPx : 32);
     const long long units_g = (long long)imgs_per_group * h * P.chunks_per_row;
     VSRB_CHECK_ARG(units_g < (1LL << 31), "wgrad: too many pixels per group");
     P.units_g = (int)units_g;
