@@ -4,7 +4,7 @@
 from collections import OrderedDict
 
 import torch
-import torch.nn as nn
+from torch import nn
 
 from vsrlab.core import PROJECT_ROOT
 from vsrlab.core.modules.conv import ConvReLU
@@ -26,14 +26,13 @@ class SpynetModule(nn.Module):
 class Spynet(nn.Module):
     def __init__(self, pretrained: bool = False):
         super().__init__()
-        self.basic_module = nn.ModuleList([SpynetModule() for _ in range(6)])
-        self.register_buffer('mean', torch.Tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1))
-        self.register_buffer('std', torch.Tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1))
+        self.basic_module = nn.ModuleList(SpynetModule() for _ in range(6))      # six pyramid levels, coarse to fine
+        for name, rgb in (("mean", (0.485, 0.456, 0.406)), ("std", (0.229, 0.224, 0.225))):   # ImageNet statistics
+            self.register_buffer(name, torch.tensor(rgb, dtype=torch.float32).view(1, 3, 1, 1))
         if pretrained:
-            # same blob location and key remap as reference spynet.py:32-36
-            state_dict = torch.load(f'{PROJECT_ROOT}/src/optical_flow/weights/spynet-sintel.pth')
-            new_dict = OrderedDict([(key[13:34] + '.0' + key[34:], state_dict[key]) for key in state_dict.keys()])
-            self.basic_module.load_state_dict(new_dict)
+            # the reference's blob location and key remap (spynet.py:32-36): "basic_module.N.basic_module.M" + ".0" + rest
+            blob = torch.load(f"{PROJECT_ROOT}/src/optical_flow/weights/spynet-sintel.pth")
+            self.basic_module.load_state_dict(OrderedDict((k[13:34] + ".0" + k[34:], v) for k, v in blob.items()))
 
     def compute_flow(self, ref, supp):
         """Flow on inputs whose sides are multiples of 32 (spynet.py:38-67)."""
@@ -44,8 +43,8 @@ class Spynet(nn.Module):
         return VF.spynet_flow(self, ref, supp, resize=True)
 
 
-def flow_warp(x, flow, interpolation='bilinear', padding_mode='zeros', align_corners=True):
+def flow_warp(x, flow, interpolation="bilinear", padding_mode="zeros", align_corners=True):
     """Bilinear backward warp; `flow` is channels-last [T,h,w,2] (spynet.py:95-106)."""
-    if interpolation != 'bilinear' or not align_corners:
+    if interpolation != "bilinear" or not align_corners:
         raise NotImplementedError("the hot path only uses bilinear / align_corners=True (reference spynet.py:95)")
     return VF.flow_warp(x, flow, padding_mode)
