@@ -404,9 +404,12 @@ def _basicvsr_run(bv, lrs: torch.Tensor, dt: int, x_nhwc: Optional[torch.Tensor]
 
     # ---- bidirectional propagation: both directions run as two weight groups ------------
     ops.TAG = "propagation"
-    x5 = x_nhwc.view(n, t, h, w, clr)
     pairs = ws("lr_pairs", (t, 2 * n, h, w, clr), tdt, dev)
-    pairs.copy_(torch.cat([x5.flip(1), x5], 0).transpose(0, 1))      # step s: [frame t-1-s | frame s]
+    key = ("pair_gather", n, t, str(dev))
+    if key not in _consts:                                             # step s: [frame t-1-s | frame s] of every clip
+        _consts[key] = torch.tensor([i * t + (t - 1 - s if g == 0 else s) for s in range(t) for g in range(2) for i in range(n)],
+                                    device=dev)
+    torch.index_select(x_nhwc.view(n * t, h * w * clr), 0, _consts[key], out=pairs.view(t * 2 * n, h * w * clr))
     bank = ws("feat_bank", (2, n, t, h, w, mid_c), tdt, dev)           # [0]=backward, [1]=forward features
     fbk, ffw = bank[0], bank[1]
     frame_el = h * w * mid_c
