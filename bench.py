@@ -8,20 +8,29 @@ unless --blocks is given), bf16 mode.  Prints ONE JSON line (rank 0).
 
 * value        frames/s, all ranks, inputs already resident in HBM (CUDA events, max over ranks)
 * e2e          same metric through the public nn.Module call with pinned HOST buffers: H2D of the
-               clip and D2H of sr/lq inside the timed region
-* roofline     the dominant kernel (tcgen05 implicit-GEMM conv): algorithmic conv FLOPs / CUDA-event
+               clip and D2H of sr/lq inside the timed region (`e2e_narrow`: the same with the opt-in
+               uint8 `sr` output the reference's PNG dump consumes)
+* roofline     the dominant kernel family (tcgen05 implicit-GEMM convs): algorithmic conv FLOPs / CUDA-event
                time of those launches, against MEASURED_PEAKS.json
-* cpu_baseline the CPU oracle (restatement of the reference's PyTorch path, oracle/) timed on this
-               box's host cores on a bounded sample
-* --impl reference: the reference's CPU path (oracle port; /root/reference cannot travel to the
-               GPU box) on all host cores, bounded sample per step.
+* parity       the same 6 frames of one 180x320 clip through the reference's own modules on the CPU
+               (oracle/_ref, else the oracle port) and through the GPU path: fp32-mode max-abs error,
+               bf16-mode PSNR delta, flow error.  A broken gate fails the benchmark.
+* cpu_baseline that reference run, timed (frames/s on this box's host cores)
+* blocks20     the model-file default 20/20-block configuration (conf/train/model/basicvsr.yaml:2,5)
+* train_cfg4   BASELINE cfg4: training step (fp16-requesting autocast + GradScaler + Adam, batch 8 x 15 frames
+               64x64 per GPU), DDP over NCCL when N > 1
+* --impl reference: the reference's own CPU implementation (oracle/_ref; else the oracle port) on all
+               host cores, bounded sample per step.
 """
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
+import subprocess
 import sys
+import tempfile
 import threading
 import time
 from pathlib import Path
@@ -34,6 +43,7 @@ sys.path.insert(0, str(ROOT))
 METRIC = "realbasicvsr_x4_output_frames_per_sec_720p"
 UNIT = "frames/s"
 T_FRAMES, LR_H, LR_W = 30, 180, 320
+CFG4_FWD_GFLOP = {5: 3824.66, 20: 9260.48}        # forward conv FLOPs of one cfg4 micro-batch; training ~ 3x
 
 
 def peaks():
@@ -45,12 +55,12 @@ def peaks():
     return {"hbm": 6650.0, "tf_burst": 1590.0, "tf_sust": 1400.0, "src": "fallback"}
 
 
-def build_model(blocks: int, device):
+def build_model(blocks: int, device, train_flow: bool = False):
     from vsrlab.vsr.models.RealBasicVSR.realbasicvsr import RealBasicVSR
     torch.manual_seed(0)
     m = RealBasicVSR(cleaning_blocks=blocks, mid_channels=64, upscale=4, res_blocks=blocks, pretrained_flow=False,
-                     train_flow=False)
-    return m.to(device).eval()
+                     train_flow=train_flow)
+    return m.to(device)
 
 
 class ClockSampler(threading.Thread):
@@ -94,66 +104,115 @@ class ClockSampler(threading.Thread):
                 "power_w": pw[len(pw) // 2] if pw else None, "power_limit_w": self.power_limit_w}
 
 
-def bind_to_gpu_numa_node(index: int):
-    """Run this process on the CPUs NVML reports as local to GPU `index`.  The end-to-end number moves ~0.7 GB per step
-    between pinned host memory and the GPU; with the host buffers on the far NUMA node the same run measured 40 % lower."""
+def bind_to_gpu_numa_node(index: int) -> str:
+    """Host placement for the end-to-end leg, per rank: (1) run on the CPUs NVML reports as local to GPU `index` when the
+    container's cpuset contains them, (2) ask the kernel to place this process's new pages - the pinned host buffers
+    allocated afterwards - on the GPU's own NUMA node (set_mempolicy(MPOL_PREFERRED)), which also works when those
+    CPUs are outside the cpuset.  Every step moves ~0.75 GB per rank between pinned host memory and the GPU; with the
+    buffers of all ranks on one node the 8-GPU run is bound by that node's memory / inter-socket path."""
+    notes = []
     try:
         import pynvml as nv
         nv.nvmlInit()
         h = nv.nvmlDeviceGetHandleByIndex(index)
-        words = nv.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
-        cpus = [64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1]
-        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
-        if cpus:
-            os.sched_setaffinity(0, cpus)
-            return f"{len(cpus)} cpus local to gpu {index}"
+        try:
+            words = nv.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+            cpus = [64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1]
+            allowed = [c for c in cpus if c in os.sched_getaffinity(0)]
+            if allowed:
+                os.sched_setaffinity(0, allowed)
+                notes.append(f"{len(allowed)} cpus local to gpu {index}")
+            else:
+                notes.append(f"cpus local to gpu {index} outside cpuset")
+        except Exception as e:  # noqa: BLE001
+            notes.append(f"affinity unchanged ({type(e).__name__})")
+        bus = nv.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        node_file = Path("/sys/bus/pci/devices") / bus[-12:].lower() / "numa_node"
+        node = int(node_file.read_text()) if node_file.exists() else -1
+        if node >= 0:
+            mask = (ctypes.c_ulong * 16)()
+            mask[node // 64] = 1 << (node % 64)
+            libc = ctypes.CDLL(None, use_errno=True)
+            rc = libc.syscall(238, 1, ctypes.byref(mask), 1024)          # x86-64 set_mempolicy(MPOL_PREFERRED, mask, maxnode)
+            notes.append(f"mempolicy prefer node {node}" if rc == 0 else f"mempolicy node {node} refused (errno {ctypes.get_errno()})")
+        else:
+            notes.append("numa node unknown")
     except Exception as e:  # noqa: BLE001
-        return f"unchanged ({type(e).__name__})"
-    return "unchanged"
+        notes.append(f"nvml unavailable ({type(e).__name__})")
+    return "; ".join(notes)
 
 
-def oracle_sample(blocks: int, frames: int, threads: int):
-    """CPU restatement of the reference path on `frames` frames of one 180x320 clip."""
+# ---------------------------------------------------------------------------------------------
+# the reference on the CPU: its own modules (oracle/_ref, byte-compiled by oracle/make_ref.py) in a process of
+# their own - they call themselves `vsrlab`, like the drop-in - or, where those are absent, the oracle port.
+# ---------------------------------------------------------------------------------------------
+def reference_available() -> bool:
+    from oracle import make_ref
+    return make_ref.available()
+
+
+def run_reference_process(blocks: int, frames: int, threads: int, steps: int = 1, warmup: int = 1, dump: str = "", seed: int = 0):
+    cmd = [sys.executable, "-m", "oracle.ref_runner", "--blocks", str(blocks), "--frames", str(frames), "--threads", str(threads),
+           "--steps", str(steps), "--warmup", str(warmup), "--seed", str(seed), "--height", str(LR_H), "--width", str(LR_W)]
+    if dump:
+        cmd += ["--dump", dump]
+    out = subprocess.run(cmd, cwd=str(ROOT), check=True, capture_output=True, text=True).stdout
+    return json.loads(out.strip().splitlines()[-1])
+
+
+def oracle_port_sample(blocks: int, frames: int, threads: int, steps: int = 1, warmup: int = 1, seed: int = 0):
+    """CPU restatement of the reference path (oracle/vsr_oracle.py) on `frames` frames of one 180x320 clip."""
     from oracle import vsr_oracle as O
     torch.set_num_threads(threads)
     sd = {k: v.detach().cpu() for k, v in build_model(blocks, "cpu").state_dict().items()}
-    x = torch.rand(1, frames, 3, LR_H, LR_W, generator=torch.Generator().manual_seed(0))
+    x = torch.rand(1, frames, 3, LR_H, LR_W, generator=torch.Generator().manual_seed(seed))
     with torch.no_grad():
+        for _ in range(warmup):
+            O.realbasicvsr(x[:, :2].clone(), sd)
         t0 = time.perf_counter()
-        O.realbasicvsr(x, sd)
+        for _ in range(steps):
+            sr, lq, ff, fb = O.realbasicvsr(x.clone(), sd, return_flows=True)
         dt = time.perf_counter() - t0
-    return frames / dt, dt
+    n = steps * frames
+    return {"frames": n, "seconds": dt, "frames_per_s": n / dt, "kind": "port", "threads": threads}, (sr, lq, ff, fb)
 
 
 def run_reference(a):
-    """--impl reference: the reference's CPU implementation (oracle port) on the host cores."""
+    """--impl reference: the reference's CPU implementation on the host cores, bounded sample per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    frames = 3
-    for _ in range(a.warmup):
-        oracle_sample(a.blocks, 2, cores)
-    t0 = time.perf_counter()
-    for _ in range(a.steps):
-        oracle_sample(a.blocks, frames, cores)
-    dt = time.perf_counter() - t0
-    v = a.steps * frames / dt
-    line = {
+    total = a.steps + a.warmup
+    frames = T_FRAMES if total <= 2 else max(3, min(T_FRAMES, 96 // max(total, 1)))      # whole run: a few minutes at most
+    if reference_available():
+        r = run_reference_process(a.blocks, frames, cores, steps=a.steps, warmup=a.warmup)
+        what = "the reference's own modules (oracle/_ref, byte-compiled from the reference sources), torch CPU fp32"
+    else:
+        r, _ = oracle_port_sample(a.blocks, frames, cores, steps=a.steps, warmup=a.warmup)
+        what = "oracle port (oracle/vsr_oracle.py; oracle/_ref was not built), torch CPU fp32"
+    v = r["frames_per_s"]
+    full = frames == T_FRAMES
+    sample = (f"{frames} frames of one {LR_H}x{LR_W} clip per step" + ("" if full else " (a bounded sample of the 30-frame clip: "
+              "frames/s is NOT extrapolated, the per-clip fixed work of a shorter clip is included)") + f"; {what}")
+    cfg = workload_config(a, 1)
+    cfg.update({"clips_per_gpu_per_step": 1, "frames_per_clip": frames, "precision": "fp32 (torch CPU, oneDNN)",
+                "cuda_graph": "n/a (CPU)", "parallelism": f"{cores} host threads, no GPU", "l2": "n/a"})
+    emit({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-        "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": workload_config(a, 1),
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{frames} frames of one 180x320 clip per step, full Real-BasicVSR forward (oracle/vsr_oracle.py)"},
+        "ms_per_step": r["seconds"] / max(a.steps, 1) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": r["kind"], "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }
-    emit(line)
+    })
 
 
 def workload_config(a, clips):
     return {"workload": f"cfg3: Real-BasicVSR x4 inference, {T_FRAMES}-frame {LR_H}x{LR_W}->{4*LR_H}x{4*LR_W} clips, "
                         f"{a.blocks}/{a.blocks} blocks", "clips_per_gpu_per_step": clips, "frames_per_clip": T_FRAMES,
-            "precision": "bf16 activations, fp32 accumulate", "cuda_graph": "whole forward captured once, replayed per step", "parallelism": f"clips sharded over {a.gpus} GPU(s), no collective",
+            "precision": "bf16 activations, fp32 accumulate", "cuda_graph": "whole forward captured once, replayed per step",
+            "parallelism": f"clips sharded over {a.gpus} GPU(s), no collective",
             "l2": "per-step working set (GBs of activations) exceeds the 126 MB L2; no explicit flush"}
 
 
@@ -164,6 +223,131 @@ def emit(line: dict) -> None:
 
 
 _REAL_STDOUT = 1
+
+
+# ---------------------------------------------------------------------------------------------
+# parity at the benchmark's own shape + the CPU baseline (rank 0, N = 1)
+# ---------------------------------------------------------------------------------------------
+def parity_and_cpu_baseline(a, dev, frames: int = 6):
+    from oracle import vsr_oracle as O
+    from vsrlab_b200 import functional as VF
+    import numpy as np
+    cores = os.cpu_count() or 1
+    if reference_available():
+        with tempfile.TemporaryDirectory() as td:
+            dump = str(Path(td) / "ref.npz")
+            r = run_reference_process(a.blocks, frames, cores, steps=1, warmup=1, dump=dump)
+            d = np.load(dump)
+            sr_ref, lq_ref = torch.from_numpy(d["sr"]), torch.from_numpy(d["lq"])
+            ff_ref, fb_ref = torch.from_numpy(d["flow_forward"]), torch.from_numpy(d["flow_backward"])
+        what = "the reference's own modules (oracle/_ref)"
+    else:
+        r, (sr_ref, lq_ref, ff_ref, fb_ref) = oracle_port_sample(a.blocks, frames, cores)
+        ff_ref, fb_ref = ff_ref.reshape(-1, 2, LR_H, LR_W), fb_ref.reshape(-1, 2, LR_H, LR_W)
+        what = "oracle port (oracle/vsr_oracle.py)"
+    model = build_model(a.blocks, dev).eval()                 # same seed, same constructor order => the reference's weights
+    x = torch.rand(1, frames, 3, LR_H, LR_W, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad(), VF.precision("fp32"):
+        xin = x.clone().to(dev)
+        sr32, lq32 = model(xin)
+        ff, fb = model.basicvsr.compute_flow(lq32)
+    with torch.no_grad(), VF.precision("bf16"):
+        sr16, _ = model(x.clone().to(dev))
+        ff16, fb16 = model.basicvsr.compute_flow(lq32)
+    hr = torch.rand(sr_ref.shape, generator=torch.Generator().manual_seed(9))
+    par = {
+        "against": what, "sample": f"{frames} frames of one {LR_H}x{LR_W} clip, {a.blocks}/{a.blocks} blocks, seed 0",
+        "fp32_max_abs": max((sr32.cpu() - sr_ref).abs().max().item(), (lq32.cpu() - lq_ref).abs().max().item()),
+        "bf16_psnr_delta_db": abs(O.psnr(sr16.cpu(), hr) - O.psnr(sr_ref, hr)),
+        "bf16_psnr_vs_reference_db": O.psnr(sr16.cpu(), sr_ref),
+        "flow_max_px": max((ff.cpu() - ff_ref).abs().max().item(), (fb.cpu() - fb_ref).abs().max().item()),
+        "flow_max_px_bf16": max((ff16.cpu() - ff_ref).abs().max().item(), (fb16.cpu() - fb_ref).abs().max().item()),
+        "gates": {"fp32_max_abs": 1e-4, "bf16_psnr_delta_db": 0.05, "flow_max_px": 1e-2},
+    }
+    par["ok"] = bool(par["fp32_max_abs"] <= 1e-4 and par["bf16_psnr_delta_db"] <= 0.05 and par["flow_max_px"] <= 1e-2
+                     and par["flow_max_px_bf16"] <= 1e-2)
+    base = {"value": r["frames_per_s"], "unit": UNIT, "cores": cores, "kind": r["kind"],
+            "sample": f"{frames} frames of one {LR_H}x{LR_W} clip ({r['seconds']:.1f} s after one warm-up pass), full forward, {what}"}
+    del model
+    return par, base
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE cfg4: the training step, on the reference's recipe (train.py:74,90-98; core/utils.py:147-151,235-240,270-280)
+# ---------------------------------------------------------------------------------------------
+def train_cfg4(a, dev, world, rank, local, steps: int = 8, warmup: int = 4, batch: int = 8, frames: int = 15, num_grad_acc: int = 4):
+    import warnings
+    import torch.distributed as dist
+    import torch.nn.functional as F
+    from vsrlab_b200 import functional as VF
+    VF.set_precision(None)                                   # follow autocast, as train.py does
+    model = build_model(a.blocks, dev, train_flow=True).train()
+    net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local]) if world > 1 else model
+    opt = torch.optim.Adam(net.parameters(), lr=1e-4, betas=(0.9, 0.99))
+    sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=600000, eta_min=1e-7)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        scaler = torch.cuda.amp.GradScaler()
+    g = torch.Generator().manual_seed(rank)
+    lr = torch.rand(batch, frames, 3, 64, 64, generator=g).to(dev)
+    hr = torch.rand(batch, frames, 3, 256, 256, generator=g).to(dev)
+
+    def charbonnier(x, y):
+        return torch.sqrt((x - y) ** 2 + 1e-9).mean()
+
+    def micro_step(i):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ctx = torch.cuda.amp.autocast()
+        with ctx:
+            sr, lq = net(lr.clone())
+            loss = charbonnier(sr, hr) + charbonnier(lq, F.interpolate(hr.flatten(0, 1), size=(64, 64), mode="bilinear").view_as(lq))
+        scaler.scale(loss / num_grad_acc).backward()         # under DDP the gradient all-reduce fires here, every micro-step
+        if (i + 1) % num_grad_acc == 0:
+            scaler.unscale_(opt)
+            torch.nn.utils.clip_grad_norm_(net.parameters(), 1.0)
+            scaler.step(opt)
+            scaler.update()
+            sched.step()
+            opt.zero_grad()
+        return loss.detach()
+
+    losses = [micro_step(i) for i in range(warmup)]
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    losses += [micro_step(i) for i in range(steps)]
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    same = True
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        w0 = torch.cat([p.detach().flatten() for p in model.parameters()])
+        ref = w0.clone()
+        dist.broadcast(ref, 0)
+        same = bool(torch.equal(w0, ref))
+        flag = torch.tensor([1.0 if same else 0.0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        same = bool(flag.item() == 1.0)
+    ms = t.item()
+    tf = 3.0 * CFG4_FWD_GFLOP.get(a.blocks, float("nan")) * world / ms              # GFLOP / ms = TFLOP/s, whole job
+    pk = peaks()
+    out = {"workload": f"cfg4: Real-BasicVSR training micro-step, batch {batch}/GPU x {frames} frames 64x64 LR, {a.blocks}/{a.blocks} blocks, "
+                       f"train_flow=true, fp16-requesting autocast + GradScaler, num_grad_acc={num_grad_acc}, Adam, clip 1.0",
+           "n_gpus": world, "parallelism": "DDP, NCCL all-reduce on every micro-step (no no_sync, as the reference)" if world > 1 else "single GPU",
+           "ms_per_step": ms, "clips_per_s": world * batch / (ms * 1e-3), "tflops": tf, "frac_of_sustained_peak": tf / world / pk["tf_sust"],
+           "loss_first": float(losses[0]), "loss_last": float(losses[-1]), "replicas_identical": same,
+           "grad_scale": float(scaler.get_scale()), "steps": steps, "warmup": warmup}
+    del net, model, opt
+    VF.set_precision(a.precision)
+    return out
 
 
 def main():
@@ -183,7 +367,8 @@ def main():
                          "sequential propagation kernels with another clip's work)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "fp32_ffma"],
                     help="bf16 (headline) | fp32 = fp32-accurate split-bf16 on the tensor cores | fp32_ffma = FFMA kernel")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the reference CPU run and the parity record")
+    ap.add_argument("--no-extras", action="store_true", help="skip the blocks20 / train_cfg4 / e2e_narrow legs")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl != "reference" else a.warmup
     if a.impl == "reference":
@@ -191,20 +376,22 @@ def main():
 
     import torch.distributed as dist
     from vsrlab_b200 import functional as VF
-    from vsrlab_b200 import ops
+    from vsrlab_b200 import ops, shard
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    numa = bind_to_gpu_numa_node(local)       # pinned host buffers are then first-touched next to the GPU's PCIe root
+    numa = bind_to_gpu_numa_node(local)       # pinned host buffers are then placed next to the GPU's PCIe root
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     VF.set_precision(a.precision)
-    model = build_model(a.blocks, dev)
+    model = build_model(a.blocks, dev).eval()
     clips = a.clips
+    # clip sharding: a global queue of world*clips clips per step, rank r takes clips r, r+W, ...
+    my_clips = shard.shard_clips(world * clips, rank, world)
     gen = torch.Generator().manual_seed(1000 + rank)
-    host_lr = torch.rand(clips, T_FRAMES, 3, LR_H, LR_W, generator=gen).pin_memory()
+    host_lr = torch.rand(len(my_clips), T_FRAMES, 3, LR_H, LR_W, generator=gen).pin_memory()
     lr_dev = host_lr.to(dev)
     work = torch.empty_like(lr_dev)
 
@@ -215,11 +402,11 @@ def main():
 
     side = [torch.cuda.Stream(device=dev) for _ in range(max(0, a.streams - 1))]
 
-    def step():
+    def step(m=model):
         work.copy_(lr_dev)                       # the model refines its input in place (reference contract)
         if a.streams <= 1:
             with torch.no_grad():
-                return model(work)
+                return m(work)
         # clips are independent: split them over the streams (same public call, one per stream)
         cur = torch.cuda.current_stream(dev)
         parts = work.chunk(a.streams, dim=0)
@@ -228,7 +415,7 @@ def main():
             st = cur if i == 0 else side[i - 1]
             st.wait_stream(cur) if i else None
             with torch.cuda.stream(st), torch.no_grad():
-                outs.append(model(part))
+                outs.append(m(part))
         for st in side:
             cur.wait_stream(st)
         return outs
@@ -255,46 +442,50 @@ def main():
     # What a user of the drop-in does for a stream of clips: H2D of clip k+1 and D2H of clip k-1 run on a copy
     # stream while `model(lr)` of clip k runs on the compute stream.  Every step's H2D and D2H are inside the
     # timed region; the region ends when the last result has landed in pinned host memory.
-    host_sr = [torch.empty(clips, T_FRAMES, 3, 4 * LR_H, 4 * LR_W).pin_memory() for _ in range(2)]
-    host_lq = [torch.empty_like(host_lr).pin_memory() for _ in range(2)]
     copy_stream = torch.cuda.Stream(device=dev)
     main_stream = torch.cuda.current_stream(dev)
 
-    def e2e_run(n_steps):
-        pending = None                                    # (sr, lq, done_event) of the previous step
-        nxt = None
-        with torch.cuda.stream(copy_stream):
-            nxt = host_lr.to(dev, non_blocking=True)
-            up = torch.cuda.Event()
-            up.record(copy_stream)
-        for k in range(n_steps):
-            x, ready = nxt, up
-            main_stream.wait_event(ready)
-            x.record_stream(main_stream)
-            with torch.no_grad():
-                sr, lq = model(x)
-            done = torch.cuda.Event()
-            done.record(main_stream)
-            with torch.cuda.stream(copy_stream):
-                if k + 1 < n_steps:                       # prefetch the next clip batch
-                    nxt = host_lr.to(dev, non_blocking=True)
-                    up = torch.cuda.Event()
-                    up.record(copy_stream)
-                copy_stream.wait_event(done)
-                sr.record_stream(copy_stream)
-                lq.record_stream(copy_stream)
-                host_sr[k % 2].copy_(sr, non_blocking=True)
-                host_lq[k % 2].copy_(lq, non_blocking=True)
-        main_stream.wait_stream(copy_stream)
+    def e2e_leg(sr_dtype, out_kind):
+        host_sr = [torch.empty(len(my_clips), T_FRAMES, 3, 4 * LR_H, 4 * LR_W, dtype=sr_dtype).pin_memory() for _ in range(2)]
+        host_lq = [torch.empty_like(host_lr).pin_memory() for _ in range(2)]
 
-    e2e_run(4)        # warm-up long enough for the caching allocator to own every output block the steady state needs
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    e2e_run(a.steps)
-    f1.record()
-    barrier()
-    ms_e2e = f0.elapsed_time(f1)
+        def e2e_run(n_steps):
+            nxt = None
+            with torch.cuda.stream(copy_stream):
+                nxt = host_lr.to(dev, non_blocking=True)
+                up = torch.cuda.Event()
+                up.record(copy_stream)
+            for k in range(n_steps):
+                x, ready = nxt, up
+                main_stream.wait_event(ready)
+                x.record_stream(main_stream)
+                with torch.no_grad(), VF.output_dtype(out_kind):
+                    sr, lq = model(x)
+                done = torch.cuda.Event()
+                done.record(main_stream)
+                with torch.cuda.stream(copy_stream):
+                    if k + 1 < n_steps:                       # prefetch the next clip batch
+                        nxt = host_lr.to(dev, non_blocking=True)
+                        up = torch.cuda.Event()
+                        up.record(copy_stream)
+                    copy_stream.wait_event(done)
+                    sr.record_stream(copy_stream)
+                    lq.record_stream(copy_stream)
+                    host_sr[k % 2].copy_(sr, non_blocking=True)
+                    host_lq[k % 2].copy_(lq, non_blocking=True)
+            main_stream.wait_stream(copy_stream)
+
+        e2e_run(4)    # warm-up long enough for the caching allocator to own every output block the steady state needs
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        e2e_run(a.steps)
+        f1.record()
+        barrier()
+        return f0.elapsed_time(f1), (host_sr[0].numel() * host_sr[0].element_size() + host_lq[0].numel() * 4)
+
+    ms_e2e, d2h_bytes = e2e_leg(torch.float32, None)
+    ms_e2e_u8, d2h_bytes_u8 = (0.0, 0) if a.no_extras else e2e_leg(torch.uint8, "uint8")
 
     # ---- per-kernel roofline: CUDA events around every launch of one more step --------------
     # The timed region replays a CUDA graph, so the per-launch pass must not be paced by the host either: a spin kernel
@@ -349,15 +540,48 @@ def main():
 
     warp_big = warp_standalone() if rank == 0 else 0.0
 
+    # ---- the model-file default 20/20 blocks (conf/train/model/basicvsr.yaml:2,5): "report both"  ----
+    blocks20 = None
+    if world == 1 and not a.no_extras and a.blocks != 20:
+        VF.clear_caches()
+        m20 = build_model(20, dev).eval()
+        for _ in range(3):
+            step(m20)
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        n20 = max(3, min(a.steps, 5))
+        for _ in range(n20):
+            step(m20)
+        g1.record()
+        torch.cuda.synchronize()
+        ms20 = g0.elapsed_time(g1) / n20
+        blocks20 = {"workload": "cfg3 with 20/20 blocks (model-file defaults)", "value": clips * T_FRAMES / (ms20 * 1e-3), "unit": UNIT,
+                    "ms_per_step": ms20, "steps": n20, "conv_tflops": clips * 32772.49 / ms20}
+        del m20
+        VF.clear_caches()
+
     if ops.debug_status() != 0:                     # a kernel gave up on a pipeline barrier: the numbers would be meaningless
         raise RuntimeError("libvsrb200 reported a pipeline time-out during the benchmark")
-    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+
+    train = None
+    if not a.no_extras:
+        VF.clear_caches()
+        torch.cuda.empty_cache()
+        train = train_cfg4(a, dev, world, rank, local)
+        VF.clear_caches()
+
+    t = torch.tensor([ms, ms_e2e, ms_e2e_u8], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = t.tolist()
-    frames_step = world * clips * T_FRAMES
+    ms, ms_e2e, ms_e2e_u8 = t.tolist()
+    frames_step, _ = shard.reduce_throughput(len(my_clips) * T_FRAMES, 0.0, dev)          # sum of frames over ranks
     value = frames_step * a.steps / (ms * 1e-3)
     e2e = frames_step * a.steps / (ms_e2e * 1e-3)
+    affinities = [numa]
+    if world > 1:
+        affinities = [None] * world
+        dist.all_gather_object(affinities, numa)
     if rank == 0:
         pk = peaks()
         traffic = {}
@@ -372,12 +596,13 @@ def main():
             "dtype": {"bf16": "bf16", "fp32": "bf16x3 (split-bf16, fp32-accurate)", "fp32_ffma": "f32"}[a.precision],
             "data": "synthetic", "config": workload_config(a, clips),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": host_lr.numel() * 4,
-                    "d2h_bytes_per_step": (host_sr[0].numel() + host_lq[0].numel()) * 4,
+                    "d2h_bytes_per_step": d2h_bytes,
                     "pipeline": "copies on a second stream overlap the next step's compute; all copies are inside the timed region",
-                    "host_affinity": numa},
+                    "host_affinity": affinities},
             "gpu_launches": launches,
             "clocks": sampler.summary(),
-            "roofline": {"kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, all launches of a step)", "bound": "tensor",
+            "roofline": {"kernel": "conv_tc_kernel + conv_ring_kernel (tcgen05 implicit-GEMM convs, all launches of a step)",
+                         "bound": "tensor",
                          "achieved": conv[1] / conv[0] / 1e12, "peak": pk["tf_sust"], "unit": "TFLOP/s",
                          "frac": conv[1] / conv[0] / 1e12 / pk["tf_sust"],
                          "traffic": (traffic.get("conv_tc") or {}).get("dram_bytes_per_launch"),
@@ -388,21 +613,32 @@ def main():
                               "unit": "GB/s", "frac": warp[1] / warp[0] / 1e9 / pk["hbm"],
                               "traffic": (traffic.get("flow_warp") or {}).get("dram_bytes_per_launch"), "traffic_source": traffic.get("flow_warp"),
                               "launches_per_step": warp[2], "share_of_step": warp[0] / max(step_s_prof, 1e-9),
-                              "note": "in-step calls move 30 MB each (L2 resident, launch-latency bound); `standalone` is the "
+                              "note": "in-step calls move 30-60 MB each (L2 resident, launch-latency bound); `standalone` is the "
                                       "same kernel on 256 feature maps (3.9 GB moved, L2 flushed)",
                               "standalone": {"achieved": warp_big, "frac": warp_big / pk["hbm"], "unit": "GB/s"}},
             "kernel_time_share": {k: round(v[0] / max(step_s_prof, 1e-9), 4) for k, v in fam.items()},
             "conv_by_part": {k: {"ms": round(v[0] * 1e3, 3), "tflops": round(v[1] / v[0] / 1e12, 1), "launches": v[2]}
                              for k, v in parts.items()},
         }
+        if ms_e2e_u8 > 0:
+            line["e2e_narrow"] = {"value": frames_step * a.steps / (ms_e2e_u8 * 1e-3), "unit": UNIT,
+                                  "h2d_bytes_per_step": host_lr.numel() * 4, "d2h_bytes_per_step": d2h_bytes_u8,
+                                  "note": "opt-in vsrlab_b200.set_output_dtype('uint8'): sr leaves the last conv as the 8-bit values the "
+                                          "reference's PNG dump stores (test.py:138-141); lq stays fp32.  The default (fp32 sr) is `e2e`."}
+        if blocks20:
+            line["blocks20"] = blocks20
+        if train:
+            line["train_cfg4"] = train
         if shapes:
             line["conv_by_shape"] = {k: {"ms": round(v[0] * 1e3, 3), "tflops": round(v[1] / v[0] / 1e12, 1), "launches": v[2]}
                                      for k, v in sorted(shapes.items(), key=lambda kv: -kv[1][0])}
         if world == 1 and not a.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            v, dtc = oracle_sample(a.blocks, 3, cores)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"3 frames of one 180x320 clip ({dtc:.1f} s), full forward, oracle/vsr_oracle.py"}
+            VF.clear_caches()
+            par, base = parity_and_cpu_baseline(a, dev)
+            line["parity"], line["cpu_baseline"] = par, base
+            if not par["ok"]:
+                emit(line)
+                raise RuntimeError(f"parity gate broken at the benchmark's shape: {par}")
         emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -66,6 +66,10 @@ extern "C" {
                               allocation, barrier set-up, weight fetch) may overlap the tail of the previous
                               kernel on the stream; only legal when `packed` was complete before that
                               previous kernel was enqueued                                                */
+#define VSRB_CONV_SR_F16 4 /* EPI_SR only: `f32_io` points to an fp16 [B,3,4h,4w] tensor (opt-in narrow output)   */
+#define VSRB_CONV_SR_U8  2 /* EPI_SR only: `f32_io` points to a uint8 [B,3,4h,4w] tensor holding
+                              floor(clamp(sr,0,1)*255 + 0.5): the bytes torchvision.utils.save_image writes
+                              for the reference's PNG dump (test.py:138-141)                               */
 
 /* Geometry of one convolution's weights: everything the packer and the launcher
  * must agree on.  Stride 1, 'same' padding (kh//2, kw//2), dilation 1. */

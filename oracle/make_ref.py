@@ -1,0 +1,69 @@
+"""Recipe that places the reference's OWN hot-path modules under oracle/_ref/ so that they can travel to the GPU box.
+TEST / BASELINE INFRASTRUCTURE ONLY.
+
+/root/reference exists only in the build container.  The reference's Real-BasicVSR path is pure Python on top of
+torch / einops / torchvision, so "building" it means byte-compiling the files the path imports, from
+where they lie under /root/reference/src, into sourceless CPython modules (`*.pyc`, same relative paths) under
+oracle/_ref/src, plus a manifest with the SHA-256 of every source file compiled.  No reference SOURCE is copied anywhere;
+oracle/_ref/ holds build outputs only, is listed in .gitignore (it never enters this repository's history) but not in
+.gpurunignore, so it rides along to the GPU box like the built .so files (same image, same interpreter).
+`oracle/ref_runner.py` imports the compiled modules under the package name the reference uses for itself (`vsrlab`) in a
+process that never imports the drop-in.
+
+    python -m oracle.make_ref          # run by __graft_entry__.build() when /root/reference is present
+"""
+from __future__ import annotations
+
+import hashlib
+import json
+import py_compile
+import sys
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+REF_SRC = Path("/root/reference/src")
+DST = HERE / "_ref" / "src"
+
+# exactly what `RealBasicVSR` imports (reference realbasicvsr.py:1-3, basicvsr.py:1-7, spynet.py:1-9, upsampling.py:1-2)
+FILES = [
+    "__init__.py",
+    "core/__init__.py",
+    "core/modules/__init__.py",
+    "core/modules/conv.py",
+    "core/modules/upsampling.py",
+    "vsr/__init__.py",
+    "vsr/models/__init__.py",
+    "vsr/models/RealBasicVSR/__init__.py",
+    "vsr/models/RealBasicVSR/realbasicvsr.py",
+    "vsr/models/RealBasicVSR/modules/__init__.py",
+    "vsr/models/RealBasicVSR/modules/basicvsr.py",
+    "vsr/models/RealBasicVSR/modules/spynet.py",
+]
+
+
+def available() -> bool:
+    m = DST.parent / "MANIFEST.json"
+    if not (DST / "vsr/models/RealBasicVSR/realbasicvsr.pyc").exists() or not m.exists():
+        return False
+    return json.loads(m.read_text()).get("python") == list(sys.version_info[:2])     # bytecode is interpreter-specific
+
+
+def build(force: bool = False) -> bool:
+    """Byte-compile the files; returns True when oracle/_ref is usable afterwards."""
+    if not REF_SRC.exists():
+        return available()
+    if available() and not force:
+        return True
+    manifest = {}
+    for rel in FILES:
+        src, dst = REF_SRC / rel, (DST / rel).with_suffix(".pyc")
+        dst.parent.mkdir(parents=True, exist_ok=True)
+        py_compile.compile(str(src), cfile=str(dst), dfile=f"<reference>/src/{rel}", doraise=True)
+        manifest[rel] = hashlib.sha256(src.read_bytes()).hexdigest()
+    (DST.parent / "MANIFEST.json").write_text(json.dumps({"source": str(REF_SRC), "python": list(sys.version_info[:2]),
+                                                           "sha256_of_sources": manifest}, indent=1))
+    return True
+
+
+if __name__ == "__main__":
+    print("oracle/_ref:", "ready" if build(force=True) else "reference not present, nothing built")

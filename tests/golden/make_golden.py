@@ -151,6 +151,22 @@ def main():
         sr, lq = net(x)
     out["sr"], out["lq"] = sr.numpy(), lq.numpy()
     np.savez_compressed(HERE / "ragged.npz", **out)
+
+    # ---- cfg2 (BASELINE.json configs[1]): SPyNet on a synthetic 7-frame 256x256 clip, both pair directions.
+    # The clip is regenerated from its seed by the tests; the flows are stored on a stride-2 lattice (phase (0,1))
+    # to keep the fixture small, plus whole-field statistics.
+    out = {}
+    torch.manual_seed(21)
+    sp = Spynet().eval()
+    clip = torch.rand(7, 3, 256, 256, generator=torch.Generator().manual_seed(2024))
+    with torch.no_grad():
+        fb = sp(clip[:-1], clip[1:])          # basicvsr.py:35 (backward flows)
+        ff = sp(clip[1:], clip[:-1])          # basicvsr.py:36 (forward flows)
+    for nm, f in (("backward", fb), ("forward", ff)):
+        out[f"flow_{nm}_s2"] = f[:, :, 0::2, 1::2].contiguous().numpy()
+        out[f"flow_{nm}_stats"] = np.array([f.double().mean().item(), f.double().std().item(), f.abs().max().item()])
+    out["clip_checksum"] = np.array([clip.double().sum().item()])
+    np.savez_compressed(HERE / "cfg2.npz", **out)
     for f in sorted(HERE.glob("*.npz")):
         print(f.name, f.stat().st_size)
 

@@ -406,3 +406,167 @@ def test_graph_replay_and_pdl_do_not_change_results(dev):
         VF.clear_caches()
     for sr, lq in outs[1:]:
         assert torch.equal(sr, outs[0][0]) and torch.equal(lq, outs[0][1])
+
+
+def test_cfg2_spynet_256(dev, golden):
+    """BASELINE.json configs[1]: SPyNet on a 7-frame 256x256 clip, both pair directions, against flows computed by
+    the reference itself (tests/golden/cfg2.npz): <= 1e-2 px (north_star), in both precision modes."""
+    from vsrlab_b200 import functional as VF, ops
+    g = golden("cfg2")
+    clip = torch.rand(7, 3, 256, 256, generator=torch.Generator().manual_seed(2024))
+    assert abs(clip.double().sum().item() - float(g["clip_checksum"][0])) < 1e-6
+    sp = build_state_dict("spynet").to(dev).eval()
+    clip = clip.to(dev)
+    for mode, tol in (("fp32", 1e-3), ("bf16", 1e-2)):
+        with torch.no_grad(), VF.precision(mode):
+            fb = sp(clip[:-1], clip[1:]).cpu()
+            ff = sp(clip[1:], clip[:-1]).cpu()
+        for nm, f in (("backward", fb), ("forward", ff)):
+            assert f.shape == (6, 2, 256, 256)
+            assert (f[:, :, 0::2, 1::2] - T(g[f"flow_{nm}_s2"])).abs().max().item() <= tol, (mode, nm)
+    assert ops.debug_status() == 0
+
+
+def _oracle_case(blocks, shape, seed):
+    from vsrlab.vsr.models.RealBasicVSR.realbasicvsr import RealBasicVSR
+    torch.manual_seed(seed)
+    net = RealBasicVSR(cleaning_blocks=blocks, mid_channels=64, upscale=4, res_blocks=blocks, pretrained_flow=False,
+                       train_flow=False).eval()
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    x = torch.rand(*shape, generator=torch.Generator().manual_seed(seed + 1))
+    with torch.no_grad():
+        sr_ref, lq_ref = O.realbasicvsr(x.clone(), sd)
+    return net, x, sr_ref, lq_ref
+
+
+def _check_modes(net, x, sr_ref, lq_ref, dev):
+    from vsrlab_b200 import functional as VF, ops
+    with torch.no_grad(), VF.precision("fp32"):
+        xin = x.clone().to(dev)
+        sr, lq = net(xin)
+    assert lq.data_ptr() == xin.data_ptr()
+    e_sr, e_lq = (sr.cpu() - sr_ref).abs().max().item(), (lq.cpu() - lq_ref).abs().max().item()
+    assert e_sr <= 1e-4 and e_lq <= 1e-4, (e_sr, e_lq)                     # north_star fp32 gate
+    with torch.no_grad(), VF.precision("bf16"):
+        sr16, lq16 = net(x.clone().to(dev))
+    hr = torch.rand(sr_ref.shape, generator=torch.Generator().manual_seed(9))
+    d = abs(O.psnr(sr16.cpu().clamp(0, 1), hr) - O.psnr(sr_ref.clamp(0, 1), hr))
+    assert d <= 0.05, d                                                     # north_star bf16 gate
+    assert O.psnr(sr16.cpu(), sr_ref) > 40.0 and O.psnr(lq16.cpu(), lq_ref) > 40.0
+    assert ops.debug_status() == 0
+
+
+@pytest.mark.parametrize("graphs", [False, True], ids=["eager", "graph"])
+def test_multi_chunk_schedule_matches_oracle(dev, graphs):
+    """The benchmark's schedule: several clips, more frames than one cleaner / tail chunk, chunk loops that iterate with
+    a remainder (functional.py CLEAN_CHUNK / TAIL_CHUNK offset slicing), eager and as a replayed CUDA graph."""
+    from vsrlab_b200 import functional as VF
+    net, x, sr_ref, lq_ref = _oracle_case(2, (2, 9, 3, 36, 52), 31)
+    net = net.to(dev)
+    keep = (VF.CLEAN_CHUNK, VF.TAIL_CHUNK, VF.GRAPHS)
+    try:
+        VF.CLEAN_CHUNK, VF.TAIL_CHUNK, VF.GRAPHS = 4, 5, graphs            # 18 frames: 4+4+4+4+2 and 5+5+5+3
+        VF.clear_caches()
+        _check_modes(net, x, sr_ref, lq_ref, dev)
+    finally:
+        VF.CLEAN_CHUNK, VF.TAIL_CHUNK, VF.GRAPHS = keep
+        VF.clear_caches()
+
+
+def test_default_chunks_more_frames_than_a_chunk(dev):
+    """Default chunk sizes (30 / 8) with 2 clips x 17 frames: B = 34 frames -> cleaner chunks 30 + 4, tail 8+8+8+8+2."""
+    net, x, sr_ref, lq_ref = _oracle_case(1, (2, 17, 3, 24, 40), 41)
+    _check_modes(net.to(dev), x, sr_ref, lq_ref, dev)
+
+
+def test_headline_shape_180x320_matches_oracle(dev):
+    """BASELINE cfg3 geometry (180x320 -> 720x1280, 5/5 blocks, experiment=basic) on 3 frames against the CPU oracle:
+    the exact tile plans, the 180 -> 192 SPyNet resize and the CTA-pair kernels of the headline benchmark."""
+    net, x, sr_ref, lq_ref = _oracle_case(5, (1, 3, 3, 180, 320), 51)
+    assert sr_ref.shape == (1, 3, 3, 720, 1280)
+    _check_modes(net.to(dev), x, sr_ref, lq_ref, dev)
+
+
+def test_two_streams_same_shape_do_not_share_graph_buffers(dev):
+    """Two CUDA streams running same-shaped clips through the same model (bench.py --streams 2, or two threads): each
+    stream gets its own captured graph, static buffers and scratch set, so the results equal the sequential ones."""
+    from vsrlab.vsr.models.RealBasicVSR.realbasicvsr import RealBasicVSR
+    from vsrlab_b200 import functional as VF, ops
+    torch.manual_seed(6)
+    model = RealBasicVSR(cleaning_blocks=1, mid_channels=64, upscale=4, res_blocks=1, pretrained_flow=False, train_flow=False)
+    model = model.to(dev).eval()
+    xs = [torch.rand(1, 4, 3, 40, 56, device=dev) for _ in range(2)]
+    keep = VF.GRAPHS
+    try:
+        VF.GRAPHS = True
+        VF.clear_caches()
+        with VF.precision("bf16"), torch.no_grad():
+            want = [tuple(t.clone() for t in model(x.clone())) for x in xs]          # sequential, default stream
+            torch.cuda.synchronize()
+            streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+            for rep in range(3):                                                     # capture, then replays that overlap
+                got = []
+                for st, x in zip(streams, xs):
+                    st.wait_stream(torch.cuda.current_stream(dev))
+                    with torch.cuda.stream(st):
+                        got.append(model(x.clone()))
+                for st in streams:
+                    torch.cuda.current_stream(dev).wait_stream(st)
+                torch.cuda.synchronize()
+                for (sr, lq), (sr0, lq0) in zip(got, want):
+                    assert torch.equal(sr, sr0) and torch.equal(lq, lq0), rep
+        assert len({k[-1] for k in VF._graphs}) >= 2                                 # one capture per calling stream
+        assert ops.debug_status() == 0
+    finally:
+        VF.GRAPHS = keep
+        VF.clear_caches()
+
+
+def test_graph_entries_own_their_workspaces(dev):
+    """A re-capture (weights changed) must release the previous capture's buffers instead of piling up scratch sets."""
+    from vsrlab.vsr.models.RealBasicVSR.realbasicvsr import RealBasicVSR
+    from vsrlab_b200 import functional as VF
+    torch.manual_seed(6)
+    model = RealBasicVSR(cleaning_blocks=1, mid_channels=64, upscale=4, res_blocks=1, pretrained_flow=False, train_flow=False)
+    model = model.to(dev).eval()
+    x = torch.rand(1, 3, 3, 64, 96, device=dev)
+    keep = VF.GRAPHS
+    try:
+        VF.GRAPHS = True
+        VF.clear_caches()
+        mem = []
+        with VF.precision("bf16"), torch.no_grad():
+            for i in range(6):
+                model(x.clone())
+                torch.cuda.synchronize()
+                mem.append(torch.cuda.memory_allocated(dev))
+                with torch.no_grad():
+                    for p in model.parameters():
+                        p.add_(1e-6)                                                 # bumps _version: next call re-captures
+        assert len(VF._graphs) == 1
+        assert not VF._ws                                                            # nothing leaked into the shared scratch table
+        assert max(mem[2:]) <= mem[1] * 1.10 + (8 << 20), mem                        # steady state, no growth per re-capture
+    finally:
+        VF.GRAPHS = keep
+        VF.clear_caches()
+
+
+def test_narrow_sr_output_matches_fp32(dev):
+    """Opt-in `sr` dtypes: uint8 must be exactly what torchvision's save_image stores from the fp32 result
+    (test.py:138-141: mul(255).add(0.5).clamp(0,255).to(uint8)); fp16 is the rounded fp32 value."""
+    from vsrlab.vsr.models.RealBasicVSR.realbasicvsr import RealBasicVSR
+    from vsrlab_b200 import functional as VF, ops
+    torch.manual_seed(6)
+    model = RealBasicVSR(cleaning_blocks=1, mid_channels=64, upscale=4, res_blocks=1, pretrained_flow=False, train_flow=False)
+    model = model.to(dev).eval()
+    x = torch.rand(2, 3, 3, 36, 52, device=dev) * 1.2 - 0.1          # some values leave [0,1]: the clamp matters
+    with VF.precision("bf16"), torch.no_grad():
+        sr32, _ = model(x.clone())
+        with VF.output_dtype("uint8"):
+            sr8, lq8 = model(x.clone())
+        with VF.output_dtype("fp16"):
+            sr16, _ = model(x.clone())
+    assert sr8.dtype == torch.uint8 and sr16.dtype == torch.float16 and lq8.dtype == torch.float32
+    assert torch.equal(sr8, sr32.mul(255).add_(0.5).clamp_(0, 255).to(torch.uint8))
+    assert torch.equal(sr16, sr32.to(torch.float16))
+    assert ops.debug_status() == 0

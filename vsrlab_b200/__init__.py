@@ -4,6 +4,7 @@ BasicVSR hot path of santurini/vsrlab.  The user-facing drop-in lives in the sib
 library (`csrc/`, `include/vsrb200.h`), its ctypes binding and the forward scheduler.
 """
 from ._lib import VsrbError, load  # noqa: F401
-from .functional import clear_caches, current_dtype, precision, set_precision  # noqa: F401
+from .functional import (clear_caches, current_dtype, output_dtype, precision, set_output_dtype,  # noqa: F401
+                         set_precision)
 
-__all__ = ["VsrbError", "load", "set_precision", "precision", "current_dtype", "clear_caches"]
+__all__ = ["VsrbError", "load", "set_precision", "precision", "current_dtype", "clear_caches", "set_output_dtype", "output_dtype"]

@@ -18,6 +18,7 @@ ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
 PAD_ZEROS, PAD_BORDER = 0, 1
 EPI_NHWC, EPI_CLEAN, EPI_FLOW, EPI_SR = 0, 1, 2, 3
 CONV_PDL = 1
+CONV_SR_U8, CONV_SR_F16 = 2, 4
 
 
 class ConvGeom(C.Structure):

@@ -332,6 +332,9 @@ def resblock(rb, inputs, segs) -> torch.Tensor:
     weight groups over equal slices of the batch (needs a batched_wgrad scope)."""
     rbs = tuple(rb) if isinstance(rb, (list, tuple)) else (rb,)
     mid = rbs[0].conv[0].out_channels
+    if mid % 16:
+        raise VsrbError(f"training path: mid_channels={mid} must be a multiple of 16 (bf16 NHWC activations are stored in "
+                        "16-channel groups); the inference path pads, the differentiable path does not")
     per_g = [[r.conv[0]] + [c for blk in r.res_block for c in (blk.conv1, blk.conv2)] for r in rbs]
     if _WGRAD_SCOPE is not None and all(c.kernel_size == (3, 3) for cg in per_g for c in cg):
         # fused node; the weights' gradients flow through the convs' tokens (inputs of the node), parked per use

@@ -293,6 +293,7 @@ void fill_epi(const vsrb_conv_args* a, const ConvPlan& p, EpiParams* e) {
         e->split = a->split;
     }
     e->f32_io = a->f32_io; e->f32_in = a->f32_in; e->aux_h = a->aux_h; e->aux_w = a->aux_w;
+    e->sr_kind = (a->flags & VSRB_CONV_SR_U8) ? 2 : ((a->flags & VSRB_CONV_SR_F16) ? 1 : 0);
     e->bias = reinterpret_cast<const float*>(a->packed);
 }
 

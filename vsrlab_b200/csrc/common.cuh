@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -100,6 +101,7 @@ struct EpiParams {
     float* f32_io;
     const float* f32_in;
     int aux_h, aux_w;
+    int sr_kind;          // EPI_SR output element: 0 fp32, 1 fp16, 2 uint8 = floor(clamp(v,0,1)*255 + 0.5) (VSRB_CONV_SR_*)
     const float* bias;    // [groups][cout_pad], packed channel order
 };
 
@@ -215,9 +217,20 @@ __device__ __forceinline__ void epi_sr_up(const EpiParams& e, int b, int y, int 
 template <int N>
 __device__ __forceinline__ void epi_sr_store(const EpiParams& e, int b, int y, int x, const float (&v)[N], const float (&up)[3]) {
     const size_t oplane = (size_t)e.H * e.W;
-    float* op = e.f32_io + (size_t)b * 3 * oplane + (size_t)y * e.W + x;
+    const size_t o = (size_t)b * 3 * oplane + (size_t)y * e.W + x;
+    if (e.sr_kind == 0) {
+        float* op = e.f32_io + o;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) op[c * oplane] = v[c] + up[c];
+        for (int c = 0; c < 3; ++c) op[c * oplane] = v[c] + up[c];
+    } else if (e.sr_kind == 1) {
+        __half* op = reinterpret_cast<__half*>(e.f32_io) + o;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) op[c * oplane] = __float2half_rn(v[c] + up[c]);
+    } else {   // what torchvision.utils.save_image stores (test.py:138-141): mul(255).add(0.5).clamp(0,255).to(uint8)
+        uint8_t* op = reinterpret_cast<uint8_t*>(e.f32_io) + o;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) op[c * oplane] = (uint8_t)fminf(fmaxf(__fadd_rn(__fmul_rn(v[c] + up[c], 255.f), 0.5f), 0.f), 255.f);   // two roundings, like torch
+    }
 }
 
 // EPI_CLEAN / EPI_FLOW in two halves as well: the fp32 value the conv result is added to ...

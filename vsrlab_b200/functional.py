@@ -36,6 +36,31 @@ CLEAN_CHUNK = int(os.environ.get("VSRB_CLEAN_CHUNK", "30"))
 TAIL_CHUNK = int(os.environ.get("VSRB_TAIL_CHUNK", "8"))
 
 
+# Opt-in narrow `sr` output (default None = fp32, the reference's dtype).  "fp16" halves and "uint8" quarters the bytes a
+# caller moves to the host; "uint8" holds exactly what the reference's PNG dump stores (test.py:138-141 ->
+# torchvision save_image: mul(255).add(0.5).clamp(0,255).to(uint8)), computed from the fp32 result inside the last conv.
+_OUT_DTYPES = {None: (torch.float32, 0), "fp32": (torch.float32, 0), "fp16": (torch.float16, 4), "uint8": (torch.uint8, 2)}
+_out_dtype: Optional[str] = None
+
+
+def set_output_dtype(kind: Optional[str]) -> None:
+    """None / 'fp32' (default), 'fp16' or 'uint8' for the `sr` tensor of the no_grad forward."""
+    global _out_dtype
+    if kind not in _OUT_DTYPES:
+        raise ValueError(f"output dtype {kind!r}: choose from None, 'fp32', 'fp16', 'uint8'")
+    _out_dtype = None if kind == "fp32" else kind
+
+
+@contextlib.contextmanager
+def output_dtype(kind: Optional[str]):
+    old = _out_dtype
+    set_output_dtype(kind)
+    try:
+        yield
+    finally:
+        set_output_dtype(old)
+
+
 def set_precision(mode: Optional[str]) -> None:
     """Force 'bf16' / 'fp32', or None to follow autocast."""
     global _forced
@@ -67,6 +92,7 @@ def current_dtype() -> int:
 # --------------------------------------------------------------------------------------
 _packed: Dict[tuple, ops.PackedConv] = {}
 _ws: Dict[tuple, torch.Tensor] = {}
+_ws_private: List[Dict[tuple, torch.Tensor]] = []      # innermost private scratch set (owned by a CUDA-graph entry)
 _consts: Dict[tuple, object] = {}
 
 
@@ -90,13 +116,26 @@ def ws(name: str, shape: Sequence[int], dtype: torch.dtype, device) -> torch.Ten
     n = 1
     for s in shape:
         n *= int(s)
-    # per stream: two clips processed on two streams must not share scratch memory
-    key = (name, dtype, str(device), torch.cuda.current_stream(device).cuda_stream)
-    t = _ws.get(key)
+    if _ws_private:
+        # warm-up / capture of a CUDA graph: the scratch set belongs to that graph entry and dies with it
+        table, key = _ws_private[-1], (name, dtype, str(device))
+    else:
+        # eager launches, per stream: two clips processed on two streams must not share scratch memory
+        table, key = _ws, (name, dtype, str(device), torch.cuda.current_stream(device).cuda_stream)
+    t = table.get(key)
     if t is None or t.numel() < n:
         t = torch.empty(max(n, 1), dtype=dtype, device=device)
-        _ws[key] = t
+        table[key] = t
     return t[:n].view(*shape)
+
+
+@contextlib.contextmanager
+def _private_workspaces(table: Dict[tuple, torch.Tensor]):
+    _ws_private.append(table)
+    try:
+        yield table
+    finally:
+        _ws_private.pop()
 
 
 def clear_caches() -> None:
@@ -113,9 +152,34 @@ def _check_input(x: torch.Tensor, what: str) -> torch.Tensor:
     return x
 
 
-def _wants_grad(mod: torch.nn.Module) -> bool:
-    """True when the call must be recorded for autograd (training step): grad mode on and something to train."""
-    return torch.is_grad_enabled() and any(p.requires_grad for p in mod.parameters())
+def _wants_grad(mod, *tensors) -> bool:
+    """True when the call must be recorded for autograd: grad mode on and something to differentiate - a trainable
+    parameter of `mod` (a module, a sequence of modules, or None) or an input that requires grad.  Every module-level
+    entry point checks this and routes to `autograd.py`; the raw kernels below never return a tensor that silently lost
+    its graph (the reference modules are plain differentiable nn.Modules)."""
+    if not torch.is_grad_enabled():
+        return False
+    if any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors):
+        return True
+    mods = [] if mod is None else (list(mod) if isinstance(mod, (list, tuple)) else [mod])
+    return any(p.requires_grad for m in mods for p in m.parameters())
+
+
+_warned_bf16_training = False
+
+
+def _autograd():
+    """The differentiable path (autograd.py).  It computes in bf16 with fp32 accumulation whatever the precision mode:
+    warn once when the caller asked for fp32 (no autocast, `set_precision('fp32')`), instead of silently degrading."""
+    global _warned_bf16_training
+    if current_dtype() != BF16 and not _warned_bf16_training:
+        import warnings
+        _warned_bf16_training = True
+        warnings.warn("vsrlab_b200: the differentiable (training) path runs bf16 activations with fp32 accumulation; "
+                      "fp32 precision was requested (no autocast / set_precision('fp32')) and applies to no_grad calls only. "
+                      "Wrap evaluation in torch.no_grad() for fp32-accurate outputs.", RuntimeWarning, stacklevel=3)
+    from . import autograd as AG
+    return AG
 
 
 def _act_c(c: int, dt: int) -> int:
@@ -148,6 +212,11 @@ _ACTS = {"none": ACT_NONE, "relu": ACT_RELU, "lrelu": ACT_LRELU}
 def conv2d(x: torch.Tensor, conv: torch.nn.Conv2d, act: str = "none", slope: float = 0.1, pixel_shuffle: int = 0) -> torch.Tensor:
     """act(conv(x)) [+ PixelShuffle]: ConvReLU (conv.py:21), PixelShufflePack (upsampling.py:10-12)."""
     x = _check_input(x, "input")
+    if _wants_grad(conv, x):
+        AG = _autograd()
+        r = pixel_shuffle or 1
+        y = AG.conv(conv, [AG.to_cl16(x)], [(0, x.shape[1])], act, slope, pixel_shuffle)
+        return y[:, :conv.out_channels // (r * r)].float().contiguous()
     dt = current_dtype()
     n, c, h, w = x.shape
     xin, ca = _to_nhwc(x, dt, "m_in")
@@ -163,6 +232,12 @@ def conv2d(x: torch.Tensor, conv: torch.nn.Conv2d, act: str = "none", slope: flo
 def conv_chain(x: torch.Tensor, convs: Sequence[torch.nn.Conv2d], act: str = "relu") -> torch.Tensor:
     """act(conv(...act(conv(x)))) - SpynetModule (spynet.py:13-21)."""
     x = _check_input(x, "input")
+    if _wants_grad(list(convs), x):
+        AG = _autograd()
+        y = AG.to_cl16(x)
+        for conv in convs:
+            y = AG.conv(conv, [y], [(0, conv.in_channels)], act)
+        return y[:, :convs[-1].out_channels].float().contiguous()
     dt = current_dtype()
     n, c, h, w = x.shape
     cur, ca = _to_nhwc(x, dt, "m_in")
@@ -214,9 +289,18 @@ def _run_resblocks(cur, ca, stem_pc, block_pcs, n, h, w, mid_c, dt, device, tag,
 def residual_stack(x: torch.Tensor, stem: Optional[torch.nn.Conv2d], blocks: Sequence[torch.nn.Module]) -> torch.Tensor:
     """ResidualBlock / ResidualConv forward (conv.py:89-92, 101-103)."""
     x = _check_input(x, "input")
+    mid = stem.out_channels if stem is not None else blocks[0].conv1.out_channels
+    if _wants_grad(([stem] if stem is not None else []) + [cv for b in blocks for cv in (b.conv1, b.conv2)], x):
+        AG = _autograd()
+        y = AG.to_cl16(x)
+        if stem is not None:
+            y = AG.conv(stem, [y], [(0, x.shape[1])], "lrelu")
+        for b in blocks:
+            t = AG.conv(b.conv1, [y], [(0, mid)], "relu")
+            y = AG.conv(b.conv2, [t], [(0, mid)], "none", residual=y)
+        return y[:, :mid].float().contiguous()
     dt = current_dtype()
     n, c, h, w = x.shape
-    mid = stem.out_channels if stem is not None else blocks[0].conv1.out_channels
     mid_c = _act_c(mid, dt)
     cur, ca = _to_nhwc(x, dt, "m_in", None if stem is not None else mid_c)
     stem_pc = packed([stem], [(0, c)], dt) if stem is not None else None
@@ -229,8 +313,16 @@ def flow_warp(x: torch.Tensor, flow: torch.Tensor, padding_mode: str = "zeros") 
     """flow_warp(x [T,c,h,w], flow [T,h,w,2]) (spynet.py:95-106)."""
     x = _check_input(x, "input")
     flow = _check_input(flow, "flow").contiguous()
-    dt = current_dtype()
     n, c, h, w = x.shape
+    if _wants_grad(None, x, flow):
+        # differentiable in the features and in the flow (fp32 data: a loss may sit right on top of it)
+        AG = _autograd()
+        nv = 1
+        while nv * 4 < c:
+            nv *= 2
+        xp = torch.nn.functional.pad(x, (0, 0, 0, 0, 0, nv * 4 - c)).contiguous(memory_format=torch.channels_last)
+        return AG.WarpFn.apply(xp, flow, padding_mode == "border")[:, :c].contiguous()
+    dt = current_dtype()
     if dt == BF16X2:
         ca = _act_c(c, dt)
     else:
@@ -310,6 +402,10 @@ def spynet_flow(sp, ref: torch.Tensor, supp: torch.Tensor, resize: bool = True) 
     """Spynet.forward / compute_flow: [T,3,h,w] x2 -> [T,2,h,w] (spynet.py:38-93)."""
     ref = _check_input(ref, "ref")
     supp = _check_input(supp, "supp")
+    if _wants_grad(sp, ref, supp):
+        if not resize and (ref.shape[-2] % 32 or ref.shape[-1] % 32):
+            raise VsrbError("Spynet.compute_flow needs sides that are multiples of 32 (reference spynet.py:49)")
+        return _autograd().spynet(sp, ref, supp)
     t = ref.shape[0]
     frames = torch.cat([ref, supp], 0).contiguous()
     idx = torch.arange(2 * t, dtype=torch.int32, device=ref.device)
@@ -335,6 +431,10 @@ def basicvsr_flows(bv, lrs: torch.Tensor):
     """BasicVSR.compute_flow: (flow_forward, flow_backward), each [n*(t-1),2,h,w] (basicvsr.py:30-37)."""
     lrs = _check_input(lrs, "lrs")
     n, t, c, h, w = lrs.shape
+    if _wants_grad(bv.spynet, lrs):
+        a, b = lrs[:, :-1].reshape(-1, c, h, w), lrs[:, 1:].reshape(-1, c, h, w)
+        AG = _autograd()
+        return AG.spynet(bv.spynet, b, a), AG.spynet(bv.spynet, a, b)        # (forward, backward): basicvsr.py:35-37
     ref, supp = _pair_indices(n, t, lrs.device)
     flows = _spynet_run(bv.spynet, lrs.contiguous().view(n * t, c, h, w), ref, supp, current_dtype())
     m = n * (t - 1)
@@ -376,6 +476,14 @@ def cleaner_forward(cl, x: torch.Tensor) -> torch.Tensor:
     if not x.is_contiguous():
         raise RuntimeError("IterativeRefinement works in place on a view of its input; pass a contiguous tensor")
     n, t, c, h, w = x.shape
+    if _wants_grad(cl, x):
+        AG = _autograd()
+        with AG.batched_wgrad():
+            y = AG.cleaner(cl, x.reshape(n * t, c, h, w)).view(n, t, c, h, w)
+        if not x.requires_grad:                  # what the reference's in-place refinement leaves in the caller's tensor
+            with torch.no_grad():
+                x.copy_(y)
+        return y
     _cleaner_run(cl, x.view(n * t, c, h, w), current_dtype())
     return x
 
@@ -436,7 +544,8 @@ def _basicvsr_run(bv, lrs: torch.Tensor, dt: int, x_nhwc: Optional[torch.Tensor]
     n_up = len(bv.upsample)
     scale = 2 ** n_up
     H, W = h * scale, w * scale
-    sr = torch.empty(n, t, 3, H, W, dtype=torch.float32, device=dev)
+    sr_dtype, sr_flag = _OUT_DTYPES[_out_dtype]
+    sr = torch.empty(n, t, 3, H, W, dtype=sr_dtype, device=dev)
     sr_flat = sr.view(n * t, 3, H, W)
     point = packed([bv.point_conv[0]], [(0, mid), (mid, mid)], dt)
     ups = [packed([u.upconv], [(0, mid)], dt, 2) for u in bv.upsample]
@@ -459,13 +568,13 @@ def _basicvsr_run(bv, lrs: torch.Tensor, dt: int, x_nhwc: Optional[torch.Tensor]
         hr = ws("tl_h", (nb, H, W, c_last), tdt, dev)
         ops.conv2d_fwd(cl0, [cur], [mid_c], nb, H, W, act=ACT_LRELU, slope=0.1, out=hr, out_c=c_last)
         ops.conv2d_fwd(cl2, [hr], [c_last], nb, H, W, act=ACT_NONE, epilogue=EPI_SR, f32_io=sr_flat[b0:b0 + nb],
-                       f32_in=x_flat[b0:b0 + nb], aux_hw=(h, w))
+                       f32_in=x_flat[b0:b0 + nb], aux_hw=(h, w), extra_flags=sr_flag)
     return sr
 
 
 def basicvsr_forward(bv, lrs: torch.Tensor) -> torch.Tensor:
-    if _wants_grad(bv):
-        from . import autograd as AG
+    if _wants_grad(bv, lrs):
+        AG = _autograd()
         ops.require_cuda(lrs, "lrs")
         with AG.batched_wgrad():
             return AG.basicvsr(bv, lrs.float())
@@ -476,9 +585,8 @@ def basicvsr_forward(bv, lrs: torch.Tensor) -> torch.Tensor:
 def realbasicvsr_forward(model, lr: torch.Tensor):
     """(sr, lq) = RealBasicVSR.forward; `lq` is `lr` itself, refined in place (realbasicvsr.py:11-15, 26-29)."""
     ops.require_cuda(lr, "lr")
-    if _wants_grad(model):
-        from . import autograd as AG
-        return AG.realbasicvsr(model, lr)
+    if _wants_grad(model, lr):
+        return _autograd().realbasicvsr(model, lr)
     if lr.dtype != torch.float32:
         raise VsrbError("RealBasicVSR refines its input in place and needs an fp32 tensor (reference realbasicvsr.py:29)")
     if not lr.is_contiguous():
@@ -496,8 +604,12 @@ def realbasicvsr_forward(model, lr: torch.Tensor):
 # CUDA-graph replay of the whole forward (several hundred dependent launches per call)
 # --------------------------------------------------------------------------------------
 GRAPHS = os.environ.get("VSRB_GRAPHS", "1") == "1"      # VSRB_GRAPHS=0: launch every kernel eagerly
-MAX_GRAPHS = 4                                          # captured (model, shape, precision) combinations kept alive
-_graphs: Dict[tuple, tuple] = {}
+MAX_GRAPHS = 4                                          # captured (model, shape, precision, stream) combinations kept alive
+# Opt-in: return the graph's static `sr` buffer itself instead of a copy (saves a 663 MB device copy per cfg3 step).
+# The tensor is then only valid until the next call with the same model / shape / stream.
+GRAPH_OUTPUT_VIEW = os.environ.get("VSRB_GRAPH_OUTPUT_VIEW", "0") == "1"
+_graphs: Dict[tuple, "_GraphEntry"] = {}
+_capture_streams: Dict[str, torch.cuda.Stream] = {}     # one long-lived capture stream per device
 # kernels of libvsrb200.so launched through graph replays (vsrb_launch_count only sees direct launches; a replay
 # launches every kernel node recorded at capture time)
 _replayed_launches = 0
@@ -511,38 +623,69 @@ def _weights_stamp(model) -> tuple:
     return tuple((p.data_ptr(), p._version) for p in model.parameters())
 
 
+class _GraphEntry:
+    """One captured forward.  It owns everything the graph's kernels touch: the static input / output and the private
+    scratch set (`workspaces`), so dropping the entry (eviction, re-capture after a weight update) frees them, and no
+    other capture or eager call can grow / free a buffer whose address is baked into this graph."""
+    __slots__ = ("stamp", "graph", "static_in", "static_sr", "model", "n_kernels", "workspaces")
+
+
+def _capture_stream(device) -> torch.cuda.Stream:
+    st = _capture_streams.get(str(device))
+    if st is None:
+        st = _capture_streams[str(device)] = torch.cuda.Stream(device=device)
+    return st
+
+
+def _evict_graphs(keep_free_fraction: float = 0.25, device=None) -> None:
+    """Oldest-first eviction: at most MAX_GRAPHS captures, and none of the old ones once the device runs short of memory
+    (a capture of cfg3 pins several GB of workspaces; test.py's ragged last window is a second shape per video)."""
+    while len(_graphs) >= MAX_GRAPHS:
+        _graphs.pop(next(iter(_graphs)))
+    if device is not None and _graphs:
+        free, total = torch.cuda.mem_get_info(device)
+        if free < keep_free_fraction * total:
+            _graphs.clear()
+            torch.cuda.empty_cache()
+
+
 def _graphed_forward(model, lr: torch.Tensor, dt: int):
-    """Capture `cleaner + BasicVSR` once per (model weights, shape, precision) and replay it.  The captured graph
-    works on a private input buffer; the caller's `lr` receives the cleaned frames afterwards, so the in-place
-    contract (`lq is lr`, overwritten) is unchanged, and `sr` is copied out of the graph's static output."""
-    key = (id(model), dt, tuple(lr.shape), str(lr.device))
+    """Capture `cleaner + BasicVSR` once per (model weights, shape, precision, calling stream) and replay it.  The captured
+    graph works on a private input buffer; the caller's `lr` receives the cleaned frames afterwards, so the in-place
+    contract (`lq is lr`, overwritten) is unchanged, and `sr` is copied out of the graph's static output.  The calling
+    stream is part of the key: two streams (or threads) running same-shaped clips get a capture each, so they never share
+    the static buffers; within one stream, replays and the copies around them are stream-ordered."""
+    cur = torch.cuda.current_stream(lr.device)
+    key = (id(model), dt, tuple(lr.shape), str(lr.device), _out_dtype, cur.cuda_stream)
     stamp = _weights_stamp(model)
     entry = _graphs.get(key)
-    if entry is None or entry[0] != stamp or entry[4]() is not model:
+    if entry is None or entry.stamp != stamp or entry.model() is not model:
+        _graphs.pop(key, None)                     # a stale capture releases its buffers before the new one allocates
+        entry = None
+        _evict_graphs(device=lr.device)
         n, t, c, h, w = lr.shape
-        static_in = torch.empty_like(lr)
-        side = torch.cuda.Stream(device=lr.device)
-        side.wait_stream(torch.cuda.current_stream(lr.device))
-        with torch.cuda.stream(side):              # warm-up on the capture stream: packs weights, sizes workspaces
-            static_in.copy_(lr)
-            x_nhwc = _cleaner_run(model.cleaner, static_in.view(n * t, c, h, w), dt)
-            _basicvsr_run(model.basicvsr, static_in, dt, x_nhwc)
-        torch.cuda.current_stream(lr.device).wait_stream(side)
-        torch.cuda.synchronize(lr.device)
-        graph = torch.cuda.CUDAGraph()
-        k0 = ops.launch_count()
-        with torch.cuda.graph(graph, stream=side):
-            x_nhwc = _cleaner_run(model.cleaner, static_in.view(n * t, c, h, w), dt)
-            static_sr = _basicvsr_run(model.basicvsr, static_in, dt, x_nhwc)
-        entry = (stamp, graph, static_in, static_sr, weakref.ref(model), ops.launch_count() - k0)
-        _graphs.pop(key, None)
-        while len(_graphs) >= MAX_GRAPHS:          # dicts keep insertion order: drop the oldest capture
-            _graphs.pop(next(iter(_graphs)))
+        entry = _GraphEntry()
+        entry.stamp, entry.model, entry.workspaces = stamp, weakref.ref(model), {}
+        entry.static_in = torch.empty_like(lr)
+        side = _capture_stream(lr.device)
+        side.wait_stream(cur)
+        with _private_workspaces(entry.workspaces):
+            with torch.cuda.stream(side):          # warm-up on the capture stream: packs weights, sizes the workspaces
+                entry.static_in.copy_(lr)
+                x_nhwc = _cleaner_run(model.cleaner, entry.static_in.view(n * t, c, h, w), dt)
+                _basicvsr_run(model.basicvsr, entry.static_in, dt, x_nhwc)
+            cur.wait_stream(side)
+            torch.cuda.synchronize(lr.device)
+            entry.graph = torch.cuda.CUDAGraph()
+            k0 = ops.launch_count()
+            with torch.cuda.graph(entry.graph, stream=side):
+                x_nhwc = _cleaner_run(model.cleaner, entry.static_in.view(n * t, c, h, w), dt)
+                entry.static_sr = _basicvsr_run(model.basicvsr, entry.static_in, dt, x_nhwc)
+            entry.n_kernels = ops.launch_count() - k0
         _graphs[key] = entry
     global _replayed_launches
-    _, graph, static_in, static_sr, _, n_kernels = entry
-    static_in.copy_(lr)
-    graph.replay()
-    _replayed_launches += n_kernels
-    lr.copy_(static_in)
-    return static_sr.clone(), lr
+    entry.static_in.copy_(lr)
+    entry.graph.replay()
+    _replayed_launches += entry.n_kernels
+    lr.copy_(entry.static_in)
+    return (entry.static_sr if GRAPH_OUTPUT_VIEW else entry.static_sr.clone()), lr

@@ -70,6 +70,21 @@ def require_cuda(t: torch.Tensor, what: str) -> None:
         raise L.VsrbError(f"{what} lives on {t.device}: vsrlab_b200 runs on CUDA (sm_100a) only; there is no CPU path")
 
 
+def check_conv_module(c) -> None:
+    """The kernels implement the convolutions of the hot path: stride 1, 'same' zero padding, no dilation, no groups
+    (reference conv.py:19,86-87,98; upsampling.py:7; basicvsr.py:18-21).  Anything else must fail loudly rather than
+    silently compute a different convolution."""
+    if not isinstance(c, torch.nn.Conv2d):
+        return
+    kh, kw = c.kernel_size
+    ok = (tuple(c.stride) == (1, 1) and tuple(c.dilation) == (1, 1) and c.groups == 1 and c.padding_mode == "zeros"
+          and c.padding in ((kh // 2, kw // 2), "same"))
+    if not ok:
+        raise L.VsrbError(f"unsupported Conv2d for the sm_100a kernels: stride={c.stride} padding={c.padding} dilation={c.dilation} "
+                          f"groups={c.groups} padding_mode={c.padding_mode}; the hot path needs stride 1, padding k//2, no dilation, "
+                          "groups 1")
+
+
 class PackedConv:
     """Device image of one convolution's weights (or of `groups` same-shaped convolutions)
     in the layout the kernels consume; see vsrb_pack_conv_weight in include/vsrb200.h."""
@@ -79,6 +94,8 @@ class PackedConv:
         w0 = convs[0].weight
         require_cuda(w0, "conv weight")
         cout, cin, kh, kw = w0.shape
+        for c in convs:
+            check_conv_module(c)
         self.split = dtype == BF16X2
         self.real_segs = tuple(segs)
         w = torch.stack([c.weight.detach().to(torch.float32) for c in convs]).contiguous()
@@ -116,13 +133,16 @@ class PackedConv:
 
     @staticmethod
     def stamp_of(convs) -> tuple:
+        """Identity + version of the parameters a packed image was built from.  In-place updates through `param.data`
+        bypass `_version`: code that writes weights that way must call `functional.clear_caches()` afterwards
+        (optimizers, `load_state_dict` and `.to()` all bump the version or replace the storage)."""
         return tuple((c.weight.data_ptr(), c.weight._version, 0 if c.bias is None else c.bias._version) for c in convs)
 
 
 def conv2d_fwd(pc: PackedConv, ins: Sequence, in_c: Sequence[int], batch: int, h: int, w: int, *,
                imgs_per_group: Optional[int] = None, act: int = ACT_NONE, slope: float = 0.1, epilogue: int = EPI_NHWC,
                out=None, out_c: int = 0, out_img_stride: int = 0, out_group_stride: int = 0, residual=None, res_c: int = 0,
-               f32_io=None, f32_in=None, aux_hw: Tuple[int, int] = (0, 0), max_ctas: int = 0) -> None:
+               f32_io=None, f32_in=None, aux_hw: Tuple[int, int] = (0, 0), max_ctas: int = 0, extra_flags: int = 0) -> None:
     """Enqueue one fused convolution.  `ins`, `out`, `residual`, `f32_io`, `f32_in` are tensors
     (or raw int device addresses) that the caller keeps alive."""
     a = L.ConvArgs()
@@ -155,7 +175,7 @@ def conv2d_fwd(pc: PackedConv, ins: Sequence, in_c: Sequence[int], batch: int, h
     a.f32_in = _p(f32_in)
     a.aux_h, a.aux_w = aux_hw
     a.max_ctas = max_ctas
-    a.flags = L.CONV_PDL if (pc.uses > 0 and PDL) else 0
+    a.flags = (L.CONV_PDL if (pc.uses > 0 and PDL) else 0) | extra_flags
     pc.uses += 1
     if PROFILE is None:                            # the common case: no per-launch bookkeeping
         L.check(L.load().vsrb_conv2d_fwd(C.byref(a), _stream()), "vsrb_conv2d_fwd")
@@ -234,6 +254,8 @@ class PackedConvT(PackedConv):
     def __init__(self, conv, dtype: int):
         lib = L.load()
         convs = list(conv) if isinstance(conv, (list, tuple)) else [conv]
+        for c in convs:
+            check_conv_module(c)
         w0 = convs[0].weight
         require_cuda(w0, "conv weight")
         cout, cin, kh, kw = w0.shape
