@@ -3,8 +3,9 @@ TEST / BASELINE INFRASTRUCTURE ONLY.
 
 /root/reference exists only in the build container.  The reference's Real-BasicVSR path is pure Python on top of
 torch / einops / torchvision, so "building" it means byte-compiling the files the path imports, from
-where they lie under /root/reference/src, into sourceless CPython modules (`*.pyc`, same relative paths) under
-oracle/_ref/src, plus a manifest with the SHA-256 of every source file compiled.  No reference SOURCE is copied anywhere;
+where they lie under /root/reference/src, into CPython bytecode files (`*.bc` = the standard .pyc container, same
+relative paths; the neutral suffix keeps snapshot tools that drop `*.pyc` from dropping them) under oracle/_ref/src,
+plus a manifest with the SHA-256 of every source file compiled.  No reference SOURCE is copied anywhere;
 oracle/_ref/ holds build outputs only, is listed in .gitignore (it never enters this repository's history) but not in
 .gpurunignore, so it rides along to the GPU box like the built .so files (same image, same interpreter).
 `oracle/ref_runner.py` imports the compiled modules under the package name the reference uses for itself (`vsrlab`) in a
@@ -43,7 +44,7 @@ FILES = [
 
 def available() -> bool:
     m = DST.parent / "MANIFEST.json"
-    if not (DST / "vsr/models/RealBasicVSR/realbasicvsr.pyc").exists() or not m.exists():
+    if not (DST / "vsr/models/RealBasicVSR/realbasicvsr.bc").exists() or not m.exists():
         return False
     return json.loads(m.read_text()).get("python") == list(sys.version_info[:2])     # bytecode is interpreter-specific
 
@@ -56,7 +57,7 @@ def build(force: bool = False) -> bool:
         return True
     manifest = {}
     for rel in FILES:
-        src, dst = REF_SRC / rel, (DST / rel).with_suffix(".pyc")
+        src, dst = REF_SRC / rel, (DST / rel).with_suffix(".bc")
         dst.parent.mkdir(parents=True, exist_ok=True)
         py_compile.compile(str(src), cfile=str(dst), dfile=f"<reference>/src/{rel}", doraise=True)
         manifest[rel] = hashlib.sha256(src.read_bytes()).hexdigest()

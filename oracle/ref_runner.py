@@ -9,6 +9,9 @@ prints one JSON line {"frames": F, "seconds": S, "frames_per_s": V, "kind": "ref
 from __future__ import annotations
 
 import argparse
+import importlib
+import importlib.abc
+import importlib.machinery
 import importlib.util
 import json
 import sys
@@ -19,14 +22,30 @@ HERE = Path(__file__).resolve().parent
 SRC = HERE / "_ref" / "src"
 
 
+class _BytecodeFinder(importlib.abc.MetaPathFinder):
+    """Resolves `vsrlab[.sub.module]` to oracle/_ref/src/sub/module.bc (or .../__init__.bc for packages): the files
+    make_ref.py byte-compiled from the reference, loaded with the stock sourceless loader."""
+
+    def find_spec(self, fullname, path=None, target=None):
+        if fullname != "vsrlab" and not fullname.startswith("vsrlab."):
+            return None
+        rel = Path(*fullname.split(".")[1:])
+        pkg, mod = SRC / rel / "__init__.bc", (SRC / rel).with_suffix(".bc")
+        if pkg.exists():
+            loader = importlib.machinery.SourcelessFileLoader(fullname, str(pkg))
+            return importlib.util.spec_from_file_location(fullname, str(pkg), loader=loader, submodule_search_locations=[str(pkg.parent)])
+        if mod.exists():
+            loader = importlib.machinery.SourcelessFileLoader(fullname, str(mod))
+            return importlib.util.spec_from_file_location(fullname, str(mod), loader=loader)
+        return None
+
+
 def load_reference_package():
     """Bind the package name `vsrlab` to oracle/_ref/src (recipe of SURVEY.md §8c)."""
     if any(k == "vsrlab" or k.startswith("vsrlab.") for k in sys.modules):
         raise RuntimeError("the drop-in `vsrlab` package is already imported in this process")
-    spec = importlib.util.spec_from_file_location("vsrlab", str(SRC / "__init__.pyc"), submodule_search_locations=[str(SRC)])
-    m = importlib.util.module_from_spec(spec)
-    sys.modules["vsrlab"] = m
-    spec.loader.exec_module(m)
+    sys.meta_path.insert(0, _BytecodeFinder())
+    importlib.import_module("vsrlab")
 
 
 def build_reference_model(blocks: int, seed: int = 0):

@@ -570,3 +570,82 @@ def test_narrow_sr_output_matches_fp32(dev):
     assert torch.equal(sr8, sr32.mul(255).add_(0.5).clamp_(0, 255).to(torch.uint8))
     assert torch.equal(sr16, sr32.to(torch.float16))
     assert ops.debug_status() == 0
+
+
+RING_CASES = [
+    # n (images per group), h, w, groups, act, residual : the ring-walk kernel (conv_ring.cu) for 3x3 64->64
+    (1, 4, 30, 1, "relu", False),          # fewer rows than lane quarters: empty walks
+    (1, 1, 7, 1, "none", False),           # a single row, one partial strip
+    (3, 37, 52, 1, "none", True),          # ragged strips, ranges that cross strip and image borders, residual
+    (2, 180, 320, 1, "relu", False),       # headline geometry
+    (2, 45, 64, 2, "lrelu", False),        # two weight groups
+    (30, 64, 64, 1, "none", True),         # training patch geometry, many images
+    (5, 23, 61, 1, "relu", False),         # strips = 3 with a 1-pixel last strip
+]
+
+
+@pytest.mark.parametrize("case", RING_CASES, ids=lambda c: f"n{c[0]}_{c[1]}x{c[2]}_g{c[3]}_{c[4]}{'_res' if c[5] else ''}")
+def test_ring_walk_conv_matches_classic_and_oracle(dev, case, monkeypatch):
+    """conv_ring_kernel against the stacked-layout kernel (same bf16 operands, fp32 accumulation in another order) and
+    against the fp32 conv on bf16-rounded operands; padded output strides as the propagation loop uses them."""
+    from vsrlab_b200 import ops
+    from vsrlab_b200._lib import ACT_LRELU, ACT_NONE, ACT_RELU, BF16
+    n, h, w, groups, act, residual = case
+    g = torch.Generator().manual_seed(n * 1000 + h * 10 + w)
+    convs = []
+    for _ in range(groups):
+        cv = torch.nn.Conv2d(64, 64, 3, 1, 1)
+        with torch.no_grad():
+            cv.weight.copy_(torch.randn(cv.weight.shape, generator=g) / 24.0)
+            cv.bias.copy_(torch.randn(cv.bias.shape, generator=g) * 0.1)
+        convs.append(cv)
+    B = n * groups
+    x = torch.randn(B, 64, h, w, generator=g)
+    res = torch.randn(B, 64, h, w, generator=g) if residual else None
+    y = torch.cat([F.conv2d(bf16r(x[i * n:(i + 1) * n]), bf16r(convs[i].weight.detach()), convs[i].bias.detach(), padding=1)
+                   for i in range(groups)])
+    y = {"none": lambda v: v, "relu": O.relu, "lrelu": O.lrelu}[act](y)
+    if residual:
+        y = y + bf16r(res)
+    pc = ops.PackedConv([c.to(dev) for c in convs], [(0, 64)], BF16)
+    xt, _ = to_dev_nhwc(x, BF16, dev)
+    rt = to_dev_nhwc(res, BF16, dev)[0] if residual else None
+    # images of a group sit 2 frames apart and the groups far apart, like frame t of the [2, N, T, h, w, C] feature bank
+    frame = h * w * 64
+    outs = []
+    for ring in (True, False):
+        if ring:
+            monkeypatch.setenv("VSRB_RING_MIN_ROWS", "0")
+            monkeypatch.delenv("VSRB_TC_NO_RING", raising=False)
+        else:
+            monkeypatch.setenv("VSRB_TC_NO_RING", "1")
+        bank = torch.full((groups, n, 2, h, w, 64), 7.0, dtype=torch.bfloat16, device=dev)
+        k0 = ops.launch_count()
+        ops.conv2d_fwd(pc, [xt], [64], B, h, w, act={"none": ACT_NONE, "relu": ACT_RELU, "lrelu": ACT_LRELU}[act], slope=0.1,
+                       out=bank.data_ptr() + frame * 2, out_c=64, out_img_stride=2 * frame, out_group_stride=n * 2 * frame,
+                       residual=rt, res_c=64 if residual else 0)
+        torch.cuda.synchronize()
+        assert ops.debug_status() == 0 and ops.launch_count() > k0
+        assert (bank[:, :, 0].float() == 7.0).all()                  # the other frame of the bank is untouched
+        outs.append(bank[:, :, 1].reshape(B, h, w, 64).float().permute(0, 3, 1, 2).cpu())
+    scale = max(y.abs().max().item(), 1.0)
+    assert (outs[0] - y).abs().max().item() <= 2.0 ** -8 * scale
+    assert (outs[1] - y).abs().max().item() <= 2.0 ** -8 * scale
+    assert (outs[0] - outs[1]).abs().max().item() <= 2.0 ** -7 * scale
+
+
+def test_ring_walk_is_the_default_for_large_launches(dev, monkeypatch):
+    """Without any override a cleaner-sized launch takes conv_ring_kernel."""
+    from vsrlab_b200 import ops
+    from vsrlab_b200._lib import ACT_RELU, BF16
+    monkeypatch.delenv("VSRB_TC_NO_RING", raising=False)
+    monkeypatch.delenv("VSRB_RING_MIN_ROWS", raising=False)
+    cv = torch.nn.Conv2d(64, 64, 3, 1, 1).to(dev)
+    pc = ops.PackedConv([cv], [(0, 64)], BF16)
+    x = torch.randn(8, 180, 320, 64, device=dev).to(torch.bfloat16)
+    out = torch.empty_like(x)
+    ops.conv2d_fwd(pc, [x], [64], 8, 180, 320, act=ACT_RELU, out=out, out_c=64)
+    torch.cuda.synchronize()
+    ref = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), cv.weight.to(torch.bfloat16).float(), cv.bias, padding=1))
+    assert (out.float().permute(0, 3, 1, 2) - ref).abs().max().item() <= 2.0 ** -8 * max(ref.abs().max().item(), 1.0)
+    assert ops.debug_status() == 0

@@ -83,17 +83,21 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--modes", default="0")
     ap.add_argument("--cases", default="all")
+    ap.add_argument("--ring-modes", default="", help="VSRB_RING_DEBUG values to sweep instead of VSRB_TC_DEBUG (conv_ring.cu)")
     a = ap.parse_args()
+    var = "VSRB_RING_DEBUG" if a.ring_modes else "VSRB_TC_DEBUG"
+    if a.ring_modes:
+        a.modes = a.ring_modes
     names = list(CASES) if a.cases == "all" else a.cases.split(",")
     print(f"{'case':18s} " + " ".join(f"{'mode' + m:>22s}" for m in a.modes.split(",")))
     for nm in names:
         row = []
         for m in a.modes.split(","):
-            os.environ["VSRB_TC_DEBUG"] = m
+            os.environ[var] = m
             ms, tf = run_case(nm)
             row.append(f"{ms*1e3:8.1f}us {tf:7.1f}TF/s")
         print(f"{nm:18s} " + " ".join(f"{r:>22s}" for r in row), flush=True)
-    os.environ["VSRB_TC_DEBUG"] = "0"
+    os.environ[var] = "0"
     assert ops.debug_status() == 0
 
 

@@ -132,9 +132,14 @@ int make_plan(const vsrb_conv_geom* g, ConvPlan* p) {
         p->wblock_bytes += (size_t)sp.chunks * kx_stages * p->b_stage_bytes[s];
     }
     p->bias_bytes = round_up((size_t)p->groups * p->cout_pad * sizeof(float), 1024);
-    if (p->dtype == VSRB_BF16)
+    p->ring = p->dtype == VSRB_BF16 && p->kh == 3 && p->kw == 3 && p->n_seg == 1 && g->seg_c[0] == 64 && p->cout == 64 && !p->pixshuf;
+    if (p->dtype == VSRB_BF16) {
         p->total_bytes = p->bias_bytes + (size_t)p->groups * p->n_blocks * p->wblock_bytes;
-    else
+        if (p->ring) {
+            p->ring_off = round_up(p->total_bytes, 1024);
+            p->total_bytes = p->ring_off + (size_t)p->groups * 2 * VSRB_RING_W_BYTES;
+        }
+    } else
         p->total_bytes = p->bias_bytes +
                          (size_t)p->groups * p->kh * p->kw * p->cin_packed * p->cout_pad * sizeof(float);
     return VSRB_OK;
@@ -224,6 +229,30 @@ __global__ void pack_tc_kernel(PackParams pp, const float* __restrict__ w, uint8
     }
 }
 
+// Ring image (conv_ring.cu): [group][cta rank][kx][96 rows][64 ch] bf16, rows swizzled like every K-major SW128 tile.
+// The B operand of the ring walk's MMA is N = 192 = [W(ky=2) | W(ky=1) | W(ky=0)] x 64 output channels; the CTA pair
+// splits it in halves of 96 rows: rank 0 holds [ky2 0-63 | ky1 0-31], rank 1 holds [ky1 32-63 | ky0 0-63].
+__global__ void pack_ring_kernel(PackParams pp, const float* __restrict__ w, uint8_t* __restrict__ out) {
+    const size_t per_rank = VSRB_RING_W_BYTES / 2;        // elements
+    const size_t total = (size_t)pp.groups * 2 * per_rank;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int g = (int)(i / (2 * per_rank));
+        size_t r = i - (size_t)g * 2 * per_rank;
+        const int rank = (int)(r / per_rank);
+        r -= (size_t)rank * per_rank;
+        const int kx = (int)(r / (96 * 64));
+        r -= (size_t)kx * 96 * 64;
+        const int row = (int)(r / 64), k = (int)(r - (size_t)row * 64);
+        const int nrow = rank * 96 + row;                  // row of the N = 192 operand
+        const int ky = 2 - nrow / 64, n = nrow & 63;
+        const float v = VSRB_W_SRC(pp, g, n, pp.seg_off[0] + k, ky, kx);
+        uint32_t off = (uint32_t)row * 128u + (uint32_t)k * 2u;
+        off ^= ((off >> 7) & 7u) << 4;
+        const size_t dst = ((size_t)(g * 2 + rank) * 3 + kx) * (96 * 128) + off;
+        *reinterpret_cast<__nv_bfloat16*>(out + dst) = __float2bfloat16_rn(v);
+    }
+}
+
 // fp32 image: [group][tap][cin_packed][cout_pad]
 __global__ void pack_f32_kernel(PackParams pp, const float* __restrict__ w, float* __restrict__ out) {
     size_t per_g = (size_t)pp.kh * pp.kw * pp.cin_packed * pp.cout_pad;
@@ -269,6 +298,10 @@ int launch_pack(const vsrb_conv_geom* g, const ConvPlan& p, const float* w, int 
         int blocks = (int)((total + 255) / 256);
         if (blocks > 4096) blocks = 4096;
         pack_tc_kernel<<<blocks, 256, 0, s>>>(pp, w, wp);
+        if (p.ring) {
+            VSRB_LAUNCH_CHECK();
+            pack_ring_kernel<<<256, 256, 0, s>>>(pp, w, reinterpret_cast<uint8_t*>(packed) + p.ring_off);
+        }
     } else {
         size_t total = (size_t)p.groups * p.kh * p.kw * p.cin_packed * p.cout_pad;
         int blocks = (int)((total + 255) / 256);
@@ -400,6 +433,7 @@ int vsrb_conv2d_fwd(const vsrb_conv_args* a, void* stream) {
         default:
             VSRB_CHECK_ARG(false, "unknown epilogue %d", a->epilogue);
     }
+    if (p.dtype == VSRB_BF16 && ring_eligible(a, p)) return launch_conv_ring(a, p, (cudaStream_t)stream);
     if (p.dtype == VSRB_BF16) return launch_conv_tc(a, p, (cudaStream_t)stream);
     return launch_conv_f32(a, p, (cudaStream_t)stream);
 }

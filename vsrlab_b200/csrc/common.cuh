@@ -77,7 +77,12 @@ struct ConvPlan {
     size_t wblock_bytes;   // packed weights of one (group, n_block)
     size_t bias_bytes;     // groups*cout_pad floats rounded to 1 KiB
     size_t total_bytes;
+    int ring;              // 3x3 64->64 bf16: a second weight image for conv_ring_kernel follows the classic one
+    size_t ring_off;       // its byte offset inside the packed buffer: [group][cta rank][kx][96 rows][128 B]
 };
+
+// conv_ring.cu: per (group, CTA rank) three filter-column tiles of 96 rows x 64 channels (see pack_ring_kernel)
+#define VSRB_RING_W_BYTES (3 * 96 * 128)
 
 int make_plan(const vsrb_conv_geom* g, ConvPlan* p);   // returns VSRB_OK or error
 
@@ -348,6 +353,8 @@ __device__ __forceinline__ void epi_store16(const EpiParams& e, int g, int b, in
 // launchers implemented in the kernel translation units
 int launch_conv_tc(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t s);
 int launch_conv_f32(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t s);
+bool ring_eligible(const vsrb_conv_args* a, const ConvPlan& p);
+int launch_conv_ring(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t s);
 int launch_pack(const vsrb_conv_geom* g, const ConvPlan& p, const float* w, int cin_total, const float* bias,
                 void* packed, cudaStream_t s);
 void fill_epi(const vsrb_conv_args* a, const ConvPlan& p, EpiParams* e);

@@ -721,7 +721,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 static std::mutex g_init_mutex;            // one-time per-process / per-device initialisation (callers may be threads)
 
-static EncodeTiledFn get_encode() {
+EncodeTiledFn get_encode() {
     static EncodeTiledFn fn = nullptr;
     static bool tried = false;
     std::lock_guard<std::mutex> lock(g_init_mutex);
