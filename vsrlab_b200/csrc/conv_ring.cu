@@ -54,7 +54,7 @@ struct RingParams {
     int H, W, strips, ipg;
     int cols;              // ipg * strips column strips per weight group
     int rpc;               // ranges per column strip (aligned split), 0 = linear split of all rows
-    long long rows_g;      // cols * H
+    uint32_t rows_g;       // cols * H
     float act_k;
     int* dbg;
     int debug;             // VSRB_RING_DEBUG bits (timing experiments only): 1 no loads, 2 no stores, 4 no MMA, 8 no epilogue math
@@ -64,17 +64,17 @@ struct RingParams {
 // (column, input row y): for every stretch of output rows [ya, yb) inside one column the input rows ya-1 .. yb.
 // An item's own row is an output row of this quarter iff ya <= y < yb.
 struct RingWalk {
-    long long lo, hi;
+    uint32_t lo, hi;
     int H, col, ya, yb, y;
     bool done;
-    __device__ __forceinline__ void init(long long lo_, long long hi_, int H_) {
+    __device__ __forceinline__ void init(uint32_t lo_, uint32_t hi_, int H_) {
         lo = lo_; hi = hi_; H = H_;
         done = lo >= hi;
         if (!done) {
-            col = (int)(lo / H);
-            ya = (int)(lo - (long long)col * H);
-            const long long rest = hi - lo;
-            yb = (rest < (long long)(H - ya)) ? ya + (int)rest : H;
+            col = (int)(lo / (uint32_t)H);
+            ya = (int)(lo - (uint32_t)col * H);
+            const uint32_t rest = hi - lo;
+            yb = (rest < (uint32_t)(H - ya)) ? ya + (int)rest : H;
             y = ya - 1;
         }
     }
@@ -86,30 +86,31 @@ struct RingWalk {
             if (lo >= hi) { done = true; return; }
             ++col;
             ya = 0;
-            const long long rest = hi - lo;
-            yb = rest < (long long)H ? (int)rest : H;
+            const uint32_t rest = hi - lo;
+            yb = rest < (uint32_t)H ? (int)rest : H;
             y = -1;
         }
     }
 };
 
-// rows [lo, hi) of range r (linear index = column * H + row)
-__host__ __device__ __forceinline__ void ring_range(long long rows_g, int H, int cols, int rpc, int n_ranges, int r, long long& lo,
-                                                    long long& hi) {
+// rows [lo, hi) of range r (linear index = column * H + row).  32-bit arithmetic: the launcher only takes this kernel
+// when rows_g * n_ranges < 2^31 (a 64-bit division costs ~100 cycles and every role computes eight of these up front).
+__host__ __device__ __forceinline__ void ring_range(uint32_t rows_g, int H, int cols, int rpc, int n_ranges, int r, uint32_t& lo,
+                                                    uint32_t& hi) {
     if (rpc > 0) {
         const int col = r / rpc, part = r - col * rpc;
         if (col >= cols) { lo = hi = 0; return; }
-        lo = (long long)col * H + (long long)H * part / rpc;
-        hi = (long long)col * H + (long long)H * (part + 1) / rpc;
+        lo = (uint32_t)col * H + (uint32_t)(H * part) / (uint32_t)rpc;
+        hi = (uint32_t)col * H + (uint32_t)(H * (part + 1)) / (uint32_t)rpc;
     } else {
-        lo = rows_g * r / n_ranges;
-        hi = rows_g * (r + 1) / n_ranges;
+        lo = rows_g * (uint32_t)r / (uint32_t)n_ranges;
+        hi = rows_g * (uint32_t)(r + 1) / (uint32_t)n_ranges;
     }
 }
 // number of items (= steps) of range [lo, hi)
-__host__ __device__ __forceinline__ int ring_items(long long lo, long long hi, int H) {
+__host__ __device__ __forceinline__ int ring_items(uint32_t lo, uint32_t hi, int H) {
     if (hi <= lo) return 0;
-    const long long c0 = lo / H, c1 = (hi - 1) / H;
+    const uint32_t c0 = lo / (uint32_t)H, c1 = (hi - 1) / (uint32_t)H;
     return (int)(hi - lo) + 2 * (int)(c1 - c0 + 1);
 }
 
@@ -164,11 +165,12 @@ __global__ void __launch_bounds__(kRingThreads, 1) conv_ring_kernel(const __grid
     const int pair0 = ((int)blockIdx.x & ~1) * 4;                // first range of this CTA pair
     // steps of the pair: the longest of its eight walks
     int S = 0;
-    for (int r = 0; r < 8; ++r) {
-        long long lo, hi;
-        ring_range(P.rows_g, P.H, P.cols, P.rpc, n_ranges, pair0 + r, lo, hi);
-        const int it = ring_items(lo, hi, P.H);
-        S = it > S ? it : S;
+    {
+        uint32_t lo, hi;
+        ring_range(P.rows_g, P.H, P.cols, P.rpc, n_ranges, pair0 + (lane & 7), lo, hi);       // lane r of 8 takes range r
+        S = ring_items(lo, hi, P.H);
+#pragma unroll
+        for (int o = 4; o >= 1; o >>= 1) S = max(S, __shfl_xor_sync(0xffffffffu, S, o));
     }
 
     if (warp == 0 && lane == 0) {
@@ -218,11 +220,14 @@ __global__ void __launch_bounds__(kRingThreads, 1) conv_ring_kernel(const __grid
             // lane q < 4 walks quarter q of this CTA; every lane knows how many of the pair's quarters are active at step t
             int items[8];
             RingWalk wk;
-            for (int r = 0; r < 8; ++r) {
-                long long lo, hi;
-                ring_range(P.rows_g, P.H, P.cols, P.rpc, n_ranges, pair0 + r, lo, hi);
-                items[r] = ring_items(lo, hi, P.H);
-                if (r == (int)crank * 4 + (lane & 3)) wk.init(lo, hi, P.H);
+            {
+                uint32_t lo, hi;
+                ring_range(P.rows_g, P.H, P.cols, P.rpc, n_ranges, pair0 + (lane & 7), lo, hi);
+                const int mine = ring_items(lo, hi, P.H);
+#pragma unroll
+                for (int r = 0; r < 8; ++r) items[r] = __shfl_sync(0xffffffffu, mine, r);
+                const int src = (int)crank * 4 + (lane & 3);                                   // lane q < 4 walks this CTA's quarter q
+                wk.init(__shfl_sync(0xffffffffu, lo, src), __shfl_sync(0xffffffffu, hi, src), P.H);
             }
             const uint32_t full_lead = mapa_rank(full0, 0);
             int slot = 0;
@@ -313,7 +318,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) conv_ring_kernel(const __grid
                 if (((s + 1) & 1) == eh) mbar_arrive_cluster(tempty_lead + 8 * s);
         RingWalk wk;
         {
-            long long lo, hi;
+            uint32_t lo, hi;
             ring_range(P.rows_g, P.H, P.cols, P.rpc, n_ranges, pair0 + (int)crank * 4 + q, lo, hi);
             wk.init(lo, hi, P.H);
         }
@@ -442,17 +447,18 @@ bool ring_eligible(const vsrb_conv_args* a, const ConvPlan& p) {
     if (a->out_img_stride % 8 != 0 || a->out_group_stride % 8 != 0 || a->out_img_stride < 0 || a->out_group_stride < 0) return false;
     if (a->residual && (a->res_c % 8 != 0 || (reinterpret_cast<uintptr_t>(a->residual) & 15) != 0)) return false;
     // small launches do not amortise the two halo rows per range
-    int min_rows = 10;
+    int min_rows = 6;
     if (const char* e = getenv("VSRB_RING_MIN_ROWS")) min_rows = atoi(e);
     const long long rows_g = (long long)a->imgs_per_group * ceil_div(a->w, kRingUW) * a->h;
+    if (rows_g * 4 * 148 >= (1LL << 31)) return false;      // the kernel's range arithmetic is 32-bit
     return rows_g >= (long long)min_rows * 4 * 148 / p.groups;
 }
 
 // steps of the slowest CTA pair for a given split (what the kernel's pairs compute for themselves)
-static int ring_steps(long long rows_g, int H, int cols, int rpc, int n_ranges) {
+static int ring_steps(uint32_t rows_g, int H, int cols, int rpc, int n_ranges) {
     int worst = 0;
     for (int r = 0; r < n_ranges; ++r) {
-        long long lo, hi;
+        uint32_t lo, hi;
         ring_range(rows_g, H, cols, rpc, n_ranges, r, lo, hi);
         const int it = ring_items(lo, hi, H);
         worst = it > worst ? it : worst;
@@ -486,7 +492,7 @@ int launch_conv_ring(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t st
     P.has_res = a->residual != nullptr;
     P.H = a->h; P.W = a->w; P.strips = ceil_div(a->w, kRingUW); P.ipg = a->imgs_per_group;
     P.cols = P.ipg * P.strips;
-    P.rows_g = (long long)P.cols * P.H;
+    P.rows_g = (uint32_t)P.cols * (uint32_t)P.H;
     P.act_k = e.act_k;
     P.dbg = debug_flag();
     {
@@ -534,7 +540,7 @@ int launch_conv_ring(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t st
     int ctas_x = (g_ring_sms[dev] / p.groups) & ~1;
     if (ctas_x < 2) ctas_x = 2;
     {   // never more ranges than rows: empty walks are legal but pointless
-        long long want = (P.rows_g + 3) / 4;
+        long long want = ((long long)P.rows_g + 3) / 4;
         want = (want + 1) & ~1LL;
         if (want < 2) want = 2;
         if ((long long)ctas_x > want) ctas_x = (int)want;
@@ -543,7 +549,7 @@ int launch_conv_ring(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t st
         const int n_ranges = 4 * ctas_x;
         P.rpc = 0;
         const int rpc = n_ranges / P.cols;
-        if (rpc >= 1 && P.rows_g <= (1LL << 20) &&
+        if (rpc >= 1 && P.rows_g <= (1u << 20) &&
             ring_steps(P.rows_g, P.H, P.cols, rpc, n_ranges) < ring_steps(P.rows_g, P.H, P.cols, 0, n_ranges))
             P.rpc = rpc;
     }
