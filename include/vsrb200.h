@@ -210,6 +210,26 @@ int vsrb_spynet_level_input(const float* lvl, const int32_t* ref_idx, const int3
 int vsrb_flow_resize(const float* flow_in, float* flow_out, int32_t P, int32_t Hp, int32_t Wp,
                      int32_t h, int32_t w, void* stream);
 
+/* ---- training objective and evaluation metrics of the callers (next rows of the path) -------
+ * reference: CharbonnierLoss (core/losses.py:10-18), compute_loss (core/utils.py:235-240: the second term compares
+ * lq with kornia `resize(hr, (h, w))` = bilinear, align_corners=False), compute_metric (core/utils.py:242-247) with
+ * piqa.PSNR / piqa.SSIM (conf/train/default.yaml:9-15).  Reductions ACCUMULATE into device doubles the caller zeroes;
+ * nothing is synchronised, no scalar travels to the host.                                                         */
+/* *sum += sum_i sqrt((x_i-y_i)^2 + eps); if grad: grad_i = s * (x_i-y_i)/sqrt(...), s = grad_scale * (*grad_scale_dev
+ * if not NULL): the backward pass passes the upstream gradient as a device scalar and 1/n as grad_scale.          */
+int vsrb_charbonnier(const float* x, const float* y, int64_t n, float eps, double* sum, float* grad,
+                     const float* grad_scale_dev, float grad_scale, void* stream);
+/* the same for lq [planes,h,w] against hr [planes,H,W] resized to (h,w) on the fly; grad is d/d lq                */
+int vsrb_charbonnier_resized(const float* lq, const float* hr, int32_t planes, int32_t h, int32_t w, int32_t H,
+                             int32_t W, float eps, double* sum, float* grad, const float* grad_scale_dev,
+                             float grad_scale, void* stream);
+/* sums[i] += sum over image i of (clamp(x,0,1) - y)^2 (piqa.PSNR on core/utils.py:244's clamped frames)           */
+int vsrb_psnr_sums(const float* x, const float* y, int32_t images, int64_t per_image, double* sums, void* stream);
+/* sums[i] += sum of the SSIM map of image i (x,y [images,channels,h,w]; 11x11 Gaussian window sigma 1.5, 'valid'
+ * borders, k1 0.01, k2 0.03, value range 1 = piqa.SSIM defaults); the map has channels*(h-10)*(w-10) entries      */
+int vsrb_ssim_sums(const float* x, const float* y, int32_t images, int32_t channels, int32_t h, int32_t w,
+                   int32_t clamp_x, double* sums, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -92,6 +92,11 @@ SYMBOLS = {
     "vsrb_avgpool2_c4": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "vsrb_spynet_level_input": (C.c_int, [C.c_void_p] * 6 + [C.c_int32] * 5 + [C.c_void_p]),
     "vsrb_flow_resize": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 5 + [C.c_void_p]),
+    "vsrb_charbonnier": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]),
+    "vsrb_charbonnier_resized": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 5 + [C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                                                       C.c_float, C.c_void_p]),
+    "vsrb_psnr_sums": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
+    "vsrb_ssim_sums": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 5 + [C.c_void_p, C.c_void_p]),
 }
 
 _lib = None
