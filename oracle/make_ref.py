@@ -42,6 +42,46 @@ FILES = [
 ]
 
 
+# The callers of the hot path, for running the reference's own scripts unchanged on top of the drop-in package
+# (tests/test_gpu_scripts.py, tools/run_reference_script.py): the entry scripts and the training runtime they import.
+CALLER_FILES = [
+    "train.py",
+    "test.py",
+    "core/utils.py",
+    "core/losses.py",
+    "core/metrics.py",
+    "core/loggers.py",
+    "vsr/dataset.py",
+    "optical_flow/__init__.py",
+    "optical_flow/models/__init__.py",
+    "optical_flow/models/raft/__init__.py",
+    "optical_flow/models/raft/raft.py",
+    "optical_flow/models/raft/corr.py",
+    "optical_flow/models/raft/extractor.py",
+    "optical_flow/models/raft/update.py",
+    "optical_flow/models/raft/utils.py",
+]
+REF_CONF = Path("/root/reference/conf")
+CONF_DST = HERE / "_ref" / "conf"
+
+
+def build_conf() -> None:
+    """The reference's Hydra config tree as JSON (the `# @package` directive, a YAML comment, is kept as a key): parsed
+    data, not a copy of the files.  The hydra shim of this repository reads .json configs like .yaml ones."""
+    import re
+    import yaml
+    from omegaconf import _Loader            # YAML 1.2 floats (1e-4), like OmegaConf reads them
+    for src in sorted(REF_CONF.rglob("*.yaml")):
+        text = src.read_text()
+        obj = yaml.load(text, Loader=_Loader) or {}
+        m = re.search(r"^\s*#\s*@package\s+(\S+)", "\n".join(text.splitlines()[:5]), re.M)
+        if m:
+            obj = {"__package__": m.group(1), **obj}
+        dst = (CONF_DST / src.relative_to(REF_CONF)).with_suffix(".json")
+        dst.parent.mkdir(parents=True, exist_ok=True)
+        dst.write_text(json.dumps(obj, indent=1))
+
+
 def available() -> bool:
     m = DST.parent / "MANIFEST.json"
     if not (DST / "vsr/models/RealBasicVSR/realbasicvsr.bc").exists() or not m.exists():
@@ -56,7 +96,12 @@ def build(force: bool = False) -> bool:
     if available() and not force:
         return True
     manifest = {}
-    for rel in FILES:
+    sys.path.insert(0, str(HERE.parent / "shims"))
+    try:
+        build_conf()
+    finally:
+        sys.path.pop(0)
+    for rel in FILES + CALLER_FILES:
         src, dst = REF_SRC / rel, (DST / rel).with_suffix(".bc")
         dst.parent.mkdir(parents=True, exist_ok=True)
         py_compile.compile(str(src), cfile=str(dst), dfile=f"<reference>/src/{rel}", doraise=True)

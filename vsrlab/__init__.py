@@ -14,3 +14,9 @@ from pathlib import Path
 # reference src/core/__init__.py:8-14 exports these on import of vsrlab.core;
 # kept so scripts that read them keep working.
 PROJECT_ROOT = Path(os.environ.get("PROJECT_ROOT", Path.cwd().parents[0] if len(Path.cwd().parents) else Path.cwd()))
+
+# The reference's caller modules (training runtime, datasets, losses, scripts' helpers) resolve underneath the drop-in
+# when VSRLAB_REFERENCE_SRC points at a tree with the reference's src/ layout (see _overlay.py).
+if os.environ.get("VSRLAB_REFERENCE_SRC"):
+    from ._overlay import install as _install_reference_overlay
+    _install_reference_overlay(os.environ["VSRLAB_REFERENCE_SRC"])
