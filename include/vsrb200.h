@@ -120,6 +120,24 @@ typedef struct vsrb_conv_args {
     int32_t      flags;       /* VSRB_CONV_* bits                                                */
     int32_t      split;       /* 1: `out`, `residual` (and the EPI_CLEAN frame) are split-bf16: per pixel
                                  [hi C | lo C] with C = out_c/2, value = hi + lo                  */
+    /* Optional fast operand for a 3-channel 3x3 segment (the image stems 3 -> 64 and 64+3 -> 64: conv.py:97-98 behind
+     * realbasicvsr.py:21 and basicvsr.py:56,71): the frames as 3x3 im2col patches, bf16 [.,h,w,32] written by
+     * vsrb_im2col3x3_c3.  When given (and the launch is large enough) the ring-walk kernel multiplies the whole
+     * 27-tap neighbourhood as ONE K = 32 chunk instead of nine K = 16 chunks of mostly padding.  Image li of weight
+     * group g starts at patch + g * patch_group_stride + li * patch_img_stride (elements; strides may be negative:
+     * the two propagation directions walk the clip in opposite orders; both 0 = dense).  in[] of that segment must
+     * still be valid (launches the ring-walk kernel does not take use it).                                        */
+    const void*  patch;
+    int64_t      patch_img_stride, patch_group_stride;
+    /* Optional fused backward warp of the 64-channel segment (north_star part 2; basicvsr.py:52-58,66-73 =
+     * flow_warp -> cat -> stem conv): when `warp_flow` is given, in[] of the 64-channel segment is the UNWARPED feature
+     * map of the previous time step and the kernel samples it (bilinear, zeros padding, spynet.py:95-106) while it
+     * builds the conv's operand rows, so the warped tensor never exists in memory.  fp32 [.,h,w,2]; image li of group
+     * g: warp_flow + g * warp_flow_group_stride + li * warp_flow_img_stride (float2 elements);
+     * the feature map likewise through in_img_stride / in_group_stride (elements, 0 = dense).               */
+    const float* warp_flow;
+    int64_t      warp_flow_img_stride, warp_flow_group_stride;
+    int64_t      in_img_stride, in_group_stride;
 } vsrb_conv_args;
 
 /* ---- library ------------------------------------------------------------------------- */
@@ -185,6 +203,9 @@ int vsrb_nchw_to_nhwc(const float* src, void* dst, int32_t n, int32_t c, int32_t
                       int32_t c_dst, int32_t dtype, void* stream);   /* channels >= c are zeroed */
 int vsrb_nhwc_to_nchw(const void* src, float* dst, int32_t n, int32_t c, int32_t h, int32_t w,
                       int32_t c_src, int32_t dtype, void* stream);
+/* 3x3 im2col of 3-channel fp32 NCHW frames [n,3,h,w] -> bf16 [n,h,w,32]: element (ky*3+kx)*3 + c of pixel (y,x) is
+ * frame[c, y+ky-1, x+kx-1] (zero outside the image), elements 27..31 are zero.  Feeds vsrb_conv_args.patch.        */
+int vsrb_im2col3x3_c3(const float* frames, void* patches, int32_t n, int32_t h, int32_t w, void* stream);
 /* inverse of nn.PixelShuffle(2) (upsampling.py:10-12) on bf16 NHWC, for the backward pass of the upsampling convs:
  * src [n, 2h, 2w, c] -> dst [n, h, w, 4c] with dst channel 4*cc + 2*i + j = src pixel (2y+i, 2x+j), channel cc */
 int vsrb_pixel_unshuffle2(const void* src, void* dst, int32_t n, int32_t h, int32_t w, int32_t c, void* stream);

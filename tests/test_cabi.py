@@ -40,8 +40,9 @@ def test_version_and_geometry_helpers_run_on_cpu(lib):
     g.cout = 64
     g.groups = 1
     g.dtype = _lib.BF16
-    # bias header + classic image (9 taps x 64 x 64 bf16) + the ring-walk image: 2 CTA ranks x 3 filter columns x 96 rows x 128 B
-    assert lib.vsrb_packed_weight_bytes(C.byref(g)) == 1024 + 9 * 64 * 64 * 2 + 2 * 3 * 96 * 128
+    # bias header + classic image (9 taps x 64 x 64 bf16) + the ring-walk image: 2 CTA ranks x (3 filter columns x 96 rows x 128 B
+    # + the 32 x 64 B im2col tile of a 3-channel segment)
+    assert lib.vsrb_packed_weight_bytes(C.byref(g)) == 1024 + 9 * 64 * 64 * 2 + 2 * (3 * 96 * 128 + 32 * 64)
     g.dtype = _lib.F32
     assert lib.vsrb_packed_weight_bytes(C.byref(g)) == 1024 + 9 * 64 * 64 * 4
     g.kh = 4                                            # even kernels are rejected with a message, not a crash

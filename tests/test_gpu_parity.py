@@ -649,3 +649,65 @@ def test_ring_walk_is_the_default_for_large_launches(dev, monkeypatch):
     ref = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), cv.weight.to(torch.bfloat16).float(), cv.bias, padding=1))
     assert (out.float().permute(0, 3, 1, 2) - ref).abs().max().item() <= 2.0 ** -8 * max(ref.abs().max().item(), 1.0)
     assert ops.debug_status() == 0
+
+
+STEM_CASES = [
+    # n per group, h, w, groups, with 64-channel segment : image stems through the ring-walk kernel's K = 32 im2col operand
+    (2, 37, 52, 1, False),       # cleaner stem 3 -> 64 (conv.py:97-98 behind realbasicvsr.py:21), ragged
+    (30, 45, 80, 1, False),
+    (2, 180, 320, 2, True),      # propagation stem cat([lr_i, feat]) -> 64 (basicvsr.py:56-58,71-73), both directions
+    (3, 23, 61, 2, True),
+    (1, 16, 16, 2, True),
+]
+
+
+@pytest.mark.parametrize("case", STEM_CASES, ids=lambda c: f"n{c[0]}_{c[1]}x{c[2]}_g{c[3]}_{'64+3' if c[4] else '3'}")
+def test_ring_walk_stems_with_im2col_patches(dev, case, monkeypatch):
+    """3 -> 64 and 64+3 -> 64 stems: the 3-channel segment as one K = 32 chunk of 3x3 patches (vsrb_im2col3x3_c3) on the
+    ring-walk kernel, against the classic kernel and the fp32 conv on bf16-rounded operands; frames addressed through
+    image / group strides like the two propagation directions do (group 1 walks the clip backwards)."""
+    from vsrlab_b200 import ops
+    from vsrlab_b200._lib import ACT_LRELU, BF16
+    n, h, w, groups, with_feat = case
+    g = torch.Generator().manual_seed(n * 77 + h + w)
+    cin = 67 if with_feat else 3
+    convs = []
+    for _ in range(groups):
+        cv = torch.nn.Conv2d(cin, 64, 3, 1, 1)
+        with torch.no_grad():
+            cv.weight.copy_(torch.randn(cv.weight.shape, generator=g) / (cin * 9) ** 0.5)
+            cv.bias.copy_(torch.randn(cv.bias.shape, generator=g) * 0.1)
+        convs.append(cv)
+    B = n * groups
+    T = 3                                                     # frames per clip in the patch bank
+    frames = torch.rand(n, T, 3, h, w, generator=g)           # the clip bank the patches are built from
+    sel = [1, 2][:groups] if groups == 2 else [1]             # group 0 reads frame 1, group 1 frame 2 of every clip
+    lr = torch.cat([frames[:, f] for f in sel])               # [B,3,h,w] in launch order
+    feat = torch.randn(B, 64, h, w, generator=g) if with_feat else None
+    x_full = torch.cat([lr, feat], 1) if with_feat else lr    # reference channel order: cat([lr_i, feat])
+    y = torch.cat([F.conv2d(bf16r(x_full[i * n:(i + 1) * n]), bf16r(convs[i].weight.detach()), convs[i].bias.detach(), padding=1)
+                   for i in range(groups)])
+    y = O.lrelu(y)
+    segs = [(3, 64), (0, 3)] if with_feat else [(0, 3)]
+    pc = ops.PackedConv([c.to(dev) for c in convs], segs, BF16)
+    lr_t, _ = to_dev_nhwc(lr, BF16, dev)
+    ins, in_c = ([to_dev_nhwc(feat, BF16, dev)[0], lr_t], [64, 16]) if with_feat else ([lr_t], [16])
+    patches = torch.empty(n * T, h, w, 32, dtype=torch.bfloat16, device=dev)
+    ops.im2col3x3(frames.reshape(n * T, 3, h, w).to(dev).contiguous(), patches, n * T, h, w)
+    pf = h * w * 32
+    outs = []
+    for ring in (True, False):
+        if ring:
+            monkeypatch.setenv("VSRB_RING_MIN_ROWS", "0")
+            monkeypatch.delenv("VSRB_TC_NO_RING", raising=False)
+        else:
+            monkeypatch.setenv("VSRB_TC_NO_RING", "1")
+        out = torch.full((B, h, w, 64), 7.0, dtype=torch.bfloat16, device=dev)
+        ops.conv2d_fwd(pc, ins, in_c, B, h, w, act=ACT_LRELU, slope=0.1, out=out, out_c=64,
+                       patch=patches.data_ptr() + sel[0] * pf * 2, patch_img_stride=T * pf, patch_group_stride=pf)
+        torch.cuda.synchronize()
+        assert ops.debug_status() == 0
+        outs.append(out.float().permute(0, 3, 1, 2).cpu())
+    scale = max(y.abs().max().item(), 1.0)
+    assert (outs[0] - y).abs().max().item() <= 2.0 ** -8 * scale
+    assert (outs[1] - y).abs().max().item() <= 2.0 ** -8 * scale

@@ -58,7 +58,7 @@ def run(script: str, overrides, project: Path, extra_env=None, timeout=None) -> 
     env["PYTHONPATH"] = os.pathsep.join([str(ROOT), str(ROOT / "shims")] + ([env["PYTHONPATH"]] if env.get("PYTHONPATH") else []))
     env["VSRLAB_REFERENCE_SRC"] = str(src)
     env.setdefault("WANDB_MODE", "disabled")
-    env.setdefault("LOGGING_DIR", str(project / "storage"))
+    env["LOGGING_DIR"] = str(project / "storage")      # (an importing parent process may have exported its own: vsrlab.core sets it)
     env.pop("PROJECT_ROOT", None)
     if "MASTER_PORT" not in env:
         s = socket.socket()

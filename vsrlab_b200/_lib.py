@@ -61,6 +61,11 @@ class ConvArgs(C.Structure):
         ("max_ctas", C.c_int32),
         ("flags", C.c_int32),
         ("split", C.c_int32),
+        ("patch", C.c_void_p),
+        ("patch_img_stride", C.c_int64), ("patch_group_stride", C.c_int64),
+        ("warp_flow", C.c_void_p),
+        ("warp_flow_img_stride", C.c_int64), ("warp_flow_group_stride", C.c_int64),
+        ("in_img_stride", C.c_int64), ("in_group_stride", C.c_int64),
     ]
 
 
@@ -72,6 +77,7 @@ SYMBOLS = {
     "vsrb_launch_count": (C.c_int64, []),
     "vsrb_debug_status": (C.c_int, [C.c_void_p]),
     "vsrb_debug_trace": (C.c_int, [C.c_void_p, C.c_int32]),
+    "vsrb_im2col3x3_c3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "vsrb_pixel_unshuffle2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "vsrb_packed_weight_bytes": (C.c_size_t, [C.POINTER(ConvGeom)]),
     "vsrb_pack_conv_weight": (C.c_int, [C.POINTER(ConvGeom), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),

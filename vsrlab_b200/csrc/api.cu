@@ -132,7 +132,17 @@ int make_plan(const vsrb_conv_geom* g, ConvPlan* p) {
         p->wblock_bytes += (size_t)sp.chunks * kx_stages * p->b_stage_bytes[s];
     }
     p->bias_bytes = round_up((size_t)p->groups * p->cout_pad * sizeof(float), 1024);
-    p->ring = p->dtype == VSRB_BF16 && p->kh == 3 && p->kw == 3 && p->n_seg == 1 && g->seg_c[0] == 64 && p->cout == 64 && !p->pixshuf;
+    p->ring = 0;
+    p->ring_main_seg = p->ring_patch_seg = -1;
+    if (p->dtype == VSRB_BF16 && p->kh == 3 && p->kw == 3 && p->cout == 64 && !p->pixshuf && p->n_seg <= 2 && !(g->transpose && p->n_seg > 1)) {
+        bool ok = true;
+        for (int s = 0; s < p->n_seg; ++s) {
+            if (g->seg_c[s] == 64 && p->ring_main_seg < 0) p->ring_main_seg = s;
+            else if (g->seg_c[s] == 3 && p->ring_patch_seg < 0 && !g->transpose) p->ring_patch_seg = s;
+            else ok = false;
+        }
+        if (ok) p->ring = (p->ring_main_seg >= 0 ? 1 : 0) | (p->ring_patch_seg >= 0 ? 2 : 0);
+    }
     if (p->dtype == VSRB_BF16) {
         p->total_bytes = p->bias_bytes + (size_t)p->groups * p->n_blocks * p->wblock_bytes;
         if (p->ring) {
@@ -165,7 +175,7 @@ __host__ __device__ static inline int orig_cout(int np, int cout, int pixshuf) {
 struct PackParams {
     int kh, kw, n_seg, groups, pixshuf;
     int seg_c[4], seg_off[4], seg_ck[4], seg_chunks[4], seg_rowbytes[4], seg_mask[4], seg_bstage[4];
-    int cin_total, cin_packed, cout, cout_pad, n_tile, n_blocks, stacked, transpose;
+    int cin_total, cin_packed, cout, cout_pad, n_tile, n_blocks, stacked, transpose, ring_main_seg, ring_patch_seg;
     size_t wblock_bytes, bias_bytes;
 };
 
@@ -240,16 +250,31 @@ __global__ void pack_ring_kernel(PackParams pp, const float* __restrict__ w, uin
         size_t r = i - (size_t)g * 2 * per_rank;
         const int rank = (int)(r / per_rank);
         r -= (size_t)rank * per_rank;
-        const int kx = (int)(r / (96 * 64));
-        r -= (size_t)kx * 96 * 64;
-        const int row = (int)(r / 64), k = (int)(r - (size_t)row * 64);
-        const int nrow = rank * 96 + row;                  // row of the N = 192 operand
-        const int ky = 2 - nrow / 64, n = nrow & 63;
-        const float v = VSRB_W_SRC(pp, g, n, pp.seg_off[0] + k, ky, kx);
-        uint32_t off = (uint32_t)row * 128u + (uint32_t)k * 2u;
-        off ^= ((off >> 7) & 7u) << 4;
-        const size_t dst = ((size_t)(g * 2 + rank) * 3 + kx) * (96 * 128) + off;
-        *reinterpret_cast<__nv_bfloat16*>(out + dst) = __float2bfloat16_rn(v);
+        const size_t base = (size_t)(g * 2 + rank) * VSRB_RING_W_BYTES;
+        if (r < VSRB_RING_W_MAIN / 2) {
+            const int kx = (int)(r / (96 * 64));
+            r -= (size_t)kx * 96 * 64;
+            const int row = (int)(r / 64), k = (int)(r - (size_t)row * 64);
+            const int nrow = rank * 96 + row;                  // row of the N = 192 operand
+            const int ky = 2 - nrow / 64, n = nrow & 63;
+            const float v = pp.ring_main_seg >= 0 ? VSRB_W_SRC(pp, g, n, pp.seg_off[pp.ring_main_seg] + k, ky, kx) : 0.f;
+            uint32_t off = (uint32_t)row * 128u + (uint32_t)k * 2u;
+            off ^= ((off >> 7) & 7u) << 4;
+            *reinterpret_cast<__nv_bfloat16*>(out + base + (size_t)kx * (96 * 128) + off) = __float2bfloat16_rn(v);
+        } else {
+            // patch tile: row = output channel (this rank's 32), k = (ky*3 + kx)*3 + c of the 3x3x3 neighbourhood (27 used of 32);
+            // 64-byte rows, SW64: 16-byte chunk index ^= (row >> 1) & 3
+            r -= VSRB_RING_W_MAIN / 2;
+            const int row = (int)(r / 32), k = (int)(r - (size_t)row * 32);
+            float v = 0.f;
+            if (pp.ring_patch_seg >= 0 && k < 27) {
+                const int tap = k / 3, c = k - tap * 3;
+                v = VSRB_W_SRC(pp, g, rank * 32 + row, pp.seg_off[pp.ring_patch_seg] + c, tap / 3, tap % 3);
+            }
+            uint32_t off = (uint32_t)row * 64u + (uint32_t)k * 2u;
+            off ^= ((off >> 7) & 3u) << 4;
+            *reinterpret_cast<__nv_bfloat16*>(out + base + VSRB_RING_W_MAIN + off) = __float2bfloat16_rn(v);
+        }
     }
 }
 
@@ -288,6 +313,7 @@ int launch_pack(const vsrb_conv_geom* g, const ConvPlan& p, const float* w, int 
         VSRB_CHECK_ARG(p.seg[i].off + p.seg[i].c <= cin_total, "segment %d exceeds cin_total %d", i, cin_total);
     }
     pp.cin_total = cin_total; pp.cin_packed = p.cin_packed; pp.cout = p.cout; pp.cout_pad = p.cout_pad;
+    pp.ring_main_seg = p.ring_main_seg; pp.ring_patch_seg = p.ring_patch_seg;
     pp.n_tile = p.n_tile; pp.n_blocks = p.n_blocks; pp.stacked = p.stacked; pp.transpose = g->transpose; pp.wblock_bytes = p.wblock_bytes; pp.bias_bytes = p.bias_bytes;
     int nb = p.groups * p.cout_pad;
     pack_bias_kernel<<<ceil_div(nb, 256), 256, 0, s>>>(pp, bias, reinterpret_cast<float*>(packed));
@@ -433,6 +459,7 @@ int vsrb_conv2d_fwd(const vsrb_conv_args* a, void* stream) {
         default:
             VSRB_CHECK_ARG(false, "unknown epilogue %d", a->epilogue);
     }
+    VSRB_CHECK_ARG(!a->warp_flow, "fused warp input is not available for this geometry / launch size");
     if (p.dtype == VSRB_BF16 && ring_eligible(a, p)) return launch_conv_ring(a, p, (cudaStream_t)stream);
     if (p.dtype == VSRB_BF16) return launch_conv_tc(a, p, (cudaStream_t)stream);
     return launch_conv_f32(a, p, (cudaStream_t)stream);

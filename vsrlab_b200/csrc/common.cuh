@@ -77,12 +77,17 @@ struct ConvPlan {
     size_t wblock_bytes;   // packed weights of one (group, n_block)
     size_t bias_bytes;     // groups*cout_pad floats rounded to 1 KiB
     size_t total_bytes;
-    int ring;              // 3x3 64->64 bf16: a second weight image for conv_ring_kernel follows the classic one
-    size_t ring_off;       // its byte offset inside the packed buffer: [group][cta rank][kx][96 rows][128 B]
+    int ring;              // 3x3 bf16 conv to 64 channels that conv_ring_kernel can run: a second weight image follows the
+                           // classic one.  Bit 1: a 64-channel segment (main operand), bit 2: a 3-channel segment (patch operand)
+    int ring_main_seg, ring_patch_seg;
+    size_t ring_off;       // byte offset of the ring image: [group][cta rank]{ [kx][96 rows][128 B] | patch [32 rows][64 B] }
 };
 
-// conv_ring.cu: per (group, CTA rank) three filter-column tiles of 96 rows x 64 channels (see pack_ring_kernel)
-#define VSRB_RING_W_BYTES (3 * 96 * 128)
+// conv_ring.cu: per (group, CTA rank) three filter-column tiles of 96 rows x 64 channels (see pack_ring_kernel), then
+// the K = 32 im2col tile of a 3-channel segment (32 rows x 64 B)
+#define VSRB_RING_W_MAIN (3 * 96 * 128)
+#define VSRB_RING_W_PATCH (32 * 64)
+#define VSRB_RING_W_BYTES (VSRB_RING_W_MAIN + VSRB_RING_W_PATCH)
 
 int make_plan(const vsrb_conv_geom* g, ConvPlan* p);   // returns VSRB_OK or error
 

@@ -36,19 +36,26 @@
 namespace vsrb {
 
 static constexpr int kRingThreads = 384;              // 4 control warps + 8 epilogue warps
-static constexpr int kRingSlots = 8;                  // activation rows in flight
+static constexpr int kRingSlots = 8;                  // activation rows in flight (6 when a patch operand rides along)
 static constexpr int kRingSlotBytes = 17 * 1024;      // 4 quarters x 32 pixels x 128 B + the two rows a kx shift runs over
+static constexpr int kRingPatchBytes = 8 * 1024;      // 4 quarters x 32 pixels x 64 B of 3x3 im2col patches
+static constexpr int kRingSlotsPatch = 6;
 static constexpr int kRingUW = 30;                    // useful output columns of a 32-pixel quarter
 static constexpr int kRingStageBytes = 8 * 4096;      // one staging row (32 pixels x 128 B) per epilogue warp
 static constexpr int kRingCtrl = 1024;
-static constexpr int kRingSmem = kRingCtrl + 1024 + VSRB_RING_W_BYTES + kRingSlots * kRingSlotBytes + kRingStageBytes;
+static constexpr int kRingSlotArea = kRingSlotsPatch * (kRingSlotBytes + kRingPatchBytes) > kRingSlots * kRingSlotBytes
+                                         ? kRingSlotsPatch * (kRingSlotBytes + kRingPatchBytes) : kRingSlots * kRingSlotBytes;
+static constexpr int kRingSmem = kRingCtrl + 1024 + VSRB_RING_W_BYTES + kRingSlotArea + kRingStageBytes;
 static constexpr int kRingAcc = 6;                    // accumulator slots (output rows in flight)
 
 struct RingParams {
     CUtensorMap in_map;    // [C, W, H, B] box {64, 32, 1, 1}
     CUtensorMap res_map;   // residual, same geometry
     CUtensorMap out_map;   // [out_c, W, H, imgs_per_group, groups] box {64, 30, 1, 1, 1}
-    const uint8_t* w;      // ring image: [group][rank][kx][96 rows][128 B]
+    CUtensorMap patch_map[2];   // per weight group: 3x3 im2col patches [32, W, H, imgs_per_group] box {32, 32, 1, 1} (SW64)
+    int has_main, has_patch;    // operands: the 64-channel segment (N = 192 ring MMAs) / the 3-channel segment as K = 32 patches
+    int num_slots, slot_bytes;
+    const uint8_t* w;      // ring image: [group][rank]{[kx][96 rows][128 B] | patch [32 rows][64 B]}
     const float* bias;     // [group][64]
     int has_res;
     int H, W, strips, ipg;
@@ -152,11 +159,12 @@ __global__ void __launch_bounds__(kRingThreads, 1) conv_ring_kernel(const __grid
     // control block: barriers, TMEM base, bias
     const uint32_t full0 = base, empty0 = base + 64, tfull0 = base + 128, tempty0 = base + 176, rbar0 = base + 224, wbar = base + 288,
                    wready = base + 296;
+    const int kSlots = P.num_slots;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + 304);
     float* bias_s = reinterpret_cast<float*>(base_ptr + 512);
     const uint32_t wres = base + kRingCtrl;
     const uint32_t slots0 = wres + VSRB_RING_W_BYTES;
-    const uint32_t stg0 = slots0 + kRingSlots * kRingSlotBytes;
+    const uint32_t stg0 = slots0 + kRingSlotArea;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = blockIdx.y;
@@ -174,12 +182,13 @@ __global__ void __launch_bounds__(kRingThreads, 1) conv_ring_kernel(const __grid
     }
 
     if (warp == 0 && lane == 0) {
-        prefetch_tensormap(&P.in_map);
+        if (P.has_main) prefetch_tensormap(&P.in_map);
+        if (P.has_patch) prefetch_tensormap(&P.patch_map[g]);
         prefetch_tensormap(&P.out_map);
         if (P.has_res) prefetch_tensormap(&P.res_map);
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < kRingSlots; ++i) {
+        for (int i = 0; i < kSlots; ++i) {
             mbar_init(full0 + 8 * i, 1);
             mbar_init(empty0 + 8 * i, 1);
         }
@@ -241,16 +250,19 @@ __global__ void __launch_bounds__(kRingThreads, 1) conv_ring_kernel(const __grid
                     int act = 0;
 #pragma unroll
                     for (int r = 0; r < 8; ++r) act += t < items[r] ? 1 : 0;
-                    mbar_expect_tx(full0 + 8 * slot, (uint32_t)act * 4096u);
+                    mbar_expect_tx(full0 + 8 * slot, (uint32_t)act * ((P.has_main ? 4096u : 0u) + (P.has_patch ? 2048u : 0u)));
                 }
                 if (lane < 4 && !wk.done && !(P.debug & 1)) {
                     const int li = wk.col / P.strips, strip = wk.col - li * P.strips;
-                    tma_load_4d_pair(&P.in_map, full_lead + 8 * slot, slots0 + slot * kRingSlotBytes + lane * 4096, 0,
-                                     strip * kRingUW - 1, wk.y, g * P.ipg + li);
+                    const uint32_t sa = slots0 + slot * P.slot_bytes;
+                    if (P.has_main)
+                        tma_load_4d_pair(&P.in_map, full_lead + 8 * slot, sa + lane * 4096, 0, strip * kRingUW - 1, wk.y, g * P.ipg + li);
+                    if (P.has_patch)      // the im2col row of this item's own pixels: no halo column, no kx shift
+                        tma_load_4d_pair(&P.patch_map[g], full_lead + 8 * slot, sa + kRingSlotBytes + lane * 2048, 0, strip * kRingUW, wk.y, li);
                 }
                 wk.next();
                 __syncwarp();
-                if (++slot == kRingSlots) { slot = 0; phase ^= 1; }
+                if (++slot == kSlots) { slot = 0; phase ^= 1; }
             }
         } else if (warp == 1) {
             // =============================== MMA issuer (leader CTA) ====================
@@ -261,8 +273,11 @@ __global__ void __launch_bounds__(kRingThreads, 1) conv_ring_kernel(const __grid
                 mbar_wait(wready, 0, P.dbg, 13, dead);             // both CTAs' weights are resident
                 // instruction descriptor: D=f32, A=B=bf16, K-major both, N = 192 (>>3 @17), M = 256 (>>4 @24) across the pair
                 const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((192u >> 3) << 17) | (16u << 24);
+                const uint32_t idesc_p = (1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | (16u << 24);
                 const uint32_t desc_hi = ((128u * 8u) >> 4) | (1u << 14) | (2u << 29);       // SBO = 8 rows, SW128
+                const uint32_t desc_hi_p = ((64u * 8u) >> 4) | (1u << 14) | (4u << 29);      // 64-byte rows, SW64
                 const uint32_t w_lo = ((wres >> 4) & 0x3FFFu) | (1u << 16);
+                const uint32_t wp_lo = (((wres + VSRB_RING_W_MAIN) >> 4) & 0x3FFFu) | (1u << 16);
                 int slot = 0, b0 = 0, nb = 2;                       // b0 = t mod 6, nb = (t + 2) mod 6
                 uint32_t phase = 0, nb_phase = 0;                   // nb_phase = ((t + 2) / 6) & 1
                 mbar_wait(tempty0 + 0, 0, P.dbg, 14, dead);         // step 0 also touches slots 0 and 1 for the first time
@@ -274,11 +289,20 @@ __global__ void __launch_bounds__(kRingThreads, 1) conv_ring_kernel(const __grid
                     mbar_wait(full0 + 8 * slot, phase, P.dbg, 16, dead);
                     tc_fence_after();
                     if (elect_one()) {
-                        const uint32_t a_lo = (((slots0 + slot * kRingSlotBytes) >> 4) & 0x3FFFu) | (1u << 16);
+                        const uint32_t sa = slots0 + slot * P.slot_bytes;
+                        const uint32_t a_lo = ((sa >> 4) & 0x3FFFu) | (1u << 16);
                         const uint32_t d0 = tmem_base + (uint32_t)b0 * 64u;
+                        if (P.has_patch && !(P.debug & 4)) {
+                            // the 27-tap neighbourhood of this row's own pixels: straight into the block of output row t
+                            const uint32_t ap_lo = (((sa + kRingSlotBytes) >> 4) & 0x3FFFu) | (1u << 16);
+#pragma unroll
+                            for (int k = 0; k < 2; ++k)
+                                umma_bf16_pair(d0 + 64u, ((uint64_t)desc_hi_p << 32) | (ap_lo + k * 2), ((uint64_t)desc_hi_p << 32) | (wp_lo + k * 2),
+                                               idesc_p, 1u);
+                        }
 #pragma unroll
                         for (int kx = 0; kx < 3; ++kx) {
-                            if (P.debug & 4) break;
+                            if ((P.debug & 4) || !P.has_main) break;
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
                                 const uint64_t ad = ((uint64_t)desc_hi << 32) | (a_lo + kx * 8 + k * 2);       // + kx rows of 128 B
@@ -290,7 +314,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) conv_ring_kernel(const __grid
                         umma_commit_pair(tfull0 + 8 * b0);         // ... and output row t-1 is complete
                     }
                     __syncwarp();
-                    if (++slot == kRingSlots) { slot = 0; phase ^= 1; }
+                    if (++slot == kSlots) { slot = 0; phase ^= 1; }
                     if (++b0 == kRingAcc) b0 = 0;
                     if (++nb == kRingAcc) { nb = 0; nb_phase ^= 1; }
                 }
@@ -442,7 +466,13 @@ static int g_ring_sms[64] = {0};
 bool ring_eligible(const vsrb_conv_args* a, const ConvPlan& p) {
     if (!p.ring || getenv("VSRB_TC_NO_RING")) return false;
     if (a->epilogue != VSRB_EPI_NHWC || a->split || a->n_in != 0 || a->max_ctas != 0) return false;
-    if (a->in_c[0] % 8 != 0 || (reinterpret_cast<uintptr_t>(a->in[0]) & 15) != 0) return false;
+    if ((p.ring & 2) && (!a->patch || p.groups > 2 || (reinterpret_cast<uintptr_t>(a->patch) & 15) != 0 || a->patch_img_stride % 8 != 0 ||
+                         a->patch_img_stride < 0 || a->patch_group_stride % 8 != 0))
+        return false;
+    if (p.ring & 1) {
+        const int ms = p.ring_main_seg;
+        if (a->in_c[ms] % 8 != 0 || (reinterpret_cast<uintptr_t>(a->in[ms]) & 15) != 0) return false;
+    }
     if (a->out_c % 8 != 0 || (reinterpret_cast<uintptr_t>(a->out) & 15) != 0) return false;
     if (a->out_img_stride % 8 != 0 || a->out_group_stride % 8 != 0 || a->out_img_stride < 0 || a->out_group_stride < 0) return false;
     if (a->residual && (a->res_c % 8 != 0 || (reinterpret_cast<uintptr_t>(a->residual) & 15) != 0)) return false;
@@ -490,6 +520,10 @@ int launch_conv_ring(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t st
     P.w = reinterpret_cast<const uint8_t*>(a->packed) + p.ring_off;
     P.bias = reinterpret_cast<const float*>(a->packed);
     P.has_res = a->residual != nullptr;
+    P.has_main = (p.ring & 1) ? 1 : 0;
+    P.has_patch = (p.ring & 2) ? 1 : 0;
+    P.num_slots = P.has_patch ? kRingSlotsPatch : kRingSlots;
+    P.slot_bytes = kRingSlotBytes + (P.has_patch ? kRingPatchBytes : 0);
     P.H = a->h; P.W = a->w; P.strips = ceil_div(a->w, kRingUW); P.ipg = a->imgs_per_group;
     P.cols = P.ipg * P.strips;
     P.rows_g = (uint32_t)P.cols * (uint32_t)P.H;
@@ -500,15 +534,32 @@ int launch_conv_ring(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t st
         P.debug = dbg_env ? atoi(dbg_env) : 0;
     }
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    {
-        cuuint64_t dims[4] = {(cuuint64_t)a->in_c[0], (cuuint64_t)a->w, (cuuint64_t)a->h, (cuuint64_t)a->batch};
-        cuuint64_t strides[3] = {(cuuint64_t)a->in_c[0] * 2, (cuuint64_t)a->w * a->in_c[0] * 2, (cuuint64_t)a->h * a->w * a->in_c[0] * 2};
+    if (P.has_main) {
+        const int ms = p.ring_main_seg;
+        cuuint64_t dims[4] = {(cuuint64_t)a->in_c[ms], (cuuint64_t)a->w, (cuuint64_t)a->h, (cuuint64_t)a->batch};
+        cuuint64_t strides[3] = {(cuuint64_t)a->in_c[ms] * 2, (cuuint64_t)a->w * a->in_c[ms] * 2, (cuuint64_t)a->h * a->w * a->in_c[ms] * 2};
         cuuint32_t box[4] = {64, 32, 1, 1};
-        CUresult r = encode(&P.in_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a->in[0]), dims, strides, box, estr,
+        CUresult r = encode(&P.in_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a->in[ms]), dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             set_error("cuTensorMapEncodeTiled (ring input) failed with %d", (int)r);
+            return VSRB_E_CUDA;
+        }
+    }
+    for (int gi = 0; gi < (P.has_patch ? p.groups : 0); ++gi) {
+        // both strides 0 = dense [groups][imgs_per_group]; with an explicit image stride the group stride is taken literally
+        // (0 is then a real value: both propagation directions read the same frame at the middle time step)
+        const long long istr = a->patch_img_stride ? a->patch_img_stride : (long long)a->h * a->w * 32;
+        const long long gstr = (a->patch_img_stride || a->patch_group_stride) ? a->patch_group_stride : istr * a->imgs_per_group;
+        char* base = reinterpret_cast<char*>(const_cast<void*>(a->patch)) + (long long)gi * gstr * 2;
+        cuuint64_t dims[4] = {32, (cuuint64_t)a->w, (cuuint64_t)a->h, (cuuint64_t)a->imgs_per_group};
+        cuuint64_t strides[3] = {64, (cuuint64_t)a->w * 64, (cuuint64_t)istr * 2};
+        cuuint32_t box[4] = {32, 32, 1, 1};
+        CUresult r = encode(&P.patch_map[gi], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("cuTensorMapEncodeTiled (ring patches) failed with %d", (int)r);
             return VSRB_E_CUDA;
         }
     }

@@ -427,7 +427,48 @@ __global__ void pixel_unshuffle2_kernel(const uint4* __restrict__ src, uint4* __
     }
 }
 
+namespace vsrb {
+// 3x3 im2col of 3-channel frames: one thread per pixel writes the 27 neighbourhood values (+ 5 zeros) as 64 bytes of bf16
+__global__ void im2col3x3_c3_kernel(const float* __restrict__ src, uint4* __restrict__ dst, int n, int h, int w) {
+    const long long total = (long long)n * h * w;
+    const long long plane = (long long)h * w;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % w);
+        const long long t = i / w;
+        const int y = (int)(t % h);
+        const long long b = t / h;
+        const float* fp = src + b * 3 * plane;
+        float v[32];
+#pragma unroll
+        for (int k = 27; k < 32; ++k) v[k] = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int yy = y + ky - 1, xx = x + kx - 1;
+                const bool in = yy >= 0 && yy < h && xx >= 0 && xx < w;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) v[(ky * 3 + kx) * 3 + c] = in ? __ldg(fp + c * plane + (long long)yy * w + xx) : 0.f;
+            }
+        uint4* op = dst + i * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            op[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]), pack_bf16(v[8 * j + 4], v[8 * j + 5]),
+                               pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+    }
+}
+}  // namespace vsrb
+
 extern "C" {
+
+int vsrb_im2col3x3_c3(const float* frames, void* patches, int32_t n, int32_t h, int32_t w, void* stream) {
+    VSRB_CHECK_ARG(frames && patches && n >= 1 && h >= 1 && w >= 1, "im2col3x3_c3: bad arguments");
+    VSRB_CHECK_ARG((reinterpret_cast<uintptr_t>(patches) & 15) == 0, "im2col3x3_c3: output must be 16-byte aligned");
+    const long long total = (long long)n * h * w;
+    vsrb::im2col3x3_c3_kernel<<<vsrb::grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(frames, reinterpret_cast<uint4*>(patches), n, h, w);
+    VSRB_LAUNCH_CHECK();
+    return VSRB_OK;
+}
 
 int vsrb_flow_warp(const void* x, int64_t x_img_stride, const float* flow, int64_t flow_img_stride, void* out, int32_t n,
                    int32_t h, int32_t w, int32_t c, int32_t dtype, int32_t padding_mode, void* stream) {

@@ -251,7 +251,7 @@ def conv_chain(x: torch.Tensor, convs: Sequence[torch.nn.Conv2d], act: str = "re
 
 
 def _run_resblocks(cur, ca, stem_pc, block_pcs, n, h, w, mid_c, dt, device, tag, final_out=None, final_strides=(0, 0),
-                   extra_in=None, extra_c=0, groups=1):
+                   extra_in=None, extra_c=0, groups=1, stem_patch=None, stem_patch_strides=(0, 0)):
     """stem (+LeakyReLU) then residual blocks on NHWC buffers; returns (tensor, channels).
     If `final_out` is given the last conv of the chain writes there (raw address allowed)."""
     tdt = ops.TORCH_DT[dt]
@@ -271,7 +271,8 @@ def _run_resblocks(cur, ca, stem_pc, block_pcs, n, h, w, mid_c, dt, device, tag,
         o, st = target(free[0])
         ins, cs = ([cur, extra_in], [ca, extra_c]) if extra_in is not None else ([cur], [ca])
         ops.conv2d_fwd(stem_pc, ins, cs, n, h, w, act=ACT_LRELU, slope=0.1, out=o, out_c=mid_c,
-                       out_img_stride=st[0], out_group_stride=st[1])
+                       out_img_stride=st[0], out_group_stride=st[1], patch=stem_patch, patch_img_stride=stem_patch_strides[0],
+                       patch_group_stride=stem_patch_strides[1])
         cur, ca, cur_i = o, mid_c, free[0]
     else:
         cur_i = -1
@@ -462,10 +463,14 @@ def _cleaner_run(cl, x: torch.Tensor, dt: int) -> torch.Tensor:
     blocks = [(packed([b.conv1], [(0, mid)], dt), packed([b.conv2], [(0, mid)], dt)) for b in cl.resblock.res_block]
     last = packed([cl.conv], [(0, mid)], dt)
     chunk = max(1, min(B, CLEAN_CHUNK))
+    # bf16 mode: the 3 -> 64 stem reads the frame as 3x3 im2col patches (one K = 32 chunk on the ring-walk kernel)
+    patches = ws("cl_patch", (chunk, h, w, 32), torch.bfloat16, dev) if (dt == BF16 and mid == 64) else None
     for _ in range(cl.steps):
         for b0 in range(0, B, chunk):
             nb = min(chunk, B - b0)
-            cur, ca = _run_resblocks(x_nhwc[b0:b0 + nb], clr, stem, blocks, nb, h, w, mid_c, dt, dev, "cl")
+            if patches is not None:
+                ops.im2col3x3(x[b0:b0 + nb], patches, nb, h, w)
+            cur, ca = _run_resblocks(x_nhwc[b0:b0 + nb], clr, stem, blocks, nb, h, w, mid_c, dt, dev, "cl", stem_patch=patches)
             ops.conv2d_fwd(last, [cur], [ca], nb, h, w, act=ACT_NONE, epilogue=EPI_CLEAN, out=x_nhwc[b0:b0 + nb], out_c=clr,
                            f32_io=x[b0:b0 + nb])
     return x_nhwc
@@ -526,6 +531,12 @@ def _basicvsr_run(bv, lrs: torch.Tensor, dt: int, x_nhwc: Optional[torch.Tensor]
     blocks = [(packed([a.conv1, b.conv1], [(0, mid)], dt), packed([a.conv2, b.conv2], [(0, mid)], dt))
               for a, b in zip(bwd.res_block, fwd.res_block)]
     warped = ws("feat_warp", (2 * n, h, w, mid_c), tdt, dev)
+    # bf16 mode: the 3-channel half of cat([lr_i, feat]) enters the stem as 3x3 im2col patches of the frame, built once per clip
+    lr_patch = None
+    if dt == BF16 and mid == 64:
+        lr_patch = ws("lr_patch", (n * t, h, w, 32), torch.bfloat16, dev)
+        ops.im2col3x3(x_flat, lr_patch, n * t, h, w)
+    pf = h * w * 32                                                      # elements of one frame of patches
     for s in range(t):
         if s == 0:
             warped.zero_()
@@ -536,8 +547,11 @@ def _basicvsr_run(bv, lrs: torch.Tensor, dt: int, x_nhwc: Optional[torch.Tensor]
                           n, h, w, mid_c, dt, PAD_ZEROS, x_img_stride=t * frame_el, flow_img_stride=(t - 1) * h * w)
         o_b = fbk.data_ptr() + (t - 1 - s) * frame_el * es
         o_f = ffw.data_ptr() + s * frame_el * es
+        # group 0 (backward chain) reads frame t-1-s of every clip, group 1 (forward chain) frame s
         _run_resblocks(warped, mid_c, stem, blocks, 2 * n, h, w, mid_c, dt, dev, "pp", final_out=o_b,
-                       final_strides=(t * frame_el, (o_f - o_b) // es), extra_in=pairs[s], extra_c=clr, groups=2)
+                       final_strides=(t * frame_el, (o_f - o_b) // es), extra_in=pairs[s], extra_c=clr, groups=2,
+                       stem_patch=None if lr_patch is None else lr_patch.data_ptr() + (t - 1 - s) * pf * 2,
+                       stem_patch_strides=(t * pf, (2 * s - (t - 1)) * pf))
 
     # ---- fusion + upsampling + reconstruction, batched over frames (basicvsr.py:75-83) --
     ops.TAG = "tail"

@@ -33,7 +33,7 @@ def _decode_into(args):
     from PIL import Image
     with Image.open(path) as im:
         a = np.asarray(im.convert("RGB"))
-    dst.copy_(torch.from_numpy(np.ascontiguousarray(a)).permute(2, 0, 1))
+    dst.copy_(torch.from_numpy(np.array(a)).permute(2, 0, 1))              # np.array: a writable copy of PIL's read-only buffer
     return None
 
 

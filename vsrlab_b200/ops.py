@@ -142,7 +142,8 @@ class PackedConv:
 def conv2d_fwd(pc: PackedConv, ins: Sequence, in_c: Sequence[int], batch: int, h: int, w: int, *,
                imgs_per_group: Optional[int] = None, act: int = ACT_NONE, slope: float = 0.1, epilogue: int = EPI_NHWC,
                out=None, out_c: int = 0, out_img_stride: int = 0, out_group_stride: int = 0, residual=None, res_c: int = 0,
-               f32_io=None, f32_in=None, aux_hw: Tuple[int, int] = (0, 0), max_ctas: int = 0, extra_flags: int = 0) -> None:
+               f32_io=None, f32_in=None, aux_hw: Tuple[int, int] = (0, 0), max_ctas: int = 0, extra_flags: int = 0,
+               patch=None, patch_img_stride: int = 0, patch_group_stride: int = 0) -> None:
     """Enqueue one fused convolution.  `ins`, `out`, `residual`, `f32_io`, `f32_in` are tensors
     (or raw int device addresses) that the caller keeps alive."""
     a = L.ConvArgs()
@@ -175,6 +176,9 @@ def conv2d_fwd(pc: PackedConv, ins: Sequence, in_c: Sequence[int], batch: int, h
     a.f32_in = _p(f32_in)
     a.aux_h, a.aux_w = aux_hw
     a.max_ctas = max_ctas
+    if patch is not None:
+        a.patch = _p(patch)
+        a.patch_img_stride, a.patch_group_stride = patch_img_stride, patch_group_stride
     a.flags = (L.CONV_PDL if (pc.uses > 0 and PDL) else 0) | extra_flags
     pc.uses += 1
     if PROFILE is None:                            # the common case: no per-launch bookkeeping
@@ -223,6 +227,11 @@ def spynet_level_input(lvl, ref_idx, supp_idx, flow_prev, flow_up, conv_in, P: i
 
 def flow_resize(fin, fout, P: int, Hp: int, Wp: int, h: int, w: int) -> None:
     L.check(L.load().vsrb_flow_resize(_p(fin), _p(fout), P, Hp, Wp, h, w, _stream()), "vsrb_flow_resize")
+
+
+def im2col3x3(frames: torch.Tensor, patches: torch.Tensor, n: int, h: int, w: int) -> None:
+    """fp32 NCHW [n,3,h,w] -> bf16 [n,h,w,32] 3x3 neighbourhoods (the K = 32 operand of the image stems)."""
+    L.check(L.load().vsrb_im2col3x3_c3(_p(frames), _p(patches), n, h, w, _stream()), "vsrb_im2col3x3_c3")
 
 
 def pixel_unshuffle2(src: torch.Tensor, dst: torch.Tensor, n: int, h: int, w: int, c: int) -> None:
