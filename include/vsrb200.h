@@ -164,6 +164,10 @@ size_t vsrb_packed_weight_bytes(const vsrb_conv_geom* g);
 int    vsrb_pack_conv_weight(const vsrb_conv_geom* g, const float* w, int32_t cin_total,
                              const float* bias, void* packed, void* stream);
 int    vsrb_conv2d_fwd(const vsrb_conv_args* a, void* stream);
+/* 1 if this launch would run on the ring-walk kernel (conv_ring.cu) - the only one that implements `warp_flow` and
+ * consumes `patch` - else 0.  A pure function of the arguments; lets a scheduler choose between the fused stem and
+ * vsrb_flow_warp + vsrb_conv2d_fwd once per shape.                                                                */
+int    vsrb_conv2d_takes_ring(const vsrb_conv_args* a);
 /* How the library will tile this geometry (diagnostics / tests): info = {stacked, n_tile, n_blocks,
  * mma_n, k_chunk of segment 0, k_chunk of segment 1, pipeline stages per tile, weight KiB per block} */
 int    vsrb_conv_plan_info(const vsrb_conv_geom* g, int32_t info[8]);

@@ -55,6 +55,14 @@ struct RingParams {
     CUtensorMap patch_map[2];   // per weight group: 3x3 im2col patches [32, W, H, imgs_per_group] box {32, 32, 1, 1} (SW64)
     int has_main, has_patch;    // operands: the 64-channel segment (N = 192 ring MMAs) / the 3-channel segment as K = 32 patches
     int num_slots, slot_bytes;
+    // fused backward warp (basicvsr.py:52-58,66-73): the main operand's rows are not loaded but SAMPLED from the previous
+    // time step's features with the flow field, by the epilogue warps, straight into the swizzled operand rows
+    int gather;
+    const __nv_bfloat16* feat;
+    long long feat_img_stride, feat_group_stride;      // elements
+    int feat_c;
+    const float2* flow;
+    long long flow_img_stride, flow_group_stride;      // float2 elements
     const uint8_t* w;      // ring image: [group][rank]{[kx][96 rows][128 B] | patch [32 rows][64 B]}
     const float* bias;     // [group][64]
     int has_res;
@@ -182,14 +190,16 @@ __global__ void __launch_bounds__(kRingThreads, 1) conv_ring_kernel(const __grid
     }
 
     if (warp == 0 && lane == 0) {
-        if (P.has_main) prefetch_tensormap(&P.in_map);
+        if (P.has_main && !P.gather) prefetch_tensormap(&P.in_map);
         if (P.has_patch) prefetch_tensormap(&P.patch_map[g]);
         prefetch_tensormap(&P.out_map);
         if (P.has_res) prefetch_tensormap(&P.res_map);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < kSlots; ++i) {
-            mbar_init(full0 + 8 * i, 1);
+            // a row is complete when its TMA bytes have landed (one expect_tx arrival of the leader's producer) and / or,
+            // with the fused warp, when the 4 + 4 gathering warps of the pair have written their quarters
+            mbar_init(full0 + 8 * i, (P.gather ? 8 : 0) + ((!P.gather || P.has_patch) ? 1 : 0));
             mbar_init(empty0 + 8 * i, 1);
         }
         for (int i = 0; i < kRingAcc; ++i) {
@@ -241,7 +251,9 @@ __global__ void __launch_bounds__(kRingThreads, 1) conv_ring_kernel(const __grid
             const uint32_t full_lead = mapa_rank(full0, 0);
             int slot = 0;
             uint32_t phase = 0;
+            const bool tma_main = P.has_main && !P.gather;
             for (int t = 0; t < S; ++t) {
+                if (!tma_main && !P.has_patch) break;              // fused warp without a patch operand: nothing to load
                 if ((P.debug & 1) && crank != 0) break;            // (timing experiment without loads: nothing paces this warp)
                 mbar_wait(empty0 + 8 * slot, phase ^ 1, P.dbg, 11, dead);
                 if (P.debug & 1) {
@@ -250,12 +262,12 @@ __global__ void __launch_bounds__(kRingThreads, 1) conv_ring_kernel(const __grid
                     int act = 0;
 #pragma unroll
                     for (int r = 0; r < 8; ++r) act += t < items[r] ? 1 : 0;
-                    mbar_expect_tx(full0 + 8 * slot, (uint32_t)act * ((P.has_main ? 4096u : 0u) + (P.has_patch ? 2048u : 0u)));
+                    mbar_expect_tx(full0 + 8 * slot, (uint32_t)act * ((tma_main ? 4096u : 0u) + (P.has_patch ? 2048u : 0u)));
                 }
                 if (lane < 4 && !wk.done && !(P.debug & 1)) {
                     const int li = wk.col / P.strips, strip = wk.col - li * P.strips;
                     const uint32_t sa = slots0 + slot * P.slot_bytes;
-                    if (P.has_main)
+                    if (tma_main)
                         tma_load_4d_pair(&P.in_map, full_lead + 8 * slot, sa + lane * 4096, 0, strip * kRingUW - 1, wk.y, g * P.ipg + li);
                     if (P.has_patch)      // the im2col row of this item's own pixels: no halo column, no kx shift
                         tma_load_4d_pair(&P.patch_map[g], full_lead + 8 * slot, sa + kRingSlotBytes + lane * 2048, 0, strip * kRingUW, wk.y, li);
@@ -346,15 +358,77 @@ __global__ void __launch_bounds__(kRingThreads, 1) conv_ring_kernel(const __grid
             ring_range(P.rows_g, P.H, P.cols, P.rpc, n_ranges, pair0 + (int)crank * 4 + q, lo, hi);
             wk.init(lo, hi, P.H);
         }
+        // ---- fused warp: this warp also PRODUCES the operand row of its quarter for the steps t with (t & 1) == eh -------
+        RingWalk fwk = wk;                        // cursor over the same items, kGatherAhead steps ahead of the epilogue
+        int fslot = 0;
+        uint32_t fphase = 0;
+        const uint32_t full_lead = mapa_rank(full0, 0);
+        constexpr int kGatherAhead = 4;           // even: a warp alternates between producing a row and finishing a row
+        auto fill_row = [&](bool mine) {
+            if (mine) {
+                mbar_wait(empty0 + 8 * fslot, fphase ^ 1, P.dbg, 19, dead);
+                if (!fwk.done) {
+                    const int li = fwk.col / P.strips, strip = fwk.col - li * P.strips;
+                    const int x = strip * kRingUW - 1 + lane, y = fwk.y;
+                    const uint32_t row = slots0 + (uint32_t)fslot * (uint32_t)P.slot_bytes + (uint32_t)q * 4096u + (uint32_t)lane * 128u;
+                    TapSet tp;
+                    bool inside = y >= 0 && y < P.H && x >= 0 && x < P.W;              // outside: the conv's zero padding
+                    if (inside) {
+                        const float2 f = __ldg(P.flow + (long long)g * P.flow_group_stride + (long long)li * P.flow_img_stride +
+                                               (long long)y * P.W + x);
+                        float ix, iy;
+                        sample_pos((float)x + f.x, (float)y + f.y, P.W, P.H, ix, iy);
+                        make_taps(ix, iy, P.W, P.H, 0, tp);
+                    }
+                    const __nv_bfloat16* fb = P.feat + (long long)g * P.feat_group_stride + (long long)li * P.feat_img_stride;
+#pragma unroll 2
+                    for (int j = 0; j < 8; ++j) {
+                        float acc[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+                        if (inside) {
+                            uint4 u[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                u[k] = tp.off[k] >= 0 ? __ldg(reinterpret_cast<const uint4*>(fb + (long long)tp.off[k] * P.feat_c + j * 8))
+                                                      : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                if (tp.off[k] >= 0) {           // same order and arithmetic as flow_warp_kernel (warp.cu)
+                                    const uint32_t uu[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        const float2 v2 = unpack_bf16(uu[e]);
+                                        acc[2 * e] = fmaf(v2.x, tp.wgt[k], acc[2 * e]);
+                                        acc[2 * e + 1] = fmaf(v2.y, tp.wgt[k], acc[2 * e + 1]);
+                                    }
+                                }
+                            }
+                        }
+                        st_shared_v4(row + (((uint32_t)j ^ ((uint32_t)lane & 7u)) << 4), pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]),
+                                     pack_bf16(acc[4], acc[5]), pack_bf16(acc[6], acc[7]));
+                    }
+                    fence_proxy_async();
+                }
+                __syncwarp();
+                if (lane == 0)
+                    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(full_lead + 8 * fslot) : "memory");
+            }
+            fwk.next();
+            if (++fslot == kSlots) { fslot = 0; fphase ^= 1; }
+        };
         const float act_k = P.act_k;
         const uint32_t stg = stg0 + (uint32_t)(eh * 4 + q) * 4096u;       // this warp's staging row
         const uint32_t rbar = rbar0 + 8 * (eh * 4 + q);
         uint32_t rphase = 0;
         griddep_wait();        // this role reads / writes global memory other kernels on the stream own
+        if (P.gather)
+            for (int t = 0; t < kGatherAhead && t < S; ++t) fill_row((t & 1) == eh);
         // output row p (p = -1 is the ring's dummy first tenant) is complete after step p + 1; slot = (p + 1) mod 6
         int slot = 0;
         uint32_t sphase = 0;                      // ((p + 1) / 6) & 1
         for (int p = -1; p <= S - 2; ++p) {
+            if (P.gather && p + 1 + kGatherAhead < S) fill_row(((p + 1 + kGatherAhead) & 1) == eh);
             const bool mine = (p & 1) == eh;
             const bool valid = mine && p >= 0 && wk.valid();
             int li = 0, x0 = 0, y = 0;
@@ -472,6 +546,9 @@ bool ring_eligible(const vsrb_conv_args* a, const ConvPlan& p) {
     if (p.ring & 1) {
         const int ms = p.ring_main_seg;
         if (a->in_c[ms] % 8 != 0 || (reinterpret_cast<uintptr_t>(a->in[ms]) & 15) != 0) return false;
+        if (a->warp_flow && (a->in_img_stride % 8 != 0 || a->in_group_stride % 8 != 0)) return false;
+    } else if (a->warp_flow) {
+        return false;
     }
     if (a->out_c % 8 != 0 || (reinterpret_cast<uintptr_t>(a->out) & 15) != 0) return false;
     if (a->out_img_stride % 8 != 0 || a->out_group_stride % 8 != 0 || a->out_img_stride < 0 || a->out_group_stride < 0) return false;
@@ -522,6 +599,18 @@ int launch_conv_ring(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t st
     P.has_res = a->residual != nullptr;
     P.has_main = (p.ring & 1) ? 1 : 0;
     P.has_patch = (p.ring & 2) ? 1 : 0;
+    P.gather = (a->warp_flow && P.has_main) ? 1 : 0;
+    if (P.gather) {
+        const int ms = p.ring_main_seg;
+        P.feat = reinterpret_cast<const __nv_bfloat16*>(a->in[ms]);
+        P.feat_c = a->in_c[ms];
+        P.feat_img_stride = a->in_img_stride ? a->in_img_stride : (long long)a->h * a->w * a->in_c[ms];
+        P.feat_group_stride = (a->in_img_stride || a->in_group_stride) ? a->in_group_stride : P.feat_img_stride * a->imgs_per_group;
+        P.flow = reinterpret_cast<const float2*>(a->warp_flow);
+        P.flow_img_stride = a->warp_flow_img_stride ? a->warp_flow_img_stride : (long long)a->h * a->w;
+        P.flow_group_stride = (a->warp_flow_img_stride || a->warp_flow_group_stride) ? a->warp_flow_group_stride
+                                                                                      : P.flow_img_stride * a->imgs_per_group;
+    }
     P.num_slots = P.has_patch ? kRingSlotsPatch : kRingSlots;
     P.slot_bytes = kRingSlotBytes + (P.has_patch ? kRingPatchBytes : 0);
     P.H = a->h; P.W = a->w; P.strips = ceil_div(a->w, kRingUW); P.ipg = a->imgs_per_group;
@@ -534,7 +623,7 @@ int launch_conv_ring(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t st
         P.debug = dbg_env ? atoi(dbg_env) : 0;
     }
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    if (P.has_main) {
+    if (P.has_main && !P.gather) {
         const int ms = p.ring_main_seg;
         cuuint64_t dims[4] = {(cuuint64_t)a->in_c[ms], (cuuint64_t)a->w, (cuuint64_t)a->h, (cuuint64_t)a->batch};
         cuuint64_t strides[3] = {(cuuint64_t)a->in_c[ms] * 2, (cuuint64_t)a->w * a->in_c[ms] * 2, (cuuint64_t)a->h * a->w * a->in_c[ms] * 2};

@@ -14,39 +14,6 @@ namespace vsrb {
 // contiguous C*sizeof(T) run per tap), blend in fp32 and store one 16-byte vector.
 // Algorithmic traffic: C*sizeof(T) read + 8 B flow + C*sizeof(T) written per pixel.
 // ---------------------------------------------------------------------------------------
-struct TapSet {
-    int off[4];     // pixel index of the tap inside the image, or -1 when it contributes zero
-    float wgt[4];
-};
-
-__device__ __forceinline__ void sample_pos(float px, float py, int w, int h, float& ix, float& iy) {
-    // the reference normalises to [-1,1] and grid_sample(align_corners=True) maps back
-    float nx = 2.0f * px / (float)max(w - 1, 1) - 1.0f;
-    float ny = 2.0f * py / (float)max(h - 1, 1) - 1.0f;
-    ix = (nx + 1.0f) / 2.0f * (float)(w - 1);
-    iy = (ny + 1.0f) / 2.0f * (float)(h - 1);
-}
-
-__device__ __forceinline__ void make_taps(float ix, float iy, int w, int h, int border, TapSet& t) {
-    if (border) {
-        ix = fminf(fmaxf(ix, 0.f), (float)(w - 1));
-        iy = fminf(fmaxf(iy, 0.f), (float)(h - 1));
-    }
-    float fx = floorf(ix), fy = floorf(iy);
-    float wx1 = ix - fx, wy1 = iy - fy, wx0 = 1.f - wx1, wy0 = 1.f - wy1;
-    // guard the float->int conversion for wild flows
-    fx = fminf(fmaxf(fx, -2.f), (float)w);
-    fy = fminf(fmaxf(fy, -2.f), (float)h);
-    int x0 = (int)fx, y0 = (int)fy;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        int xi = x0 + (k & 1), yi = y0 + (k >> 1);
-        bool ok = xi >= 0 && xi < w && yi >= 0 && yi < h;
-        t.off[k] = ok ? yi * w + xi : -1;
-        t.wgt[k] = ((k & 1) ? wx1 : wx0) * ((k >> 1) ? wy1 : wy0);
-    }
-}
-
 template <typename T> struct Vec16;
 template <> struct Vec16<__nv_bfloat16> {
     static constexpr int N = 8;
@@ -428,33 +395,26 @@ __global__ void pixel_unshuffle2_kernel(const uint4* __restrict__ src, uint4* __
 }
 
 namespace vsrb {
-// 3x3 im2col of 3-channel frames: one thread per pixel writes the 27 neighbourhood values (+ 5 zeros) as 64 bytes of bf16
+// 3x3 im2col of 3-channel frames: one thread per (pixel, 16-byte quarter of its 64-byte patch row): eight of the 27
+// neighbourhood values (+ 5 zeros at the end), so a warp's stores are 512 consecutive bytes
 __global__ void im2col3x3_c3_kernel(const float* __restrict__ src, uint4* __restrict__ dst, int n, int h, int w) {
-    const long long total = (long long)n * h * w;
+    const long long total = (long long)n * h * w * 4;
     const long long plane = (long long)h * w;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int x = (int)(i % w);
-        const long long t = i / w;
+        const int j = (int)(i & 3);
+        const long long pix = i >> 2;
+        const int x = (int)(pix % w);
+        const long long t = pix / w;
         const int y = (int)(t % h);
-        const long long b = t / h;
-        const float* fp = src + b * 3 * plane;
-        float v[32];
+        const float* fp = src + (t / h) * 3 * plane;
+        float v[8];
 #pragma unroll
-        for (int k = 27; k < 32; ++k) v[k] = 0.f;
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const int yy = y + ky - 1, xx = x + kx - 1;
-                const bool in = yy >= 0 && yy < h && xx >= 0 && xx < w;
-#pragma unroll
-                for (int c = 0; c < 3; ++c) v[(ky * 3 + kx) * 3 + c] = in ? __ldg(fp + c * plane + (long long)yy * w + xx) : 0.f;
-            }
-        uint4* op = dst + i * 4;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            op[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]), pack_bf16(v[8 * j + 4], v[8 * j + 5]),
-                               pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+        for (int e = 0; e < 8; ++e) {
+            const int k = 8 * j + e, tap = k / 3, c = k - tap * 3;
+            const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+            v[e] = (k < 27 && yy >= 0 && yy < h && xx >= 0 && xx < w) ? __ldg(fp + c * plane + (long long)yy * w + xx) : 0.f;
+        }
+        dst[i] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
     }
 }
 }  // namespace vsrb
@@ -464,7 +424,7 @@ extern "C" {
 int vsrb_im2col3x3_c3(const float* frames, void* patches, int32_t n, int32_t h, int32_t w, void* stream) {
     VSRB_CHECK_ARG(frames && patches && n >= 1 && h >= 1 && w >= 1, "im2col3x3_c3: bad arguments");
     VSRB_CHECK_ARG((reinterpret_cast<uintptr_t>(patches) & 15) == 0, "im2col3x3_c3: output must be 16-byte aligned");
-    const long long total = (long long)n * h * w;
+    const long long total = (long long)n * h * w * 4;
     vsrb::im2col3x3_c3_kernel<<<vsrb::grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(frames, reinterpret_cast<uint4*>(patches), n, h, w);
     VSRB_LAUNCH_CHECK();
     return VSRB_OK;
