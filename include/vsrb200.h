@@ -154,6 +154,11 @@ int         vsrb_debug_status(void* stream);
  * last tile stored, stores drained, exit); copies the first `n_ctas` CTAs' stamps of the last launch to `out[n_ctas*8]` */
 int         vsrb_debug_trace(uint64_t* out, int32_t n_ctas);
 
+/* debug aid: with VSRB_RING_DEBUG bit 64 set, CTA (0,0) of every ring-walk conv adds up clock cycles: out[0] MMA issuer waiting
+ * for a free accumulator slot, [1] waiting for operand rows, [2] steps issued, [3] gather warp waiting for a free operand
+ * slot, [4] gathering, [5] epilogue warp waiting for finished rows, [6] epilogue work                                  */
+int         vsrb_ring_debug_stats(uint64_t* out, int32_t reset);
+
 /* ---- convolution: replaces nn.Conv2d -> F.conv2d (+ the pointwise op that follows it) --
  * reference: conv.py:89-92,101-103 (ResidualConv/ResidualBlock), conv.py:21 (ConvReLU),
  * upsampling.py:10-12 (PixelShufflePack), basicvsr.py:75-82 (point_conv, conv_last, skip),

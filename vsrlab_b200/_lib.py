@@ -77,6 +77,7 @@ SYMBOLS = {
     "vsrb_launch_count": (C.c_int64, []),
     "vsrb_debug_status": (C.c_int, [C.c_void_p]),
     "vsrb_debug_trace": (C.c_int, [C.c_void_p, C.c_int32]),
+    "vsrb_ring_debug_stats": (C.c_int, [C.c_void_p, C.c_int32]),
     "vsrb_im2col3x3_c3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "vsrb_pixel_unshuffle2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "vsrb_packed_weight_bytes": (C.c_size_t, [C.POINTER(ConvGeom)]),

@@ -159,6 +159,12 @@ __device__ __forceinline__ void ring_fill_block(uint32_t taddr, const float* bia
     }
 }
 
+// VSRB_RING_DEBUG bit 64: cycle counters of CTA (0,0): [0] issuer waiting for a free accumulator slot, [1] issuer waiting for
+// operand rows, [2] steps, [3] gather warp 4 waiting for a free operand slot, [4] its gather time, [5] its wait for finished
+// rows, [6] its epilogue time (vsrb_ring_debug_stats)
+__device__ unsigned long long g_ring_stat[8];
+__device__ __forceinline__ long long ring_clock() { return clock64(); }
+
 __global__ void __launch_bounds__(kRingThreads, 1) conv_ring_kernel(const __grid_constant__ RingParams P) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -172,7 +178,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) conv_ring_kernel(const __grid
     float* bias_s = reinterpret_cast<float*>(base_ptr + 512);
     const uint32_t wres = base + kRingCtrl;
     const uint32_t slots0 = wres + VSRB_RING_W_BYTES;
-    const uint32_t stg0 = slots0 + kRingSlotArea;
+    const uint32_t stg0 = slots0 + (uint32_t)P.num_slots * (uint32_t)P.slot_bytes;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = blockIdx.y;
@@ -297,8 +303,17 @@ __global__ void __launch_bounds__(kRingThreads, 1) conv_ring_kernel(const __grid
                 for (int t = 0; t < S; ++t) {
                     // the slot of output row t+1 is touched for the first time at this step: its previous tenant
                     // (row t-5) must have been read out and the block(s) re-initialised
+                    const bool stat = (P.debug & 64) && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
+                    const long long c0 = stat ? ring_clock() : 0;
                     mbar_wait(tempty0 + 8 * nb, nb_phase, P.dbg, 15, dead);
+                    const long long c1 = stat ? ring_clock() : 0;
                     mbar_wait(full0 + 8 * slot, phase, P.dbg, 16, dead);
+                    if (stat) {
+                        const long long c2 = ring_clock();
+                        atomicAdd(&g_ring_stat[0], (unsigned long long)(c1 - c0));
+                        atomicAdd(&g_ring_stat[1], (unsigned long long)(c2 - c1));
+                        atomicAdd(&g_ring_stat[2], 1ull);
+                    }
                     tc_fence_after();
                     if (elect_one()) {
                         const uint32_t sa = slots0 + slot * P.slot_bytes;
@@ -359,6 +374,10 @@ __global__ void __launch_bounds__(kRingThreads, 1) conv_ring_kernel(const __grid
             wk.init(lo, hi, P.H);
         }
         // ---- fused warp: this warp also PRODUCES the operand row of its quarter for the steps t with (t & 1) == eh -------
+        // Measured (tools/stem_bench.py, VSRB_RING_DEBUG=64): a row costs the warp ~6 000 cycles of shuffles, FMAs, packs and
+        // stores even without its global loads (+1 100 with them), i.e. the gather is bound by ONE warp's instruction latency -
+        // the stand-alone flow_warp kernel spreads the same work over 64 warps per SM.  Splitting a row between the two warps
+        // of a quarter made it worse (each half still pays the fixed flow -> taps -> loads chain).
         RingWalk fwk = wk;                        // cursor over the same items, kGatherAhead steps ahead of the epilogue
         int fslot = 0;
         uint32_t fphase = 0;
@@ -366,53 +385,83 @@ __global__ void __launch_bounds__(kRingThreads, 1) conv_ring_kernel(const __grid
         constexpr int kGatherAhead = 4;           // even: a warp alternates between producing a row and finishing a row
         auto fill_row = [&](bool mine) {
             if (mine) {
+                const bool stat = (P.debug & 64) && blockIdx.x == 0 && blockIdx.y == 0 && warp == 4 && lane == 0;
+                const long long c0 = stat ? ring_clock() : 0;
                 mbar_wait(empty0 + 8 * fslot, fphase ^ 1, P.dbg, 19, dead);
+                const long long c1 = stat ? ring_clock() : 0;
+                if (stat) atomicAdd(&g_ring_stat[3], (unsigned long long)(c1 - c0));
                 if (!fwk.done) {
                     const int li = fwk.col / P.strips, strip = fwk.col - li * P.strips;
                     const int x = strip * kRingUW - 1 + lane, y = fwk.y;
-                    const uint32_t row = slots0 + (uint32_t)fslot * (uint32_t)P.slot_bytes + (uint32_t)q * 4096u + (uint32_t)lane * 128u;
+                    // lane = pixel for the sampling positions ...
                     TapSet tp;
-                    bool inside = y >= 0 && y < P.H && x >= 0 && x < P.W;              // outside: the conv's zero padding
+                    const bool inside = y >= 0 && y < P.H && x >= 0 && x < P.W;        // outside: the conv's zero padding
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { tp.off[k] = -1; tp.wgt[k] = 0.f; }
                     if (inside) {
-                        const float2 f = __ldg(P.flow + (long long)g * P.flow_group_stride + (long long)li * P.flow_img_stride +
-                                               (long long)y * P.W + x);
+                        const float2 f = (P.debug & 32) ? make_float2(0.25f, 0.25f)
+                                                        : __ldg(P.flow + (long long)g * P.flow_group_stride + (long long)li * P.flow_img_stride +
+                                                                (long long)y * P.W + x);
                         float ix, iy;
                         sample_pos((float)x + f.x, (float)y + f.y, P.W, P.H, ix, iy);
                         make_taps(ix, iy, P.W, P.H, 0, tp);
                     }
                     const __nv_bfloat16* fb = P.feat + (long long)g * P.feat_group_stride + (long long)li * P.feat_img_stride;
-#pragma unroll 2
-                    for (int j = 0; j < 8; ++j) {
-                        float acc[8];
+                    // ... and 8 lanes per pixel for the gathers: one load instruction reads four whole 128-byte pixel rows
+                    const int j = lane & 7;
+                    // two batches of four pixel groups: all sixteen 16-byte loads of a batch are issued before the first result is
+                    // used (the shared-memory stores below are compiler barriers: without the explicit batching every group paid
+                    // its own L2 round trip, 8 in a row)
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-                        if (inside) {
-                            uint4 u[4];
+                    for (int half = 0; half < 2; ++half) {
+                        int o[4][4];
+                        float wt[4][4];
+                        uint4 u[4][4];
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                u[k] = tp.off[k] >= 0 ? __ldg(reinterpret_cast<const uint4*>(fb + (long long)tp.off[k] * P.feat_c + j * 8))
-                                                      : make_uint4(0u, 0u, 0u, 0u);
+                        for (int gi = 0; gi < 4; ++gi) {
+                            const int src = (half * 4 + gi) * 4 + (lane >> 3);
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
-                                if (tp.off[k] >= 0) {           // same order and arithmetic as flow_warp_kernel (warp.cu)
-                                    const uint32_t uu[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+                                o[gi][k] = __shfl_sync(0xffffffffu, tp.off[k], src);
+                                wt[gi][k] = __shfl_sync(0xffffffffu, tp.wgt[k], src);
+                            }
+                        }
+#pragma unroll
+                        for (int gi = 0; gi < 4; ++gi)
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                u[gi][k] = (o[gi][k] >= 0 && !(P.debug & 16)) ? __ldg(reinterpret_cast<const uint4*>(fb + (long long)o[gi][k] * P.feat_c + j * 8))
+                                                         : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                        for (int gi = 0; gi < 4; ++gi) {
+                            const int src = (half * 4 + gi) * 4 + (lane >> 3);
+                            float acc[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                if (o[gi][k] >= 0) {            // same order and arithmetic as flow_warp_kernel (warp.cu)
+                                    const uint32_t uu[4] = {u[gi][k].x, u[gi][k].y, u[gi][k].z, u[gi][k].w};
 #pragma unroll
                                     for (int e = 0; e < 4; ++e) {
                                         const float2 v2 = unpack_bf16(uu[e]);
-                                        acc[2 * e] = fmaf(v2.x, tp.wgt[k], acc[2 * e]);
-                                        acc[2 * e + 1] = fmaf(v2.y, tp.wgt[k], acc[2 * e + 1]);
+                                        acc[2 * e] = fmaf(v2.x, wt[gi][k], acc[2 * e]);
+                                        acc[2 * e + 1] = fmaf(v2.y, wt[gi][k], acc[2 * e + 1]);
                                     }
                                 }
                             }
+                            const uint32_t prow = slots0 + (uint32_t)fslot * (uint32_t)P.slot_bytes + (uint32_t)q * 4096u + (uint32_t)src * 128u;
+                            st_shared_v4(prow + (((uint32_t)j ^ ((uint32_t)src & 7u)) << 4), pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]),
+                                         pack_bf16(acc[4], acc[5]), pack_bf16(acc[6], acc[7]));
                         }
-                        st_shared_v4(row + (((uint32_t)j ^ ((uint32_t)lane & 7u)) << 4), pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]),
-                                     pack_bf16(acc[4], acc[5]), pack_bf16(acc[6], acc[7]));
                     }
                     fence_proxy_async();
                 }
                 __syncwarp();
-                if (lane == 0)
-                    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(full_lead + 8 * fslot) : "memory");
+                // plain arrive, like every other cross-CTA handshake here: the rows are in THIS CTA's shared memory, published
+                // to the async proxy by the fence above; a .release.cluster arrive costs a cluster-wide fence per row (4x the kernel)
+                if (lane == 0) mbar_arrive_cluster(full_lead + 8 * fslot);
+                if (stat) atomicAdd(&g_ring_stat[4], (unsigned long long)(ring_clock() - c1));
             }
             fwk.next();
             if (++fslot == kSlots) { fslot = 0; fphase ^= 1; }
@@ -453,7 +502,11 @@ __global__ void __launch_bounds__(kRingThreads, 1) conv_ring_kernel(const __grid
                 }
                 __syncwarp();
             }
+            const bool estat = (P.debug & 64) && blockIdx.x == 0 && blockIdx.y == 0 && warp == 4 && lane == 0;
+            const long long e0 = estat ? ring_clock() : 0;
             mbar_wait(tfull0 + 8 * s, sp, P.dbg, 17, dead);
+            const long long e1 = estat ? ring_clock() : 0;
+            if (estat) atomicAdd(&g_ring_stat[5], (unsigned long long)(e1 - e0));
             tc_fence_after();
             float v[64];
             if (valid) {
@@ -510,6 +563,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) conv_ring_kernel(const __grid
                     bulk_commit();
                 }
             }
+            if (estat) atomicAdd(&g_ring_stat[6], (unsigned long long)(ring_clock() - e1));
         }
         if (lane == 0) bulk_wait_all();                            // staged rows must be read out before shared memory goes away
         tc_fence_before();
@@ -697,7 +751,7 @@ int launch_conv_ring(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t st
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(ctas_x, p.groups);
     cfg.blockDim = dim3(kRingThreads);
-    cfg.dynamicSmemBytes = kRingSmem;
+    cfg.dynamicSmemBytes = kRingCtrl + 1024 + VSRB_RING_W_BYTES + P.num_slots * P.slot_bytes + kRingStageBytes;
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
     int na = 0;
@@ -719,3 +773,15 @@ int launch_conv_ring(const vsrb_conv_args* a, const ConvPlan& p, cudaStream_t st
 }
 
 }  // namespace vsrb
+
+extern "C" int vsrb_ring_debug_stats(uint64_t* out, int32_t reset) {
+    using namespace vsrb;
+    VSRB_CHECK_ARG(out, "ring_debug_stats: null output");
+    VSRB_CUDA(cudaDeviceSynchronize());
+    VSRB_CUDA(cudaMemcpyFromSymbol(out, g_ring_stat, sizeof(unsigned long long) * 8));
+    if (reset) {
+        unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        VSRB_CUDA(cudaMemcpyToSymbol(g_ring_stat, z, sizeof(z)));
+    }
+    return VSRB_OK;
+}

@@ -36,8 +36,10 @@ CLEAN_CHUNK = int(os.environ.get("VSRB_CLEAN_CHUNK", "30"))
 TAIL_CHUNK = int(os.environ.get("VSRB_TAIL_CHUNK", "8"))
 # the image stems (3 -> 64, 64+3 -> 64) read the frame as 3x3 im2col patches (K = 32 on the ring-walk kernel); 0 = nine K = 16 chunks
 STEM_PATCHES = os.environ.get("VSRB_STEM_PATCHES", "1") == "1"
-# flow_warp of the propagated features fused into the stem conv (basicvsr.py:52-58,66-73): the warped tensor never exists
-FUSED_WARP = os.environ.get("VSRB_FUSED_WARP", "1") == "1"
+# flow_warp of the propagated features fused into the stem conv (basicvsr.py:52-58,66-73): the warped tensor never exists.
+# Opt-in: bit-identical results and no flow_warp launches, but measured slightly slower than the two separate kernels
+# (stem 49 us vs 19 + 2 x 12 us at the cfg3 shape: DESIGN.md) - the separate path is the default.
+FUSED_WARP = os.environ.get("VSRB_FUSED_WARP", "0") == "1"
 
 
 # Opt-in narrow `sr` output (default None = fp32, the reference's dtype).  "fp16" halves and "uint8" quarters the bytes a
