@@ -206,6 +206,14 @@ int vsrb_flow_warp(const void* x, int64_t x_img_stride /* elements, 0 = dense */
                    int64_t flow_img_stride /* float2 elements, 0 = dense */, void* out, int32_t n,
                    int32_t h, int32_t w, int32_t c, int32_t dtype, int32_t padding_mode, void* stream);
 
+/* the same for `groups` x `imgs_per_group` images in ONE launch: image li of group g reads x + g * x_group_stride + li *
+ * x_img_stride (elements) and flow + g * flow_group_stride + li * flow_img_stride (float2 elements; group strides may be
+ * negative), out is dense [groups * imgs_per_group, h, w, c].  The two propagation directions of a time step
+ * (basicvsr.py:52-54 and :66-69) warp different frames of the feature bank with different flow fields.  bf16 only.     */
+int vsrb_flow_warp_groups(const void* x, int64_t x_img_stride, int64_t x_group_stride, const float* flow,
+                          int64_t flow_img_stride, int64_t flow_group_stride, void* out, int32_t imgs_per_group,
+                          int32_t groups, int32_t h, int32_t w, int32_t c, int32_t dtype, int32_t padding_mode, void* stream);
+
 /* ---- layout: module-boundary NCHW fp32 <-> internal NHWC ------------------------------
  * (the reference keeps NCHW throughout; these sit at the nn.Module boundary)            */
 int vsrb_nchw_to_nhwc(const float* src, void* dst, int32_t n, int32_t c, int32_t h, int32_t w,

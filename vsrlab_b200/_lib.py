@@ -93,6 +93,8 @@ SYMBOLS = {
     "vsrb_flow_warp_bwd": (C.c_int, [C.c_void_p] * 5 + [C.c_int32] * 6 + [C.c_void_p]),
     "vsrb_flow_warp": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                  C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "vsrb_flow_warp_groups": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p] + [C.c_int32] * 7 +
+                              [C.c_void_p]),
     "vsrb_nchw_to_nhwc": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p]),
     "vsrb_nhwc_to_nchw": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p]),
     "vsrb_spynet_pyramid_base": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 5 +

@@ -53,7 +53,8 @@ struct WarpTap {
 template <typename T, int TPP, bool kSplit = false>
 __global__ void __launch_bounds__(256) flow_warp_kernel(const T* __restrict__ x, long long x_stride,
                                                         const float2* __restrict__ flow, long long f_stride,
-                                                        T* __restrict__ out, int n, int h, int w, int border, int tpp_rt) {
+                                                        T* __restrict__ out, int n, int h, int w, int border, int tpp_rt,
+                                                        int ipg = 0x7fffffff, long long x_gstride = 0, long long f_gstride = 0) {
     __shared__ WarpTap taps[kWarpPix];
     constexpr int VEC = Vec16<T>::N;
     const int tpp = TPP > 0 ? TPP : tpp_rt;            // TPP == 0: any channel count (runtime divisions)
@@ -67,11 +68,14 @@ __global__ void __launch_bounds__(256) flow_warp_kernel(const T* __restrict__ x,
         if (pix < total) {
             const int img = pix / hw, r = pix - img * hw;
             const int yy = r / w, xx = r - yy * w;
-            const float2 f = __ldg(flow + (long long)img * f_stride + r);
+            // images come in groups of `ipg` (the two propagation directions read different frames of the feature bank
+            // and different flow fields): image = group * ipg + li
+            const int grp = img / ipg, li = img - grp * ipg;
+            const float2 f = __ldg(flow + (long long)grp * f_gstride + (long long)li * f_stride + r);
             float ix, iy;
             sample_pos((float)xx + f.x, (float)yy + f.y, w, h, ix, iy);
             make_taps(ix, iy, w, h, border, taps[threadIdx.x].t);
-            taps[threadIdx.x].base = (long long)img * x_stride;
+            taps[threadIdx.x].base = (long long)grp * x_gstride + (long long)li * x_stride;
         }
     }
     __syncthreads();
@@ -117,18 +121,18 @@ __global__ void __launch_bounds__(256) flow_warp_kernel(const T* __restrict__ x,
 
 template <typename T>
 static int launch_flow_warp(const T* x, long long xs, const float2* flow, long long fs, T* out, int n, int h, int w, int c,
-                            int border, cudaStream_t s) {
+                            int border, cudaStream_t s, int ipg = 0x7fffffff, long long xg = 0, long long fg = 0) {
     constexpr int VEC = Vec16<T>::N;
     const int tpp = c / VEC;
     const int blocks = (int)(((long long)n * h * w + kWarpPix - 1) / kWarpPix);
     switch (tpp) {
-        case 1: flow_warp_kernel<T, 1><<<blocks, 256, 0, s>>>(x, xs, flow, fs, out, n, h, w, border, tpp); break;
-        case 2: flow_warp_kernel<T, 2><<<blocks, 256, 0, s>>>(x, xs, flow, fs, out, n, h, w, border, tpp); break;
-        case 4: flow_warp_kernel<T, 4><<<blocks, 256, 0, s>>>(x, xs, flow, fs, out, n, h, w, border, tpp); break;
-        case 8: flow_warp_kernel<T, 8><<<blocks, 256, 0, s>>>(x, xs, flow, fs, out, n, h, w, border, tpp); break;
-        case 16: flow_warp_kernel<T, 16><<<blocks, 256, 0, s>>>(x, xs, flow, fs, out, n, h, w, border, tpp); break;
-        case 32: flow_warp_kernel<T, 32><<<blocks, 256, 0, s>>>(x, xs, flow, fs, out, n, h, w, border, tpp); break;
-        default: flow_warp_kernel<T, 0><<<blocks, 256, 0, s>>>(x, xs, flow, fs, out, n, h, w, border, tpp); break;
+        case 1: flow_warp_kernel<T, 1><<<blocks, 256, 0, s>>>(x, xs, flow, fs, out, n, h, w, border, tpp, ipg, xg, fg); break;
+        case 2: flow_warp_kernel<T, 2><<<blocks, 256, 0, s>>>(x, xs, flow, fs, out, n, h, w, border, tpp, ipg, xg, fg); break;
+        case 4: flow_warp_kernel<T, 4><<<blocks, 256, 0, s>>>(x, xs, flow, fs, out, n, h, w, border, tpp, ipg, xg, fg); break;
+        case 8: flow_warp_kernel<T, 8><<<blocks, 256, 0, s>>>(x, xs, flow, fs, out, n, h, w, border, tpp, ipg, xg, fg); break;
+        case 16: flow_warp_kernel<T, 16><<<blocks, 256, 0, s>>>(x, xs, flow, fs, out, n, h, w, border, tpp, ipg, xg, fg); break;
+        case 32: flow_warp_kernel<T, 32><<<blocks, 256, 0, s>>>(x, xs, flow, fs, out, n, h, w, border, tpp, ipg, xg, fg); break;
+        default: flow_warp_kernel<T, 0><<<blocks, 256, 0, s>>>(x, xs, flow, fs, out, n, h, w, border, tpp, ipg, xg, fg); break;
     }
     return VSRB_OK;
 }
@@ -457,6 +461,23 @@ int vsrb_flow_warp(const void* x, int64_t x_img_stride, const float* flow, int64
     } else {
         VSRB_CHECK_ARG(false, "flow_warp: bad dtype");
     }
+    if (rc != VSRB_OK) return rc;
+    VSRB_LAUNCH_CHECK();
+    return VSRB_OK;
+}
+
+int vsrb_flow_warp_groups(const void* x, int64_t x_img_stride, int64_t x_group_stride, const float* flow, int64_t flow_img_stride,
+                          int64_t flow_group_stride, void* out, int32_t imgs_per_group, int32_t groups, int32_t h, int32_t w, int32_t c,
+                          int32_t dtype, int32_t padding_mode, void* stream) {
+    VSRB_CHECK_ARG(x && flow && out && imgs_per_group >= 1 && groups >= 1 && h >= 1 && w >= 1, "flow_warp_groups: bad arguments");
+    VSRB_CHECK_ARG(padding_mode == VSRB_PAD_ZEROS || padding_mode == VSRB_PAD_BORDER, "flow_warp_groups: bad padding mode");
+    VSRB_CHECK_ARG(dtype == VSRB_BF16 && c % 8 == 0, "flow_warp_groups: bf16 NHWC with c %% 8 == 0 only");
+    VSRB_CHECK_ARG((long long)imgs_per_group * groups * h * w < (1LL << 31), "flow_warp_groups: more than 2^31 pixels in one call");
+    const long long xs = x_img_stride ? x_img_stride : (long long)h * w * c;
+    const long long fs = flow_img_stride ? flow_img_stride : (long long)h * w;
+    int rc = launch_flow_warp<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(x), xs, reinterpret_cast<const float2*>(flow), fs,
+                                             reinterpret_cast<__nv_bfloat16*>(out), imgs_per_group * groups, h, w, c, padding_mode,
+                                             (cudaStream_t)stream, imgs_per_group, x_group_stride, flow_group_stride);
     if (rc != VSRB_OK) return rc;
     VSRB_LAUNCH_CHECK();
     return VSRB_OK;

@@ -555,6 +555,13 @@ def _basicvsr_run(bv, lrs: torch.Tensor, dt: int, x_nhwc: Optional[torch.Tensor]
             warped.zero_()
         elif fused:
             pass
+        elif dt == BF16:
+            # both directions in one launch: backward chain = bank frame t-s warped by flows_b[t-1-s], forward chain = bank
+            # frame s-1 warped by flows_f[s-1] (basicvsr.py:52-54, 66-69)
+            xb, xf = fbk.data_ptr() + (t - s) * frame_el * es, ffw.data_ptr() + (s - 1) * frame_el * es
+            wb, wf = flows_b.data_ptr() + (t - 1 - s) * h * w * 8, flows_f.data_ptr() + (s - 1) * h * w * 8
+            ops.flow_warp_groups(xb, (t * frame_el, (xf - xb) // es), wb, ((t - 1) * h * w, (wf - wb) // 8), warped, n, 2, h, w, mid_c, dt,
+                                 PAD_ZEROS)
         else:
             ops.flow_warp(fbk.data_ptr() + (t - s) * frame_el * es, flows_b.data_ptr() + (t - 1 - s) * h * w * 8, warped[:n],
                           n, h, w, mid_c, dt, PAD_ZEROS, x_img_stride=t * frame_el, flow_img_stride=(t - 1) * h * w)

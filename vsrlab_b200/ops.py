@@ -211,6 +211,14 @@ def flow_warp(x, flow, out, n: int, h: int, w: int, c: int, dtype: int, padding:
                                         _stream()), "vsrb_flow_warp")
 
 
+def flow_warp_groups(x, x_strides: Tuple[int, int], flow, flow_strides: Tuple[int, int], out, imgs_per_group: int, groups: int, h: int,
+                     w: int, c: int, dtype: int, padding: int = PAD_ZEROS) -> None:
+    """One launch for `groups` sets of images that read different bases (x / flow: raw addresses + (image, group) strides)."""
+    with _Timed("flow_warp", float(imgs_per_group * groups) * h * w * (2 * c * ESIZE[dtype] + 8)):
+        L.check(L.load().vsrb_flow_warp_groups(_p(x), x_strides[0], x_strides[1], _p(flow), flow_strides[0], flow_strides[1], _p(out),
+                                               imgs_per_group, groups, h, w, c, dtype, padding, _stream()), "vsrb_flow_warp_groups")
+
+
 def nchw_to_nhwc(src: torch.Tensor, dst: torch.Tensor, n: int, c: int, h: int, w: int, c_dst: int, dtype: int) -> None:
     L.check(L.load().vsrb_nchw_to_nhwc(_p(src), _p(dst), n, c, h, w, c_dst, dtype, _stream()), "vsrb_nchw_to_nhwc")
 
