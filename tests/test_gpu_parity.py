@@ -474,7 +474,7 @@ def test_multi_chunk_schedule_matches_oracle(dev, graphs):
 
 
 def test_default_chunks_more_frames_than_a_chunk(dev):
-    """Default chunk sizes (30 / 8) with 2 clips x 17 frames: B = 34 frames -> cleaner chunks 30 + 4, tail 8+8+8+8+2."""
+    """Default chunk sizes (60 / 15) with 2 clips x 17 frames: B = 34 frames -> one cleaner chunk, tail chunks 15 + 15 + 4."""
     net, x, sr_ref, lq_ref = _oracle_case(1, (2, 17, 3, 24, 40), 41)
     _check_modes(net.to(dev), x, sr_ref, lq_ref, dev)
 

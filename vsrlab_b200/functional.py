@@ -32,8 +32,8 @@ _NAMES = {"bf16": BF16, "fp32": _FP32, "f32": _FP32, "fp32_ffma": F32, "fp32_x3"
 
 # tunables: frames / images per launch batch.  Measured on B200 (gpurun_out bench4*): the ~8 us fixed cost per
 # launch outweighs L2 residency, so batches are large; the tail is capped by the HR buffers (118 MB per frame).
-CLEAN_CHUNK = int(os.environ.get("VSRB_CLEAN_CHUNK", "30"))
-TAIL_CHUNK = int(os.environ.get("VSRB_TAIL_CHUNK", "8"))
+CLEAN_CHUNK = int(os.environ.get("VSRB_CLEAN_CHUNK", "60"))
+TAIL_CHUNK = int(os.environ.get("VSRB_TAIL_CHUNK", "15"))
 # the image stems (3 -> 64, 64+3 -> 64) read the frame as 3x3 im2col patches (K = 32 on the ring-walk kernel); 0 = nine K = 16 chunks
 STEM_PATCHES = os.environ.get("VSRB_STEM_PATCHES", "1") == "1"
 # flow_warp of the propagated features fused into the stem conv (basicvsr.py:52-58,66-73): the warped tensor never exists.
