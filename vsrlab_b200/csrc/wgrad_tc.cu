@@ -5,10 +5,15 @@
 // is a GEMM whose K dimension is the pixel index.  Both operands are "MN-major" for UMMA: a TMA box of
 // pixels x 64 channels lands in shared memory as rows of 128 bytes (128B swizzle) = K rows of 64
 // contiguous M (resp. N) elements, which is exactly the canonical MN-major layout, so no transpose is needed:
-//   A (M side) = the activation x, shifted by the filter tap: the same three kx-shifted halo copies the forward
-//                conv uses; a tap (ky,kx) is copy kx starting ky*16 rows further down.  Two taps are issued as ONE
-//                M=128 MMA: the descriptor's leading-dimension byte offset (the distance between consecutive
-//                64-element M blocks) points from the first tap's tile to the second tap's tile.
+//   A (M side) = the activation x, shifted by the filter tap.  ONE halo box of (4 + 2) rows x (16 + 2) pixels per tile:
+//                an MN-major SW128 operand may start at any 128-byte K row of its tile (tools/umma_mn_offset_test.cu: the
+//                hardware swizzles on absolute address bits), so tap (ky, kx) of K step ks is simply the 16 consecutive
+//                pixels that start at pixel ((ky + ks) * 18 + kx) of the box.  (Round 1 loaded three kx-shifted copies, 2.7x
+//                the unique bytes.  Measured after the change: same 85 us for 120 x 64x64 images - VSRB_WG_DEBUG shows the
+//                kernel is MMA-ISSUE bound, not load bound: twenty N = 64 MMAs of ~96 cycles per 64-pixel tile = 1.1 us,
+//                57 us with the final atomics skipped and no MMAs at all.)  Two taps are issued as ONE M=128 MMA:
+//                the descriptor's leading-dimension byte offset (the distance between consecutive 64-element M blocks)
+//                points from the first tap's window to the second tap's window (one pixel, or one box row).
 //   B (N side) = the output gradient dz (N = 64 output channels).
 //   D          = five accumulators of 128 x 64 fp32 in TMEM (9 taps = 4 pairs + 1 single), kept for the whole
 //                persistent CTA; K advances 16 pixels (2048 bytes) per MMA.
@@ -25,13 +30,12 @@ namespace vsrb {
 
 static constexpr int kWgThreads = 256;
 static constexpr int kWgTW = 16, kWgRows = 4;                               // 64-pixel tiles: four K=16 steps
-static constexpr int kWgCopyBytes = (kWgRows + 2) * kWgTW * 128;            // one kx-shifted halo copy: 12 KiB
+static constexpr int kWgXW = kWgTW + 2;                                     // halo box width in pixels
+static constexpr int kWgXBytes = (kWgRows + 2) * kWgXW * 128;               // the halo box: 13.5 KiB
+static constexpr int kWgCopyBytes = 14 * 1024;                              // ... padded so that the dz tile stays 1 KiB aligned
 static constexpr int kWgZBytes = kWgRows * kWgTW * 128;                     // dz tile: 8 KiB
-static constexpr int kWgStageBytes = 3 * kWgCopyBytes + kWgZBytes;          // 44 KiB
-// ncu (120 x 64 x 64 images, 64 -> 64): 60 us, 346 MB through the TMA at 5.8 TB/s - the three kx-shifted copies are 2.7x
-// the unique bytes - and the tensor pipe active 32 % of the time: load-bound.  Four 44 KiB stages of 64 pixels keep more
-// loads in flight than two 76 KiB stages of 128; building the kx copies on chip from one load is the known next step.
-static constexpr int kWgStages = 4;
+static constexpr int kWgStageBytes = kWgCopyBytes + kWgZBytes;              // 22 KiB
+static constexpr int kWgStages = 8;
 static constexpr int kWgSmem = 1024 + 1024 + kWgStages * kWgStageBytes;
 
 static constexpr int kWgMaxChunks = 16;
@@ -83,7 +87,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
     const int my_tiles = (P.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
     if (warp == 0) {
-        // ---- producer: three kx-shifted halo copies of x and the dz tile per pixel tile ----
+        // ---- producer: one halo box of x and the dz tile per pixel tile ----
         int slot = 0;
         uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
@@ -97,10 +101,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
             if (elect_one() && (P.debug & 4)) {
                 mbar_arrive(full0 + 8 * slot);                // timing decomposition: no loads
             } else if (elect_one()) {
-                mbar_expect_tx(full0 + 8 * slot, kWgStageBytes);
-                for (int kx = 0; kx < 3; ++kx)
-                    tma_load_4d(&P.xmap[chunk], full0 + 8 * slot, sa + kx * kWgCopyBytes, P.c0, tx * kWgTW + kx - 1, ty * kWgRows - 1, img);
-                tma_load_4d(&P.zmap[chunk], full0 + 8 * slot, sa + 3 * kWgCopyBytes, P.n0, tx * kWgTW, ty * kWgRows, img);
+                mbar_expect_tx(full0 + 8 * slot, kWgXBytes + kWgZBytes);
+                tma_load_4d(&P.xmap[chunk], full0 + 8 * slot, sa, P.c0, tx * kWgTW - 1, ty * kWgRows - 1, img);
+                tma_load_4d(&P.zmap[chunk], full0 + 8 * slot, sa + kWgCopyBytes, P.n0, tx * kWgTW, ty * kWgRows, img);
             }
             __syncwarp();
             if (++slot == kWgStages) { slot = 0; phase ^= 1; }
@@ -117,19 +120,20 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
             mbar_wait(full0 + 8 * slot, phase, P.dbg, 12, dead);
             tc_fence_after();
             if (elect_one()) {
-                const uint32_t zb = sa + 3 * kWgCopyBytes;
+                const uint32_t zb = sa + kWgCopyBytes;
+                constexpr uint32_t kRow = kWgXW * 128u;            // one box row: 18 pixels
 #pragma unroll
                 for (int ks = 0; ks < ((P.debug & 2) ? 0 : kWgRows); ++ks) {
                     const uint64_t bd = mn_desc(zb + ks * 2048u, 0u);
                     const uint32_t acc = (first && ks == 0) ? 0u : 1u;
-                    // pairs (ky,0)&(ky,1): second tile lives one halo copy further
+                    // pairs (ky,0)&(ky,1): the second tap's window starts one pixel further
 #pragma unroll
                     for (int ky = 0; ky < 3; ++ky)
-                        umma_bf16(tmem_base + ky * 64, mn_desc(sa + (ky + ks) * 2048u, kWgCopyBytes), bd, idesc, acc);
-                    // pair (0,2)&(1,2): same copy, one filter row (16 pixels = 2048 B) further
-                    umma_bf16(tmem_base + 3 * 64, mn_desc(sa + 2 * kWgCopyBytes + ks * 2048u, 2048u), bd, idesc, acc);
+                        umma_bf16(tmem_base + ky * 64, mn_desc(sa + (ky + ks) * kRow, 128u), bd, idesc, acc);
+                    // pair (0,2)&(1,2): two pixels in, the second tap one box row further down
+                    umma_bf16(tmem_base + 3 * 64, mn_desc(sa + ks * kRow + 256u, kRow), bd, idesc, acc);
                     // (2,2) & a don't-care second half
-                    umma_bf16(tmem_base + 4 * 64, mn_desc(sa + 2 * kWgCopyBytes + (2 + ks) * 2048u, 2048u), bd, idesc, acc);
+                    umma_bf16(tmem_base + 4 * 64, mn_desc(sa + (2 + ks) * kRow + 256u, 128u), bd, idesc, acc);
                 }
                 umma_commit(empty0 + 8 * slot);
             }
@@ -307,7 +311,7 @@ int launch_wgrad_tc_multi(const void* const* xs, int x_c, int c0, int ci_off, co
         {
             cuuint64_t dims[4] = {(cuuint64_t)x_c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)batch};
             cuuint64_t strides[3] = {(cuuint64_t)x_c * 2, (cuuint64_t)w * x_c * 2, (cuuint64_t)h * w * x_c * 2};
-            cuuint32_t box[4] = {64, kWgTW, kWgRows + 2, 1};
+            cuuint32_t box[4] = {64, kWgXW, kWgRows + 2, 1};
             CUresult r = encode(&P.xmap[k], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(xs[k]), dims, strides, box, estr,
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
