@@ -373,11 +373,14 @@ __global__ void __launch_bounds__(kRingThreads, 1) conv_ring_kernel(const __grid
             ring_range(P.rows_g, P.H, P.cols, P.rpc, n_ranges, pair0 + (int)crank * 4 + q, lo, hi);
             wk.init(lo, hi, P.H);
         }
+        const uint32_t stg = stg0 + (uint32_t)(eh * 4 + q) * 4096u;       // this warp's staging row
         // ---- fused warp: this warp also PRODUCES the operand row of its quarter for the steps t with (t & 1) == eh -------
-        // Measured (tools/stem_bench.py, VSRB_RING_DEBUG=64): a row costs the warp ~6 000 cycles of shuffles, FMAs, packs and
-        // stores even without its global loads (+1 100 with them), i.e. the gather is bound by ONE warp's instruction latency -
-        // the stand-alone flow_warp kernel spreads the same work over 64 warps per SM.  Splitting a row between the two warps
-        // of a quarter made it worse (each half still pays the fixed flow -> taps -> loads chain).
+        // Measured (tools/stem_bench.py, VSRB_RING_DEBUG=64, ncu source view profiles/r2_fused_stem_hot_sass.txt): a row costs
+        // its warp ~7 000 cycles - flow load -> taps -> two batches of tap loads are three dependent L2 round trips, plus
+        // ~600 instructions issued by one warp - against a budget of ~1 800 (two MMA steps minus the epilogue of a row).  The
+        // stand-alone flow_warp kernel hides the same latency with 64 warps per SM.  Splitting a row between the two warps of
+        // a quarter made it worse (each half still pays the fixed chain); shared-memory tap exchange instead of shuffles and
+        // leaving L1 more room changed nothing.
         RingWalk fwk = wk;                        // cursor over the same items, kGatherAhead steps ahead of the epilogue
         int fslot = 0;
         uint32_t fphase = 0;
@@ -407,7 +410,16 @@ __global__ void __launch_bounds__(kRingThreads, 1) conv_ring_kernel(const __grid
                         make_taps(ix, iy, P.W, P.H, 0, tp);
                     }
                     const __nv_bfloat16* fb = P.feat + (long long)g * P.feat_group_stride + (long long)li * P.feat_img_stride;
-                    // ... and 8 lanes per pixel for the gathers: one load instruction reads four whole 128-byte pixel rows
+                    // ... and 8 lanes per pixel for the gathers: one load instruction reads four whole 128-byte pixel rows.
+                    // The tap tables change hands through this warp's (idle) staging row rather than 64 shuffles per row (measured
+                    // neutral: ncu's source view puts the row's stalls on the first uses of the flow and tap loads - three
+                    // dependent L2 round trips per row - not on instruction issue).
+                    if (lane == 0) bulk_wait_read<0>();            // a previous output row may still be read from there by the TMA
+                    __syncwarp();
+                    st_shared_v4(stg + (uint32_t)lane * 32u, (uint32_t)tp.off[0], (uint32_t)tp.off[1], (uint32_t)tp.off[2], (uint32_t)tp.off[3]);
+                    st_shared_v4(stg + (uint32_t)lane * 32u + 16u, __float_as_uint(tp.wgt[0]), __float_as_uint(tp.wgt[1]),
+                                 __float_as_uint(tp.wgt[2]), __float_as_uint(tp.wgt[3]));
+                    __syncwarp();
                     const int j = lane & 7;
                     // two batches of four pixel groups: all sixteen 16-byte loads of a batch are issued before the first result is
                     // used (the shared-memory stores below are compiler barriers: without the explicit batching every group paid
@@ -420,18 +432,17 @@ __global__ void __launch_bounds__(kRingThreads, 1) conv_ring_kernel(const __grid
 #pragma unroll
                         for (int gi = 0; gi < 4; ++gi) {
                             const int src = (half * 4 + gi) * 4 + (lane >> 3);
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                o[gi][k] = __shfl_sync(0xffffffffu, tp.off[k], src);
-                                wt[gi][k] = __shfl_sync(0xffffffffu, tp.wgt[k], src);
-                            }
+                            const uint4 to = ld_shared_v4(stg + (uint32_t)src * 32u), tw = ld_shared_v4(stg + (uint32_t)src * 32u + 16u);
+                            o[gi][0] = (int)to.x; o[gi][1] = (int)to.y; o[gi][2] = (int)to.z; o[gi][3] = (int)to.w;
+                            wt[gi][0] = __uint_as_float(tw.x); wt[gi][1] = __uint_as_float(tw.y);
+                            wt[gi][2] = __uint_as_float(tw.z); wt[gi][3] = __uint_as_float(tw.w);
                         }
 #pragma unroll
                         for (int gi = 0; gi < 4; ++gi)
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
                                 u[gi][k] = (o[gi][k] >= 0 && !(P.debug & 16)) ? __ldg(reinterpret_cast<const uint4*>(fb + (long long)o[gi][k] * P.feat_c + j * 8))
-                                                         : make_uint4(0u, 0u, 0u, 0u);
+                                                                             : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
                         for (int gi = 0; gi < 4; ++gi) {
                             const int src = (half * 4 + gi) * 4 + (lane >> 3);
@@ -467,7 +478,6 @@ __global__ void __launch_bounds__(kRingThreads, 1) conv_ring_kernel(const __grid
             if (++fslot == kSlots) { fslot = 0; fphase ^= 1; }
         };
         const float act_k = P.act_k;
-        const uint32_t stg = stg0 + (uint32_t)(eh * 4 + q) * 4096u;       // this warp's staging row
         const uint32_t rbar = rbar0 + 8 * (eh * 4 + q);
         uint32_t rphase = 0;
         griddep_wait();        // this role reads / writes global memory other kernels on the stream own
