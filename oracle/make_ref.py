@@ -46,6 +46,7 @@ FILES = [
 # (tests/test_gpu_scripts.py, tools/run_reference_script.py): the entry scripts and the training runtime they import.
 CALLER_FILES = [
     "train.py",
+    "train_gan.py",
     "test.py",
     "core/utils.py",
     "core/losses.py",

@@ -2,7 +2,7 @@
 
 Covers what santurini/vsrlab uses: `@hydra.main(config_path, config_name, version_base)` with defaults-list composition
 (config groups, nested defaults relative to the including file, `_self_`, `# @package _global_` overlays such as
-`+experiment=basic`), command-line overrides (`a.b=v`, `+a.b=v`, `~a.b`, `group=option`, `group/sub=option`), the
+`+experiment=basic`, their `override /group: option` lines), command-line overrides (`a.b=v`, `+a.b=v`, `~a.b`, `group=option`, `group/sub=option`), the
 `hydra.job.env_set` block of conf/hydra/default.yaml, and `hydra.utils.instantiate` (see utils.py).  The composed config
 is an `omegaconf.DictConfig` of the sibling shim.  Configs may be `.yaml` or `.json` files."""
 from __future__ import annotations
@@ -68,7 +68,9 @@ def _compose_file(cfg_dir: Path, rel: str, package: str, group_choice: dict, ext
         if isinstance(d, str):
             d = {d.rsplit("/", 1)[0]: d.rsplit("/", 1)[1]} if "/" in d else {d: None}
         (grp, opt), = d.items()
-        grp = grp.replace("optional ", "").replace("override ", "").strip()
+        if grp.startswith("override "):
+            continue                                      # changes a choice made elsewhere; collected by compose()
+        grp = grp.replace("optional ", "").strip()
         absolute = grp.startswith("/")
         grp_path = grp.lstrip("/") if absolute else (f"{group_dir}/{grp}" if group_dir else grp)
         opt = group_choice.get(grp_path, opt)
@@ -113,6 +115,14 @@ def compose(config_path: str, config_name: str, overrides: Optional[List[str]] =
                 group_choice[key] = raw
         else:
             value_ops.append(("add" if add else "set", key, yaml.load(raw, Loader=_Loader) if raw != "" else ""))
+    for e in extra:                                       # `override /group: option` lines of appended overlays (+experiment=...)
+        (grp, opt), = e.items()
+        content, _ = _load_file(cfg_dir, f"{grp}/{opt}")
+        for d in content.get("defaults", []) or []:
+            if isinstance(d, dict):
+                (k, v), = d.items()
+                if k.startswith("override "):
+                    group_choice.setdefault(k[len("override "):].strip().lstrip("/"), v)
     merged = _compose_file(cfg_dir, config_name, "", group_choice, extra)
     for op, key, val in value_ops:
         if op == "del":

@@ -48,10 +48,42 @@ def amplify_flow(sd, prefix, gain):
     return sd
 
 
+def gan_golden():
+    """UNetDiscriminator: eval-mode logits, train-mode logits (one power iteration) and gradients."""
+    import importlib
+    UNetDiscriminator = importlib.import_module("vsrlab.vsr.models.RealBasicVSR.modules.unet-discriminator").UNetDiscriminator
+    out = {}
+    torch.manual_seed(31)
+    D = UNetDiscriminator(3, 16)
+    cs, ck = sd_checksum(D.state_dict())
+    out["sd_checksum"], out["sd_keys"] = cs, ck
+    img = torch.rand(2, 3, 32, 40, generator=torch.Generator().manual_seed(32))
+    out["img"] = img.numpy()
+    D.eval()
+    with torch.no_grad():
+        out["logits_eval"] = D(img).numpy()
+    D.train()
+    x = img.clone().requires_grad_(True)
+    y = D(x)
+    out["logits_train"] = y.detach().numpy()
+    w = torch.rand(y.shape, generator=torch.Generator().manual_seed(33)) - 0.5
+    (y * w).sum().backward()
+    out["cot"] = w.numpy()
+    out["grad_img"] = x.grad.numpy()
+    for k in ("conv_0.weight", "conv_0.bias", "conv_2.conv.weight_orig", "conv_5.conv.weight_orig", "conv_9.weight"):
+        out["grad." + k] = dict(D.named_parameters())[k].grad.numpy()
+    out["u_after." + "conv_2"] = D.conv_2.conv.weight_u.numpy()
+    np.savez_compressed(HERE / "gan.npz", **out)
+
+
 def main():
     warnings.filterwarnings("ignore")
     torch.set_num_threads(8)
     load_reference()
+    if "--only-gan" in sys.argv:
+        gan_golden()
+        return
+    gan_golden()
     from vsrlab.core.modules.conv import ResidualBlock
     from vsrlab.core.modules.upsampling import PixelShufflePack
     from vsrlab.vsr.models.RealBasicVSR.modules.basicvsr import BasicVSR

@@ -1,4 +1,4 @@
-"""the reference's own `train.py` and `test.py`, unchanged, on top of the drop-in package.
+"""the reference's own `train.py`, `train_gan.py` and `test.py`, unchanged, on top of the drop-in package.
 
 The scripts and the caller modules they import are the reference's (from /root/reference where present, else the
 byte-compiled copies under oracle/_ref); hydra / omegaconf / kornia / piqa are the minimal shims under shims/; the data
@@ -55,6 +55,28 @@ def test_reference_train_py_runs_unchanged(project):
     # Adam state holds one step for every trainable tensor
     steps = {int(s["step"]) for s in ckpt["optimizer_state_dict"]["state"].values()}
     assert steps == {1}
+
+
+def test_reference_train_gan_py_runs_unchanged(project):
+    """`train_gan.py +experiment=basic_gan` with the drop-in generator AND discriminator.  Environment
+    overrides: the experiment's `train.restore` names a checkpoint on the author's disk (null here), the VGG weights of
+    PerceptualLoss need a download (`train.perceptual_loss=null` takes the script's own dummy_loss branch, train_gan.py:105)."""
+    import run_reference_script as R
+    ov = ["+experiment=basic_gan", "train.restore=null", "train.perceptual_loss=null", "train.model.pretrained_flow=false",
+          "~train.scheduler.generator.verbose", "~train.scheduler.discriminator.verbose",
+          "train.max_epochs=1", "train.data.batch_size=2", "train.num_grad_acc=2", "train.data.num_workers=1",
+          "train.data.datasets.train.length=4", "train.data.datasets.val.length=2", "train.data.datasets.train.seq=5",
+          "train.data.datasets.train.lr_size=[32,32]", "train.model.cleaning_blocks=1", "train.model.res_blocks=1",
+          "core.run_id=dropin_gan"]
+    r = R.run("train_gan", ov, project, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + "\n" + r.stderr[-3000:]
+    assert "build discriminator" in r.stdout and "Start Training" in r.stdout and "Epoch 0 - Elapsed time" in r.stdout
+    run_dir = project / "storage" / "video-super-resolution" / "dropin_gan"
+    ckpt = torch.load(run_dir / "checkpoint.tar", map_location="cpu")
+    assert all(torch.isfinite(v).all() for v in ckpt["model_state_dict"].values() if v.is_floating_point())
+    # 4 clips in loader batches of batch_size // num_grad_acc = 1 (core/utils.py:205), accumulated by 2: two generator
+    # steps, neither skipped by the GradScaler (finite gradients through the discriminator under fp16 autocast)
+    assert {int(s["step"]) for s in ckpt["optimizer_state_dict"]["state"].values()} == {2}
 
 
 def test_reference_test_py_runs_unchanged(project):

@@ -17,6 +17,22 @@ def test_seeded_ctor_reproduces_reference_init(golden, kind, fixture):
     np.testing.assert_allclose(cs, g["sd_checksum"], rtol=0, atol=1e-9)
 
 
+def test_discriminator_ctor_reproduces_reference_init(golden):
+    """UNetDiscriminator (gan.yaml:17-20): same keys (spectral-norm parametrisation included) and seeded values."""
+    import importlib
+    g = golden("gan")
+    torch.manual_seed(31)
+    D = importlib.import_module("vsrlab.vsr.models.RealBasicVSR.modules.unet-discriminator").UNetDiscriminator(3, 16)
+    sd = D.state_dict()
+    keys = sorted(sd.keys())
+    assert keys == [str(k) for k in g["sd_keys"]]
+    cs = np.array([[sd[k].double().sum().item(), (sd[k].double() ** 2).sum().item()] for k in keys])
+    np.testing.assert_allclose(cs, g["sd_checksum"], rtol=0, atol=1e-9)
+    assert [n for n, _ in D.named_parameters()][:3] == ["conv_0.weight", "conv_0.bias", "conv_1.conv.weight_orig"]
+    with pytest.raises(Exception):                       # no CPU fallback here either
+        D(torch.rand(1, 3, 16, 16))
+
+
 def test_state_dict_layout_and_ctor_contract():
     from vsrlab.vsr.models.RealBasicVSR.realbasicvsr import RealBasicVSR
     m = RealBasicVSR(cleaning_blocks=5, mid_channels=64, upscale=4, res_blocks=5, pretrained_flow=False, train_flow=True)

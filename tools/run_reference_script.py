@@ -1,4 +1,4 @@
-"""Run one of the reference's OWN entry scripts (train.py / test.py), unchanged, on top of the drop-in `vsrlab` package.
+"""Run one of the reference's OWN entry scripts (train.py / train_gan.py / test.py), unchanged, on top of the drop-in `vsrlab` package.
 
     python tools/run_reference_script.py train --project /tmp/proj -- +experiment=basic train.model.pretrained_flow=false ...
 
@@ -81,7 +81,7 @@ def main():
         i = argv.index("--")
         argv, overrides = argv[:i], argv[i + 1:]
     ap = argparse.ArgumentParser()
-    ap.add_argument("script", choices=["train", "test"])
+    ap.add_argument("script", choices=["train", "train_gan", "test"])
     ap.add_argument("--project", default="")
     a = ap.parse_args(argv)
     a.overrides = overrides

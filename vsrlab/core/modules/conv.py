@@ -7,6 +7,7 @@ hands raw device pointers to the sm_100a kernels through the C-ABI.
 Only the attribute names, the order in which the convolutions are created (it fixes the order of the RNG draws of a
 seeded constructor) and the call signatures are the reference's; everything a forward does happens in vsrlab_b200."""
 from torch import nn
+from torch.nn.utils import spectral_norm
 
 from vsrlab_b200 import functional as VF
 
@@ -51,3 +52,16 @@ class ResidualBlock(nn.Module):
 
     def forward(self, x):
         return VF.residual_stack(x, self.conv[0], list(self.res_block))
+
+
+class SpectralConv(nn.Module):
+    """Bias-free conv under `torch.nn.utils.spectral_norm` (reference conv.py:6-13; the building block of the GAN
+    discriminator, unet-discriminator.py:8-15).  Same parametrisation as the reference, hence the same state_dict keys
+    (`conv.weight_orig`, `conv.weight_u`, `conv.weight_v`); 3x3 stride 1 and 4x4 stride 2 run on the sm_100a kernels."""
+
+    def __init__(self, in_ch, out_ch, ks=3, stride=1, pad=1):
+        super().__init__()
+        self.conv = spectral_norm(nn.Conv2d(in_ch, out_ch, ks, stride, pad, bias=False))
+
+    def forward(self, x):
+        return VF.spectral_conv2d(x, self)

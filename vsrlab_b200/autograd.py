@@ -230,6 +230,9 @@ class WarpFn(torch.autograd.Function):
 # the modules, differentiable
 # --------------------------------------------------------------------------------------
 def conv(mod, inputs: Sequence[torch.Tensor], segs, act="none", slope=0.1, pixshuf=0, residual=None) -> torch.Tensor:
+    for t in (*inputs, *([] if residual is None else [residual])):
+        if t.dtype != torch.bfloat16:      # e.g. a torch op in between ran under autocast, whose fp32 list includes upsampling
+            raise VsrbError(f"autograd.conv: activations must be bf16, got {t.dtype}")
     token, box = _weight_token(mod, segs)
     if token is not None:      # the weight's gradient flows through the token's node; this use sees the weight as a constant
         return ConvFn.apply(mod.weight.detach(), None if mod.bias is None else mod.bias.detach(), token, box, mod, tuple(segs), act, slope,
@@ -465,3 +468,91 @@ def realbasicvsr(model, lr: torch.Tensor):
     with torch.no_grad():
         lr.copy_(lq)
     return sr, lq
+
+
+# --------------------------------------------------------------------------------------
+# GAN discriminator: SpectralConv / UNetDiscriminator on the same conv kernels
+# --------------------------------------------------------------------------------------
+class _DerivedConv:
+    """What ConvFn / PackedConv read from an nn.Conv2d, for a weight that is DERIVED from the module's parameters on every
+    call (spectral normalisation; the 3x3 re-layout of a 4x4 stride-2 filter).  One holder lives on each module; bumping
+    `_vsrb_version` invalidates the packed image even when the fresh weight tensor reuses an old address."""
+
+    def __init__(self):
+        self.weight = self.bias = None
+        self.kernel_size = (3, 3)
+        self.in_channels = self.out_channels = 0
+        self._vsrb_version = 0
+
+    def set(self, weight):
+        self.weight = weight
+        self.out_channels, self.in_channels = weight.shape[0], weight.shape[1]
+        self._vsrb_version += 1
+        return self
+
+
+def _normalised_weight(conv):
+    """The weight `torch.nn.utils.spectral_norm` would hand to F.conv2d: its forward pre-hook recomputes `conv.weight` from
+    weight_orig / u / v (one power iteration in training mode, like a real forward)."""
+    for hook in conv._forward_pre_hooks.values():
+        hook(conv, None)
+    return conv.weight
+
+
+_S2_IDX = None
+
+
+def _stride2_as_3x3(w: torch.Tensor) -> torch.Tensor:
+    """A 4x4, stride-2, pad-1 filter [co, ci, 4, 4] as the equivalent 3x3, stride-1, pad-1 filter [co, 4 ci, 3, 3] on the
+    pixel-unshuffled input (channel 4c + 2dy + dx = input pixel (2Y+dy, 2X+dx)): output (Y, X) reads input row 2Y + ky - 1,
+    i.e. unshuffled row Y + t - 1 with (t, dy) = (0,1), (1,0), (1,1), (2,0) for ky = 0..3; 20 of the 36 taps are zero."""
+    global _S2_IDX
+    if _S2_IDX is None or _S2_IDX[0].device != w.device:
+        k_of = {(0, 1): 0, (1, 0): 1, (1, 1): 2, (2, 0): 3}
+        idx = torch.zeros(2, 2, 3, 3, dtype=torch.long)
+        msk = torch.zeros(2, 2, 3, 3)
+        for (ty, dy), ky in k_of.items():
+            for (tx, dx), kx in k_of.items():
+                idx[dy, dx, ty, tx] = ky * 4 + kx
+                msk[dy, dx, ty, tx] = 1.0
+        _S2_IDX = (idx.flatten().to(w.device), msk.flatten().to(w.device))
+    idx, msk = _S2_IDX
+    co, ci = w.shape[:2]
+    w3 = w.flatten(2)[:, :, idx] * msk.to(w.dtype)                       # [co, ci, 36] ordered (dy, dx, ty, tx)
+    return w3.view(co, ci * 4, 3, 3)
+
+
+def spectral_conv(sc, x: torch.Tensor, act: str, slope: float) -> torch.Tensor:
+    """act(SpectralConv(x)) on a bf16 channels_last tensor (channels padded to 16): 3x3 stride 1, or 4x4 stride 2 as
+    pixel-unshuffle + 3x3 (exact)."""
+    conv = sc.conv
+    w = _normalised_weight(conv)
+    holder = sc.__dict__.setdefault("_vsrb_holder", _DerivedConv())
+    cin = conv.in_channels
+    if conv.kernel_size == (3, 3) and conv.stride == (1, 1) and conv.padding == (1, 1):
+        return globals()["conv"](holder.set(w), [x], [(0, cin)], act, slope)
+    if conv.kernel_size == (4, 4) and conv.stride == (2, 2) and conv.padding == (1, 1):
+        if cin % 4:
+            raise VsrbError("4x4 stride-2 SpectralConv: in_channels must be a multiple of 4 on this path")
+        xs = _cl(F.pixel_unshuffle(x[:, :cin], 2))
+        return globals()["conv"](holder.set(_stride2_as_3x3(w)), [xs], [(0, 4 * cin)], act, slope)
+    raise VsrbError(f"SpectralConv geometry k={conv.kernel_size} stride={conv.stride} pad={conv.padding} is not implemented "
+                    "(3x3 s1 p1 and 4x4 s2 p1 are)")
+
+
+def unet_discriminator(D, img: torch.Tensor) -> torch.Tensor:
+    """UNetDiscriminator.forward (unet-discriminator.py:19-31)."""
+    def up(t):     # (autocast lists upsampling as an fp32 op: back to bf16 for the next conv)
+        return _cl(F.interpolate(t, scale_factor=2, mode="bilinear", align_corners=False).to(torch.bfloat16))
+    mid = D.conv_0.out_channels
+    f0 = conv(D.conv_0, [to_cl16(img)], [(0, img.shape[1])], "lrelu", 0.2)
+    f1 = spectral_conv(D.conv_1, f0, "lrelu", 0.2)
+    f2 = spectral_conv(D.conv_2, f1, "lrelu", 0.2)
+    f3 = spectral_conv(D.conv_3, f2, "lrelu", 0.2)
+    f3 = up(f3)
+    f4 = up(spectral_conv(D.conv_4, f3, "lrelu", 0.2) + f2)
+    f5 = up(spectral_conv(D.conv_5, f4, "lrelu", 0.2) + f1)
+    f6 = spectral_conv(D.conv_6, f5, "lrelu", 0.2) + f0
+    out = spectral_conv(D.conv_7, f6, "lrelu", 0.2)
+    out = spectral_conv(D.conv_8, out, "lrelu", 0.2)
+    return conv(D.conv_9, [out], [(0, mid)], "none")[:, :1].float().contiguous()

@@ -317,6 +317,29 @@ def residual_stack(x: torch.Tensor, stem: Optional[torch.nn.Conv2d], blocks: Seq
     return _to_nchw(cur, n, mid, h, w, ca, dt)
 
 
+def spectral_conv2d(x: torch.Tensor, sc) -> torch.Tensor:
+    """SpectralConv.forward (conv.py:6-13): conv with the spectrally normalised weight, no bias, no activation."""
+    x = _check_input(x, "input")
+    AG = _autograd() if _wants_grad(sc, x) else None
+    from . import autograd as A
+    with (contextlib.nullcontext() if AG is not None else torch.no_grad()):
+        y = A.spectral_conv(sc, A.to_cl16(x), "none", 0.0)
+    return y[:, :sc.conv.out_channels].float().contiguous()
+
+
+def unet_discriminator_forward(D, img: torch.Tensor) -> torch.Tensor:
+    """UNetDiscriminator.forward (unet-discriminator.py:19-31) on the conv kernels; bf16 activations, fp32 logits."""
+    img = _check_input(img, "img")
+    if img.shape[-2] % 8 or img.shape[-1] % 8:
+        raise VsrbError("UNetDiscriminator needs sides that are multiples of 8 (three stride-2 encoders)")
+    from . import autograd as A
+    if _wants_grad(D, img):
+        _autograd()
+        return A.unet_discriminator(D, img)
+    with torch.no_grad():
+        return A.unet_discriminator(D, img)
+
+
 def flow_warp(x: torch.Tensor, flow: torch.Tensor, padding_mode: str = "zeros") -> torch.Tensor:
     """flow_warp(x [T,c,h,w], flow [T,h,w,2]) (spynet.py:95-106)."""
     x = _check_input(x, "input")

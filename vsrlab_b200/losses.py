@@ -8,6 +8,8 @@ of `hr` is computed inside the second term's kernel, and the metrics return devi
 
 * `CharbonnierLoss`          drop-in for `vsrlab.core.losses.CharbonnierLoss` (same constructor, same forward(x, y))
 * `realbasicvsr_loss`        both terms of `compute_loss` (core/utils.py:235-240) in two launches
+* `PerceptualLoss`, `AdversarialLoss`   the GAN recipe's two extra terms (core/losses.py:29-74): the VGG19
+                             feature stack runs on the conv kernels (frozen weights: input gradients only)
 * `PSNR`, `SSIM`             modules with piqa's call signature (defaults of piqa.PSNR / piqa.SSIM), results stay on
                              the device; `MetricCollection.forward` of the reference calls `.item()` on them, which works.
 """
@@ -102,6 +104,89 @@ def realbasicvsr_loss(sr: torch.Tensor, hr: torch.Tensor, lq: Optional[torch.Ten
     if lq is not None:
         loss = loss + _CharbonnierResizedFn.apply(lq, hr, eps)
     return loss
+
+
+LAYER_WEIGHTS = {"2": 0.1, "7": 0.1, "16": 0.8, "25": 0.9, "34": 1.0}        # core/losses.py:8
+
+
+class PerceptualLoss(torch.nn.Module):
+    """`vsrlab.core.losses.PerceptualLoss` (core/losses.py:29-64) with the VGG19 feature stack on the sm_100a conv kernels:
+    weight * sum_k layer_weights[k] * L1(features_k(yhat), features_k(y)).  Same constructor (`weight`); `vgg_layers` lets
+    a caller hand in the `torchvision` feature stack (the default, like the reference, asks torchvision for the
+    ImageNet-pretrained one, which needs a download).  Notes on fidelity: the reference stores `output[name] = x` and then
+    runs the next `ReLU(inplace=True)` ON THAT TENSOR, so the features of layers 2, 7, 16 and 25 are post-ReLU and only
+    layer 34 (the last of the slice) is a raw conv output - reproduced here by fusing each ReLU into its conv.  VGG
+    parameters are frozen (core/losses.py:36-37): the backward computes input gradients only."""
+
+    def __init__(self, weight=1, vgg_layers=None, layer_weights=None):
+        super().__init__()
+        self.weight = weight
+        self.layer_weights = dict(layer_weights or LAYER_WEIGHTS)
+        if vgg_layers is None:
+            from torchvision import models
+            vgg_layers = models.vgg19(weights="IMAGENET1K_V1").features[:max(map(int, self.layer_weights)) + 1]
+        self.vgg_layers = vgg_layers
+        for p in self.vgg_layers.parameters():
+            p.requires_grad = False
+
+    def features(self, x: torch.Tensor) -> dict:
+        """x [N,3,h,w] -> {layer name: bf16 channels_last feature map}"""
+        import torch.nn.functional as F
+        from . import autograd as A
+        require_cuda(x, "perceptual loss input")
+        t = A.to_cl16(x)
+        out = {}
+        layers = list(self.vgg_layers.named_children())
+        taps = self.layer_weights
+        i = 0
+        while i < len(layers):
+            name, m = layers[i]
+            if isinstance(m, torch.nn.Conv2d):
+                nxt = layers[i + 1] if i + 1 < len(layers) else None
+                relu = nxt is not None and isinstance(nxt[1], torch.nn.ReLU)
+                # a tapped conv followed by an out-of-place ReLU keeps its raw output: do not fuse in that case
+                fuse = relu and (nxt[1].inplace or name not in taps)
+                t = A.conv(m, [t], [(0, m.in_channels)], "relu" if fuse else "none")
+                if name in taps:
+                    out[name] = t
+                if fuse:
+                    if nxt[0] in taps:
+                        out[nxt[0]] = t
+                    i += 1
+            elif isinstance(m, torch.nn.MaxPool2d):
+                t = A._cl(F.max_pool2d(t, m.kernel_size, m.stride, m.padding))
+            elif isinstance(m, torch.nn.ReLU):
+                t = F.relu(t)
+            else:
+                raise L.VsrbError(f"PerceptualLoss: layer {name} ({type(m).__name__}) is not part of a VGG feature stack")
+            if name in taps and name not in out:
+                out[name] = t
+            i += 1
+        return out
+
+    def forward(self, yhat: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        h, w = y.shape[-2:]
+        fx = self.features(yhat.reshape(-1, 3, h, w))
+        with torch.no_grad():
+            fy = self.features(y.detach().reshape(-1, 3, h, w))
+        loss = 0
+        for k, wk in self.layer_weights.items():
+            loss = loss + (fx[k].float() - fy[k].float()).abs().mean() * wk
+        return loss * self.weight
+
+
+class AdversarialLoss(torch.nn.Module):
+    """`vsrlab.core.losses.AdversarialLoss` (core/losses.py:66-74): BCE-with-logits against a constant target; the weight
+    applies to the generator's term only."""
+
+    def __init__(self, weight=2e-5):
+        super().__init__()
+        self.weight = weight
+
+    def forward(self, x, target, is_disc=False):
+        import torch.nn.functional as F
+        loss = F.binary_cross_entropy_with_logits(x, torch.full_like(x, float(target)))
+        return loss if is_disc else loss * self.weight
 
 
 class PSNR(torch.nn.Module):
