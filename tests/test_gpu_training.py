@@ -89,6 +89,61 @@ def test_conv_gradients(dev, case):
         assert rel(rd.grad[:, :cout].float().cpu(), rr.grad) < 1e-2
 
 
+
+TAPS_CASES = [
+    # (K, cin, cin tensor channels, cout, B, h, w): SPyNet's five 7x7 layers at several pyramid sizes, image / 1x1 / odd widths
+    (7, 8, 16, 32, 3, 32, 48), (7, 32, 32, 64, 2, 64, 64), (7, 64, 64, 32, 2, 32, 32), (7, 32, 32, 16, 3, 16, 16), (7, 16, 16, 2, 4, 20, 28),
+    (7, 32, 32, 64, 5, 2, 2), (7, 64, 64, 32, 3, 4, 4), (7, 8, 16, 32, 2, 8, 8),
+    (3, 3, 16, 64, 2, 20, 36), (1, 128, 128, 64, 2, 12, 20), (5, 24, 32, 40, 2, 18, 22), (3, 80, 80, 72, 1, 9, 17),
+]
+
+
+@pytest.mark.parametrize("case", TAPS_CASES, ids=lambda c: "k%d_%d(%d)->%d_b%d_%dx%d" % c)
+def test_wgrad_taps_kernel(dev, case):
+    """csrc/wgrad_taps.cu (tap-stacking tcgen05 weight gradient) against fp64 torch on the same bf16 operands, and against the
+    mma.sync kernel it replaces (VSRB_WGRAD_MMA=1).  Padding channels of the activation tensors hold NaN: they must not leak."""
+    import os
+    from vsrlab_b200 import _lib as L
+    from vsrlab_b200 import ops
+    from vsrlab_b200._lib import BF16
+    K, cin, xc, cout, B, h, w = case
+    g = torch.Generator().manual_seed(K * 1000 + cin + cout)
+    x = bf16r(torch.randn(B, cin, h, w, generator=g))
+    dz = bf16r(torch.randn(B, cout, h, w, generator=g))
+    zc = (cout + 15) // 16 * 16
+    CL = torch.channels_last
+    xp = torch.full((B, xc, h, w), float("nan"), dtype=torch.bfloat16, device=dev).contiguous(memory_format=CL)
+    zp = torch.full((B, zc, h, w), float("nan"), dtype=torch.bfloat16, device=dev).contiguous(memory_format=CL)
+    xp[:, :cin] = x.to(dev)
+    zp[:, :cout] = dz.to(dev)
+    wr = torch.zeros(cout, cin, K, K, dtype=torch.float64, requires_grad=True)
+    (F.conv2d(x.double(), wr, None, 1, K // 2) * dz.double()).sum().backward()
+    geom = L.ConvGeom()
+    geom.kh = geom.kw = K
+    geom.n_seg, geom.cout, geom.pixshuf, geom.groups, geom.dtype, geom.transpose = 1, cout, 0, 1, BF16, 0
+    geom.seg_off[0], geom.seg_c[0] = 0, cin
+    outs = {}
+    for mode in ("taps", "mma") if K != 5 else ("taps",):       # (the mma.sync kernel has no 5x5 instance)
+        if mode == "mma":
+            os.environ["VSRB_WGRAD_MMA"] = "1"
+        try:
+            dw = torch.zeros(cout, cin, K, K, dtype=torch.float32, device=dev)
+            db = torch.zeros(cout, dtype=torch.float32, device=dev)
+            ops.conv2d_wgrad(geom, [xp], [xc], zp, zc, B, h, w, cin, dw, db)
+            ops.conv2d_wgrad(geom, [xp], [xc], zp, zc, B, h, w, cin, dw, None)          # accumulates
+            torch.cuda.synchronize()
+        finally:
+            os.environ.pop("VSRB_WGRAD_MMA", None)
+        outs[mode] = dw.cpu() / 2
+        assert torch.isfinite(dw).all()
+        assert rel(db.cpu(), dz.sum((0, 2, 3))) < 1e-3
+    scale = wr.grad.abs().max().item()
+    assert (outs["taps"].double() - wr.grad).abs().max().item() < 2e-3 * scale + 1e-4, (outs["taps"].double() - wr.grad).abs().max().item()
+    assert rel(outs["taps"], wr.grad.float()) < 1e-3
+    if "mma" in outs:
+        assert rel(outs["taps"], outs["mma"]) < 1e-3
+
+
 @pytest.mark.parametrize("border,dtype", [(False, torch.bfloat16), (True, torch.float32)])
 def test_warp_gradients(dev, border, dtype):
     from vsrlab_b200 import autograd as AG

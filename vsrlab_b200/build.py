@@ -9,7 +9,7 @@ from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
-SOURCES = ["api.cu", "conv_tc.cu", "conv_ring.cu", "conv_f32.cu", "warp.cu", "train.cu", "wgrad_tc.cu", "loss.cu"]
+SOURCES = ["api.cu", "conv_tc.cu", "conv_ring.cu", "conv_f32.cu", "warp.cu", "train.cu", "wgrad_tc.cu", "wgrad_taps.cu", "loss.cu"]
 OUT = CSRC / "libvsrb200.so"
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "-shared", "--threads", "0"]      # the six translation units compile in parallel

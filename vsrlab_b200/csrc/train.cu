@@ -457,6 +457,8 @@ int launch_bias_grad_multi(const void* const* dzs, int n_chunks, int dz_c, long 
                            cudaStream_t s);
 int launch_wgrad_tc_multi(const void* const* xs, int x_c, int c0, int ci_off, const void* const* dzs, int dz_c, int n_chunks,
                           int batch, int h, int w, int cout, int cin_total, float* dw, cudaStream_t stream);
+int launch_wgrad_taps(const void* x, int x_c, int x_c0, int ci_n, int ci_off, const void* dz, int dz_c, int z_c0, int co_n, int K,
+                      int batch, int h, int w, int cin_total, float* dw, cudaStream_t stream);
 
 }  // namespace vsrb
 
@@ -512,6 +514,11 @@ int vsrb_conv2d_wgrad(const vsrb_conv_geom* g, const void* const* in, const int3
     // FFMA kernel
     const bool tc_ok = g->dtype == VSRB_BF16 && g->kh == 3 && g->kw == 3 && g->groups == 1 && dz_c >= g->cout &&
                        (reinterpret_cast<uintptr_t>(dz) & 15) == 0 && !getenv("VSRB_WGRAD_SIMT");
+    // ... except that every other bf16 segment of an odd square filter up to 7x7 (SPyNet's 7x7 stacks, 3-channel image
+    // segments, 1x1) takes the tap-stacking tcgen05 kernel of wgrad_taps.cu; VSRB_WGRAD_MMA=1 keeps the mma.sync kernel
+    const bool taps_ok = g->dtype == VSRB_BF16 && g->kh == g->kw && (g->kw & 1) && g->kw <= 7 && g->groups == 1 && dz_c % 8 == 0 &&
+                         (reinterpret_cast<uintptr_t>(dz) & 15) == 0 && !getenv("VSRB_WGRAD_SIMT") && !getenv("VSRB_WGRAD_FFMA") &&
+                         !getenv("VSRB_WGRAD_MMA");
     bool on_tc[4] = {false, false, false, false};
     // (co, ci) tile of the mma.sync kernel: as narrow as its segments allow (the FFMA kernels keep 64 x 64)
     int co_t = 64, ci_t = 64, cmax = 0;
@@ -533,6 +540,16 @@ int vsrb_conv2d_wgrad(const vsrb_conv_geom* g, const void* const* in, const int3
                                          (cudaStream_t)stream);
                 if (rc != VSRB_OK) return rc;
             }
+            continue;
+        }
+        if (taps_ok && (reinterpret_cast<uintptr_t>(in[s]) & 15) == 0) {
+            for (int c0 = 0; c0 < g->seg_c[s]; c0 += 64)
+                for (int n0 = 0; n0 < g->cout; n0 += 64) {
+                    const int ci_n = g->seg_c[s] - c0 < 64 ? g->seg_c[s] - c0 : 64, co_n = g->cout - n0 < 64 ? g->cout - n0 : 64;
+                    int rc = launch_wgrad_taps(in[s], in_c[s], c0, ci_n, g->seg_off[s] + c0, dz, dz_c, n0, co_n, g->kw, batch, h, w, cin_total,
+                                               dw, (cudaStream_t)stream);
+                    if (rc != VSRB_OK) return rc;
+                }
             continue;
         }
         for (int c0 = 0; c0 < g->seg_c[s]; c0 += ci_t) {
