@@ -82,7 +82,8 @@ __global__ void __launch_bounds__(128) mn_modes_test(int C, int s, int lbo_rows,
 
 // cycles per MMA: `reps` MMAs (M = 128, K = 16) on one accumulator, A in the given MN-major mode (or K-major SW128 when
 // a_kmajor), B MN-major with pitch pb (N <= pb/2 per block; larger N re-reads the block through LBO = 0)
-__global__ void __launch_bounds__(128) mn_cost_test(int pa, int pb, int N, int a_kmajor, int reps, long long* cycles) {
+__global__ void __launch_bounds__(128) mn_cost_test(int pa, int pb, int N, int a_kmajor, int reps, long long* cycles, int start_rows = 0,
+                                                    int cycle_rows = 0, int lbo_rows = 1, int n_acc = 1) {
     extern __shared__ uint8_t raw_[];
     const uint32_t raw = smem_u32(raw_);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -114,6 +115,24 @@ __global__ void __launch_bounds__(128) mn_cost_test(int pa, int pb, int N, int a
         }
         const uint64_t bd = mn_desc_mode(base + 24 * 1024, 0u, (uint32_t)pb);
         const long long t0 = clock64();
+        if (start_rows || cycle_rows || lbo_rows != 1 || n_acc != 1) {
+            // windows that start `start_rows` (+ 0..7 * cycle_rows) pixel rows into the tile, M blocks lbo_rows rows apart,
+            // round-robin over n_acc accumulators; the eight descriptors are built before the clock starts
+            uint64_t ds[8];
+            for (int j = 0; j < 8; ++j)
+                ds[j] = mn_desc_mode(base + (uint32_t)(start_rows + j * cycle_rows) * (uint32_t)pa, (uint32_t)(lbo_rows * pa), (uint32_t)pa);
+            const long long t1 = clock64();
+            for (int i = 0; i < reps; i += 8) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) umma_bf16(tmem + (uint32_t)((j % n_acc) * N), ds[j], bd, idesc, (i + j) >= n_acc ? 1u : 0u);
+            }
+            umma_commit(bar);
+            bool dead2 = false;
+            int dbg2 = 0;
+            mbar_wait(bar, 0, &dbg2, 1, dead2);
+            *cycles = clock64() - t1;
+            return;
+        } else
         for (int i = 0; i < reps; ++i) umma_bf16(tmem, ad, bd, idesc, i ? 1u : 0u);
         umma_commit(bar);
         bool dead = false;
@@ -172,6 +191,21 @@ int main() {
                 }
                 printf("A %s pitch %3d, B MN-major 128, M=128 N=%3d K=16: %.1f cycles per MMA\n", km ? "K-major " : "MN-major", pa, Ns[ni], (double)c / reps);
             }
+        }
+    // the weight-gradient kernel's access pattern: unaligned window starts, one-pixel M block distance, several accumulators
+    for (int pa = 32; pa <= 128; pa *= 2)
+        for (int variant = 0; variant < 6; ++variant) {
+            const int start = (variant == 1 || variant == 3) ? 3 : 0, cyc = (variant == 2 || variant == 3) ? 11 : 0;
+            const int lbo = variant == 4 ? 0 : 1, nacc = variant == 5 ? 4 : 1;
+            long long c = 0;
+            for (int rep = 0; rep < 2; ++rep) {
+                mn_cost_test<<<1, 128, 52 * 1024>>>(pa, 128, 32, 0, reps, dc, start, cyc, lbo, nacc);
+                cudaError_t e = cudaDeviceSynchronize();
+                if (e != cudaSuccess) { printf("cost test: CUDA error %s\n", cudaGetErrorString(e)); return 1; }
+                cudaMemcpy(&c, dc, 8, cudaMemcpyDeviceToHost);
+            }
+            printf("A MN-major pitch %3d N=32: start row %d, cycling %2d rows, M blocks %d rows apart, %d accumulators: %.1f cycles per MMA\n", pa,
+                   start, cyc, lbo, nacc, (double)c / reps);
         }
     return 0;
 }

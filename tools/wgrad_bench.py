@@ -1,4 +1,9 @@
-"""Micro-benchmark of the weight-gradient kernels: python tools/wgrad_bench.py [--imgs 120 --hw 64]"""
+"""Weight-gradient kernels on the shapes of the cfg4 training step: time per launch (CUDA events, L2 flushed between
+launches) of the tap-stacking tcgen05 kernel (csrc/wgrad_taps.cu) against the mma.sync kernel it replaces, with the
+VSRB_WG_DEBUG decomposition (1 = no final atomics, 2 = no MMAs, 4 = no loads).
+
+    python tools/wgrad_bench.py [--images 224]
+"""
 import argparse
 import os
 import sys
@@ -6,45 +11,57 @@ from pathlib import Path
 
 import torch
 
-ROOT = Path(__file__).resolve().parents[1]
-sys.path.insert(0, str(ROOT))
-from vsrlab_b200 import autograd as AG, ops  # noqa: E402
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+from vsrlab_b200 import _lib as L, load, ops  # noqa: E402
+from vsrlab_b200._lib import BF16  # noqa: E402
 
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--imgs", type=int, default=120)
-    ap.add_argument("--hw", type=int, default=64)
-    ap.add_argument("--cin", type=int, default=64)
-    ap.add_argument("--cout", type=int, default=64)
-    ap.add_argument("--k", type=int, default=3)
+    ap.add_argument("--images", type=int, default=224)
+    ap.add_argument("--modes", default="taps,mma,taps:1,taps:2,taps:3,taps:4")
     a = ap.parse_args()
+    load()
     dev = torch.device("cuda:0")
-    cv = torch.nn.Conv2d(a.cin, a.cout, a.k, 1, a.k // 2)
-    g = AG._wgrad_geom(cv, ((0, a.cin),))
-    x = AG.to_cl16(torch.randn(a.imgs, a.cin, a.hw, a.hw).to(dev))
-    dz = AG.to_cl16(torch.randn(a.imgs, a.cout, a.hw, a.hw).to(dev))
-    dw = torch.zeros(a.cout, a.cin, a.k, a.k, device=dev)
-    db = torch.zeros(a.cout, device=dev)
-
-    def call():
-        ops.conv2d_wgrad(g, [x], [x.shape[1]], dz, dz.shape[1], a.imgs, a.hw, a.hw, a.cin, dw, db)
-    for _ in range(3):
-        call()
-    torch.cuda.synchronize()
-    ts = []
-    for _ in range(20):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        call()
-        e1.record()
-        torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
-    ts.sort()
-    ms = ts[len(ts) // 2]
-    fl = 2.0 * a.imgs * a.hw * a.hw * a.cin * a.cout * a.k * a.k
-    print(f"wgrad {a.k}x{a.k} {a.cin}->{a.cout} {a.imgs}x{a.hw}x{a.hw}: {ms * 1e3:.1f} us  {fl / ms / 1e9:.1f} TF/s  "
-          f"(VSRB_WG_DEBUG={os.environ.get('VSRB_WG_DEBUG', '0')} VSRB_WG_CTAS={os.environ.get('VSRB_WG_CTAS', '-')})")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    CL = torch.channels_last
+    shapes = [(7, 8, 16, 32), (7, 32, 32, 64), (7, 64, 64, 32), (7, 32, 32, 16), (7, 16, 16, 2), (3, 3, 16, 64), (1, 128, 128, 64), (3, 64, 64, 64)]
+    for side in (64, 32, 16):
+        for K, cin, xc, cout in shapes:
+            B = a.images
+            zc = (cout + 15) // 16 * 16
+            x = torch.randn(B, xc, side, side, device=dev).to(torch.bfloat16).contiguous(memory_format=CL)
+            dz = torch.randn(B, zc, side, side, device=dev).to(torch.bfloat16).contiguous(memory_format=CL)
+            geom = L.ConvGeom()
+            geom.kh = geom.kw = K
+            geom.n_seg, geom.cout, geom.pixshuf, geom.groups, geom.dtype, geom.transpose = 1, cout, 0, 1, BF16, 0
+            geom.seg_off[0], geom.seg_c[0] = 0, cin
+            dw = torch.zeros(cout, cin, K, K, dtype=torch.float32, device=dev)
+            flops = 2.0 * B * side * side * cin * cout * K * K
+            row = []
+            for mode in a.modes.split(","):
+                name, _, dbg = mode.partition(":")
+                os.environ.pop("VSRB_WGRAD_MMA", None)
+                os.environ.pop("VSRB_WG_DEBUG", None)
+                if name == "mma":
+                    os.environ["VSRB_WGRAD_MMA"] = "1"
+                if dbg:
+                    os.environ["VSRB_WG_DEBUG"] = dbg
+                ts = []
+                for i in range(6):
+                    flush.zero_()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    ops.conv2d_wgrad(geom, [x], [xc], dz, zc, B, side, side, cin, dw, None)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    if i >= 2:
+                        ts.append(e0.elapsed_time(e1) * 1e3)
+                us = sorted(ts)[len(ts) // 2]
+                row.append(f"{mode} {us:7.1f} us ({flops / us / 1e6:6.1f} TF/s)")
+            print(f"{K}x{K} {cin:3d}->{cout:3d} {B}x{side}x{side}: " + " | ".join(row), flush=True)
+    os.environ.pop("VSRB_WGRAD_MMA", None)
+    os.environ.pop("VSRB_WG_DEBUG", None)
 
 
 if __name__ == "__main__":

@@ -1,20 +1,24 @@
 // Weight gradient of K x K convolutions (K = 1, 3, 5, 7) over 16-, 32- or 64-channel blocks on the tensor cores: the
 // layers wgrad_tc.cu does not take - SPyNet's 7x7 stacks (8->32->64->32->16->2), 3-channel image segments, 1x1 fusion.
 //
-//   Out[ty][tx][s][u] = sum over pixels p of  S[p + (ty, tx) - K/2][s] * U[p][u]
+//   Out[ty][tx][s][u] = sum over pixels (y, x) of  S[y][x + tx - K/2][s] * U[y - ty + K/2][x][u]
 //
 // is a GEMM over the pixel index with both operands MN-major (a TMA box of pixels x C channels is K rows of C contiguous
-// elements).  S, the operand whose windows are shifted by the filter tap, is the NARROWER of (x, dz): its 128/Cs windows of
-// consecutive kx fill the M = 128 rows of ONE instruction - the descriptor's leading-dimension offset is one pixel, and an
-// MN-major operand may start at any pixel row of its tile in the 32B, 64B and 128B swizzle modes alike
-// (tools/umma_mn_modes_test.cu; the same test measures 40 / 41 / 49 cycles per M=128, K=16 MMA at N = 16 / 32 / 64).  U is
-// the wider tensor, N = Cu.  With S = x the taps are the filter's (ky, kx) = (ty, tx); with S = dz the sum runs over the
-// mirrored taps (ky, kx) = (K-1-ty, K-1-tx) - zero padding outside the image is the TMA's out-of-bounds fill either way.
-//   7x7, 32 -> 64 channels: 14 MMAs (7 ky x 2 groups of 4 kx) of N = 64 per 16 pixels instead of 49 x 4 mma.sync tiles.
-// The K*G accumulators of N columns exceed the 512 TMEM columns for the two wide layers: blockIdx.y splits the ky range
-// (each pass loads only the rows it needs).  One halo box of S and one tile of U per 16 x R pixel tile, mbarrier ring.
-// Epilogue: per 16 U channels the accumulators go through shared memory in OIHW order, then leave as runs of nky*K
-// consecutive floats with coalesced atomics.
+// elements), and BOTH filter axes are folded into ONE instruction per 16 pixels:
+//   * S, the NARROWER of (x, dz), carries the horizontal shift: its 128/Cs windows of consecutive tx fill the M = 128 rows
+//     (the descriptor's leading-dimension offset is one pixel; an MN-major operand may start at any pixel row of its tile in
+//     the 32B, 64B and 128B swizzle modes alike - tools/umma_mn_modes_test.cu);
+//   * U, the wider tensor, carries the vertical shift: the N columns are the Cu channels of up to 256/Cu box rows one below
+//     the other (leading-dimension offset = one box row).
+// 7x7, 8 -> 32 channels: ONE MMA of N = 224 per 16 pixels instead of 49 x 2 mma.sync tiles.  The point of the stacking is
+// the tensor pipe's cost of 40 / 41 / 49 / 65 / 129 cycles at N = 16 / 32 / 64 / 128 / 256 (same tool): seven N = 32 MMAs
+// cost 287 cycles, one N = 224 MMA 112, and the issuing thread has to feed 7x fewer instructions.
+// With S = x the taps are the filter's (ky, kx) = (ty, tx); with S = dz the sum runs over the mirrored taps
+// (K-1-ty, K-1-tx) - zero padding outside the image is the TMA's out-of-bounds fill either way.  When G * K * Cu
+// accumulator columns exceed the 512 of TMEM (or K * Cu > 256), blockIdx.y splits the ty range; each pass loads only the
+// U rows it needs.  One box of S (R rows, 16 + K-1 pixels) and one of U (R + nj-1 rows, 16 pixels) per 16 x R pixel tile,
+// mbarrier ring.  Epilogue: per 16 U channels the accumulators go through shared memory in OIHW order, then leave as runs
+// of nj*K consecutive floats with coalesced atomics.
 #include <stdlib.h>
 
 #include <mutex>
@@ -33,8 +37,8 @@ struct WgTapsParams {
     int K, pad;                 // filter size, K / 2
     int cs, cu;                 // channel block of S / U: 16, 32 or 64
     int rows;                   // tile rows R
-    int nky_max, G, tpg;        // ky per pass; MMAs per ky; taps per MMA (128 / cs)
-    int s_bytes, u_bytes, stage_bytes, stages;
+    int nj_max, G, tpg;         // U rows (ty values) per pass; MMAs per 16 pixels; tx per MMA (128 / cs)
+    int s_bytes, u_bytes, u_off, stage_bytes, stages;   // u_off: where the U box sits inside a stage
     int tiles_x, tiles_per_img, total_tiles;
     int s_c0, u_c0;             // first channel of the block inside its tensor
     int s_is_x;                 // 1: S = x (rows of Out are input channels), 0: S = dz
@@ -64,10 +68,12 @@ __global__ void __launch_bounds__(kTpThreads, 1) wgrad_taps_kernel(const __grid_
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + 192);
     const uint32_t stage0 = base + 1024;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ky0 = blockIdx.y * P.nky_max;
-    const int nky = (P.K - ky0) < P.nky_max ? (P.K - ky0) : P.nky_max;
+    // this pass owns the U rows (N blocks) j0 .. j0 + nj - 1; block j holds ty = K-1-j
+    const int j0 = blockIdx.y * P.nj_max;
+    const int nj = (P.K - j0) < P.nj_max ? (P.K - j0) : P.nj_max;
     const int box_w = kTpTW + P.K - 1;
     const uint32_t pitch_s = 2u * P.cs, pitch_u = 2u * P.cu;
+    const uint32_t acc_cols = (uint32_t)(P.nj_max * P.cu);            // TMEM columns per accumulator (one per tx group)
 
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < P.stages; ++i) {
@@ -104,52 +110,60 @@ __global__ void __launch_bounds__(kTpThreads, 1) wgrad_taps_kernel(const __grid_
                     mbar_arrive(full0 + 8 * slot);
                 } else {
                     mbar_expect_tx(full0 + 8 * slot, P.s_bytes + P.u_bytes);
-                    tma_load_4d(&P.smap, full0 + 8 * slot, sa, P.s_c0, tx * kTpTW - P.pad, ty * P.rows - P.pad + ky0, img);
-                    tma_load_4d(&P.umap, full0 + 8 * slot, sa + P.stage_bytes - P.u_bytes, P.u_c0, tx * kTpTW, ty * P.rows, img);
+                    tma_load_4d(&P.smap, full0 + 8 * slot, sa, P.s_c0, tx * kTpTW - P.pad, ty * P.rows, img);
+                    tma_load_4d(&P.umap, full0 + 8 * slot, sa + P.u_off, P.u_c0, tx * kTpTW, ty * P.rows - P.pad + j0, img);
                 }
             }
             __syncwarp();
             if (++slot == P.stages) { slot = 0; phase ^= 1; }
         }
     } else if (warp == 1) {
-        // ---- MMA issuer: per tile row (K = 16 pixels) and (ky, kx group): Out[128 x Cu] += S_windows^T[128 x 16] * U[16 x Cu] ----
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(P.cu >> 3) << 17) | (8u << 24);
+        // ---- MMA issuer: per tile row (K = 16 pixels) and tx group: Out_g[128 x nj*Cu] += S_windows^T[128 x 16] * U_rows[16 x nj*Cu].
+        // The loops run warp-uniformly and only the instruction is predicated on the elected lane, so the operand words live in
+        // uniform registers; descriptor high words are constants, the low words (start >> 4 | LBO >> 4 @16) advance by adds.
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)((nj * P.cu) >> 3) << 17) | (8u << 24);
+        const uint32_t a_hi = (uint32_t)(mn_desc_pitch(0u, 0u, pitch_s) >> 32), b_hi = (uint32_t)(mn_desc_pitch(0u, 0u, pitch_u) >> 32);
+        const uint32_t a_lbo = (pitch_s >> 4) << 16, b_lbo = ((kTpTW * pitch_u) >> 4) << 16;
+        const uint32_t row_step = ((uint32_t)box_w * pitch_s) >> 4, g_step = ((uint32_t)P.tpg * pitch_s) >> 4, b_step = (kTpTW * pitch_u) >> 4;
+        const int G = P.G, rows = (P.debug & 2) ? 0 : P.rows;
+        const bool leader = elect_one();
+        const uint32_t tm0 = __shfl_sync(0xffffffffu, tmem_base, 0);
         int slot = 0;
         uint32_t phase = 0;
-        bool first = true;
+        uint32_t acc = 0u;
         for (int it = 0; it < my_tiles; ++it) {
             const uint32_t sa = stage0 + slot * P.stage_bytes;
-            const uint32_t ub = sa + P.stage_bytes - P.u_bytes;
+            const uint32_t ub = sa + P.u_off;
             mbar_wait(full0 + 8 * slot, phase, P.dbg, 22, dead);
             tc_fence_after();
-            if (elect_one()) {
-                const int rows = (P.debug & 2) ? 0 : P.rows;
-                for (int ks = 0; ks < rows; ++ks) {
-                    const uint64_t bd = mn_desc_pitch(ub + (uint32_t)ks * kTpTW * pitch_u, 0u, pitch_u);
-                    const uint32_t acc = (first && ks == 0) ? 0u : 1u;
-                    for (int kyi = 0; kyi < nky; ++kyi) {
-                        const uint32_t row = sa + (uint32_t)((ks + kyi) * box_w) * pitch_s;
-                        for (int g = 0; g < P.G; ++g)
-                            umma_bf16(tmem_base + (uint32_t)((kyi * P.G + g) * P.cu), mn_desc_pitch(row + (uint32_t)(g * P.tpg) * pitch_s, pitch_s, pitch_s),
-                                      bd, idesc, acc);
-                    }
+            uint32_t a_row = ((sa >> 4) & 0x3FFFu) | a_lbo, b_lo = ((ub >> 4) & 0x3FFFu) | b_lbo;
+            for (int ks = 0; ks < rows; ++ks) {
+                uint32_t a_lo = a_row, tm = tm0;
+                for (int g = 0; g < G; ++g) {
+                    if (leader) umma_bf16_words(tm, a_lo, a_hi, b_lo, b_hi, idesc, acc);
+                    tm += acc_cols;
+                    a_lo += g_step;
                 }
-                umma_commit(empty0 + 8 * slot);
+                acc = 1u;
+                a_row += row_step;
+                b_lo += b_step;
             }
+            if (leader) umma_commit(empty0 + 8 * slot);
             __syncwarp();
-            first = false;
+            acc = 1u;
             if (++slot == P.stages) { slot = 0; phase ^= 1; }
         }
-        if (elect_one()) umma_commit(done);
+        if (leader) umma_commit(done);
         __syncwarp();
     } else if (warp >= 4) {
         mbar_wait(done, 0, P.dbg, 23, dead);
         tc_fence_after();
     }
-    // ---- epilogue: 16 U channels at a time.  stg[co_local][ci_local][j], j = the run of nky*K taps this pass owns ----
-    const int run = nky * P.K;
+    // ---- epilogue: 16 U channels at a time.  stg[co_local][ci_local][r], r = the run of nj*K taps this pass owns ----
+    const int run = nj * P.K;
     const int A = P.s_is_x ? 16 : P.cs, B = P.s_is_x ? P.cs : 16;      // extents of (co_local, ci_local) in the staging block
-    const int j_base = P.s_is_x ? ky0 * P.K : (P.K - ky0 - nky) * P.K;  // first tap of the run on the OIHW (ky, kx) axis
+    // S = x: block j is ky = K-1-j, the pass owns ky in [K-j0-nj, K-j0);  S = dz: block j is ky = j
+    const int r_base = P.s_is_x ? (P.K - j0 - nj) * P.K : j0 * P.K;
     float* stg = reinterpret_cast<float*>(base_ptr + 1024);
     const int KK = P.K * P.K;
     for (int n0 = 0; n0 < P.cu; n0 += 16) {
@@ -158,18 +172,18 @@ __global__ void __launch_bounds__(kTpThreads, 1) wgrad_taps_kernel(const __grid_
             const int wq = warp - 4;
             const int m = wq * 32 + lane;
             const int t = m / P.cs, c = m - t * P.cs;
-            for (int kyi = 0; kyi < nky; ++kyi)
-                for (int g = 0; g < P.G; ++g) {
+            for (int g = 0; g < P.G; ++g)
+                for (int jl = 0; jl < nj; ++jl) {
                     uint32_t r[16];
-                    tmem_ld16_nowait(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((kyi * P.G + g) * P.cu + n0), r);
+                    tmem_ld16_nowait(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)g * acc_cols + (uint32_t)(jl * P.cu + n0), r);
                     tmem_ld_wait();
-                    const int kx = g * P.tpg + t;
-                    if (kx < P.K) {
-                        const int j = P.s_is_x ? kyi * P.K + kx : (nky - 1 - kyi) * P.K + (P.K - 1 - kx);
+                    const int tx = g * P.tpg + t;
+                    if (tx < P.K) {
+                        const int rr = P.s_is_x ? (nj - 1 - jl) * P.K + tx : jl * P.K + (P.K - 1 - tx);
 #pragma unroll
                         for (int q = 0; q < 16; ++q) {
                             const int a = P.s_is_x ? q : c, b = P.s_is_x ? c : q;
-                            stg[(a * B + b) * run + j] = __uint_as_float(r[q]);
+                            stg[(a * B + b) * run + rr] = __uint_as_float(r[q]);
                         }
                     }
                 }
@@ -181,10 +195,10 @@ __global__ void __launch_bounds__(kTpThreads, 1) wgrad_taps_kernel(const __grid_
             const int co_lim = P.co_valid - (P.s_is_x ? n0 : 0), ci_lim = P.ci_valid - (P.s_is_x ? 0 : n0);
             const int total = A * B * run;
             for (int i = threadIdx.x; i < total; i += kTpThreads) {
-                const int ab = i / run, j = i - ab * run;
+                const int ab = i / run, rr = i - ab * run;
                 const int a = ab / B, b = ab - a * B;
                 if (a < co_lim && b < ci_lim)
-                    atomicAdd(P.dw + ((size_t)(co_base + a) * P.cin_total + ci_base + b) * KK + j_base + j, stg[i]);
+                    atomicAdd(P.dw + ((size_t)(co_base + a) * P.cin_total + ci_base + b) * KK + r_base + rr, stg[i]);
             }
         }
     }
@@ -241,22 +255,24 @@ int launch_wgrad_taps(const void* x, int x_c, int x_c0, int ci_n, int ci_off, co
     P.K = K; P.pad = K / 2;
     P.tpg = 128 / P.cs;
     P.G = ceil_div(K, P.tpg);
-    P.nky_max = 512 / (P.G * P.cu);
-    if (P.nky_max > K) P.nky_max = K;
-    const int passes = ceil_div(K, P.nky_max);
+    P.nj_max = 512 / (P.G * P.cu);                  // TMEM: G accumulators of nj * cu columns
+    if (P.nj_max > 256 / P.cu) P.nj_max = 256 / P.cu;   // N <= 256 per instruction
+    if (P.nj_max > K) P.nj_max = K;
+    const int passes = ceil_div(K, P.nj_max);
     P.rows = K >= 5 ? 8 : 4;
     if (h <= 4) P.rows = 4;
-    const int box_w = kTpTW + K - 1, box_h = P.rows + P.nky_max - 1;
-    P.s_bytes = box_w * box_h * P.cs * 2;
-    P.u_bytes = kTpTW * P.rows * P.cu * 2;
-    // the U tile sits at the END of the stage (1 KiB aligned); the S box at its start; the windows of the junk taps beyond kx = K-1
-    // read at most 16 pixels past the box, i.e. into the gap or the U tile: finite or not, those accumulator rows are never used
-    // (u_bytes is a multiple of 2 KiB, so the tile at the end of the stage is 1 KiB aligned)
-    P.stage_bytes = ((P.s_bytes + 16 * P.cs * 2 + 1023) & ~1023) + P.u_bytes;
+    const int box_w = kTpTW + K - 1, u_rows = P.rows + P.nj_max - 1;
+    P.s_bytes = box_w * P.rows * P.cs * 2;
+    P.u_bytes = kTpTW * u_rows * P.cu * 2;
+    // the S box at the start of a stage, the U box behind it (1 KiB aligned); the windows of the junk taps beyond tx = K-1
+    // read at most 16 pixels past the S box, i.e. into the gap: finite or not, those accumulator rows are never used
+    // (u_bytes is a multiple of 512 B; the stage size is rounded so that both boxes start 1 KiB aligned)
+    P.u_off = (P.s_bytes + 16 * P.cs * 2 + 1023) & ~1023;
+    P.stage_bytes = P.u_off + ((P.u_bytes + 1023) & ~1023);
     P.stages = kSmemMax / P.stage_bytes;
     if (P.stages > kTpMaxStages) P.stages = kTpMaxStages;
     VSRB_CHECK_ARG(P.stages >= 2, "wgrad_taps: stage of %d bytes does not fit", P.stage_bytes);
-    const int stg_bytes = 16 * P.cs * P.nky_max * K * 4;
+    const int stg_bytes = 16 * P.cs * P.nj_max * K * 4;
     VSRB_CHECK_ARG(stg_bytes <= P.stages * P.stage_bytes, "wgrad_taps: staging block of %d bytes does not fit", stg_bytes);
     P.tiles_x = ceil_div(w, kTpTW);
     P.tiles_per_img = P.tiles_x * ceil_div(h, P.rows);
@@ -280,7 +296,7 @@ int launch_wgrad_taps(const void* x, int x_c, int x_c0, int ci_n, int ci_off, co
     {
         cuuint64_t dims[4] = {(cuuint64_t)s_c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)batch};
         cuuint64_t strides[3] = {(cuuint64_t)s_c * 2, (cuuint64_t)w * s_c * 2, (cuuint64_t)h * w * s_c * 2};
-        cuuint32_t box[4] = {(cuuint32_t)P.cs, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+        cuuint32_t box[4] = {(cuuint32_t)P.cs, (cuuint32_t)box_w, (cuuint32_t)P.rows, 1};
         CUresult r = encode(&P.smap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(s_ptr), dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, swz(P.cs), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("wgrad_taps: tensor map (S) failed with %d", (int)r); return VSRB_E_CUDA; }
@@ -288,7 +304,7 @@ int launch_wgrad_taps(const void* x, int x_c, int x_c0, int ci_n, int ci_off, co
     {
         cuuint64_t dims[4] = {(cuuint64_t)u_c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)batch};
         cuuint64_t strides[3] = {(cuuint64_t)u_c * 2, (cuuint64_t)w * u_c * 2, (cuuint64_t)h * w * u_c * 2};
-        cuuint32_t box[4] = {(cuuint32_t)P.cu, (cuuint32_t)kTpTW, (cuuint32_t)P.rows, 1};
+        cuuint32_t box[4] = {(cuuint32_t)P.cu, (cuuint32_t)kTpTW, (cuuint32_t)u_rows, 1};
         CUresult r = encode(&P.umap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(u_ptr), dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, swz(P.cu), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("wgrad_taps: tensor map (U) failed with %d", (int)r); return VSRB_E_CUDA; }

@@ -112,6 +112,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
         // ---- MMA issuer: D_pair[128 x 64] += X_pair^T[128 x 16] * dZ[16 x 64] for kWgRows K steps x 5 tap pairs ----
         // instruction descriptor: D=f32, A=B=bf16, A and B MN-major (bits 15, 16), N=64, M=128
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | (8u << 24);
+        const bool leader = elect_one();
+        const uint32_t tm0 = __shfl_sync(0xffffffffu, tmem_base, 0);
         int slot = 0;
         uint32_t phase = 0;
         bool first = true;
@@ -119,29 +121,33 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
             const uint32_t sa = stage0 + slot * kWgStageBytes;
             mbar_wait(full0 + 8 * slot, phase, P.dbg, 12, dead);
             tc_fence_after();
-            if (elect_one()) {
-                const uint32_t zb = sa + kWgCopyBytes;
-                constexpr uint32_t kRow = kWgXW * 128u;            // one box row: 18 pixels
+            if (!(P.debug & 2)) {     // warp-uniform arithmetic, only the instruction is predicated on the elected lane (no R2UR)
+                // descriptor low words advance by adds (the issuing thread has ~49 cycles per N = 64 MMA): the high word and the
+                // LBO fields are constants, every window start below is the stage address plus an immediate
+                constexpr uint32_t kRow16 = (kWgXW * 128u) >> 4;    // one box row of 18 pixels, in 16-byte units
+                constexpr uint32_t kHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+                constexpr uint32_t kLboPx = (128u >> 4) << 16, kLboRow = kRow16 << 16;
+                const uint32_t x0 = (sa >> 4) & 0x3FFFu, z0 = ((sa + kWgCopyBytes) >> 4) & 0x3FFFu;
 #pragma unroll
-                for (int ks = 0; ks < ((P.debug & 2) ? 0 : kWgRows); ++ks) {
-                    const uint64_t bd = mn_desc(zb + ks * 2048u, 0u);
+                for (int ks = 0; ks < kWgRows; ++ks) {
+                    const uint32_t bd = z0 + ks * (2048u >> 4);
                     const uint32_t acc = (first && ks == 0) ? 0u : 1u;
                     // pairs (ky,0)&(ky,1): the second tap's window starts one pixel further
 #pragma unroll
                     for (int ky = 0; ky < 3; ++ky)
-                        umma_bf16(tmem_base + ky * 64, mn_desc(sa + (ky + ks) * kRow, 128u), bd, idesc, acc);
+                        if (leader) umma_bf16_words(tm0 + ky * 64, (x0 + (ky + ks) * kRow16) | kLboPx, kHi, bd, kHi, idesc, acc);
                     // pair (0,2)&(1,2): two pixels in, the second tap one box row further down
-                    umma_bf16(tmem_base + 3 * 64, mn_desc(sa + ks * kRow + 256u, kRow), bd, idesc, acc);
+                    if (leader) umma_bf16_words(tm0 + 3 * 64, (x0 + ks * kRow16 + (256u >> 4)) | kLboRow, kHi, bd, kHi, idesc, acc);
                     // (2,2) & a don't-care second half
-                    umma_bf16(tmem_base + 4 * 64, mn_desc(sa + (2 + ks) * kRow + 256u, 128u), bd, idesc, acc);
+                    if (leader) umma_bf16_words(tm0 + 4 * 64, (x0 + (2 + ks) * kRow16 + (256u >> 4)) | kLboPx, kHi, bd, kHi, idesc, acc);
                 }
-                umma_commit(empty0 + 8 * slot);
             }
+            if (leader) umma_commit(empty0 + 8 * slot);
             __syncwarp();
             first = false;
             if (++slot == kWgStages) { slot = 0; phase ^= 1; }
         }
-        if (elect_one()) umma_commit(done);
+        if (leader) umma_commit(done);
         __syncwarp();
     } else if (warp >= 4) {
         // ---- epilogue (once), part 1: TMEM -> shared memory in the OIHW order of the 64(co) x 64(ci) x 9 block.  Lanes
