@@ -345,7 +345,32 @@ def train_cfg4(a, dev, world, rank, local, steps: int = 8, warmup: int = 4, batc
            "ms_per_step": ms, "clips_per_s": world * batch / (ms * 1e-3), "tflops": tf, "frac_of_sustained_peak": tf / world / pk["tf_sust"],
            "loss_first": float(losses[0]), "loss_last": float(losses[-1]), "replicas_identical": same,
            "grad_scale": float(scaler.get_scale()), "steps": steps, "warmup": warmup}
-    del net, model, opt
+    if world == 1:
+        # the opt-in whole-step graph (vsrlab_b200.graphs.GraphedTrainStep: forward + backward + clip + Adam in ONE CUDA graph,
+        # bf16 autocast, no GradScaler): what the same kernels cost when the host is out of the way.  The eager number above
+        # is bound by Python launch overhead and varies with the box's host (42 - 57 ms seen for the same 35 ms of kernels).
+        from vsrlab_b200.graphs import GraphedTrainStep
+        del opt
+        opt_g = torch.optim.Adam(model.parameters(), lr=1e-4, betas=(0.9, 0.99), capturable=True)
+
+        def loss_fn(outs, hr_):
+            sr, lq = outs
+            return charbonnier(sr, hr_) + charbonnier(lq, F.interpolate(hr_.flatten(0, 1), size=(64, 64), mode="bilinear").view_as(lq))
+        gstep = GraphedTrainStep(model, opt_g, loss_fn, (lr, hr), clip_grad_norm=1.0, warmup=3)
+        for _ in range(2):
+            gstep(lr, hr)
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(steps):
+            gl = gstep(lr, hr)
+        g1.record()
+        torch.cuda.synchronize()
+        gms = g0.elapsed_time(g1) / steps
+        out["cuda_graph"] = {"ms_per_step": gms, "clips_per_s": batch / (gms * 1e-3), "tflops": 3.0 * CFG4_FWD_GFLOP.get(a.blocks, float("nan")) / gms,
+                             "loss": float(gl), "recipe": "GraphedTrainStep: bf16 autocast, Adam(capturable), clip 1.0, optimizer step every replay"}
+        del gstep, opt_g
+    del net, model
     VF.set_precision(a.precision)
     return out
 

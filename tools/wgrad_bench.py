@@ -19,14 +19,18 @@ from vsrlab_b200._lib import BF16  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--images", type=int, default=224)
-    ap.add_argument("--modes", default="taps,mma,taps:1,taps:2,taps:3,taps:4")
+    ap.add_argument("--modes", default="taps,mma,taps:1,taps:2,taps:3,taps:4", help="taps | mma | all (= every segment on the tap kernel), each optionally :<VSRB_WG_DEBUG bits>")
+    ap.add_argument("--sides", default="64,32,16")
+    ap.add_argument("--shapes", default="", help="K,cin,x_channels,cout;... instead of the cfg4 list")
     a = ap.parse_args()
     load()
     dev = torch.device("cuda:0")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     CL = torch.channels_last
     shapes = [(7, 8, 16, 32), (7, 32, 32, 64), (7, 64, 64, 32), (7, 32, 32, 16), (7, 16, 16, 2), (3, 3, 16, 64), (1, 128, 128, 64), (3, 64, 64, 64)]
-    for side in (64, 32, 16):
+    if a.shapes:
+        shapes = [tuple(int(v) for v in sh.split(",")) for sh in a.shapes.split(";")]
+    for side in [int(v) for v in a.sides.split(",")]:
         for K, cin, xc, cout in shapes:
             B = a.images
             zc = (cout + 15) // 16 * 16
@@ -43,6 +47,9 @@ def main():
                 name, _, dbg = mode.partition(":")
                 os.environ.pop("VSRB_WGRAD_MMA", None)
                 os.environ.pop("VSRB_WG_DEBUG", None)
+                os.environ.pop("VSRB_WGRAD_TAPS_ALL", None)
+                if name == "all":
+                    os.environ["VSRB_WGRAD_TAPS_ALL"] = "1"
                 if name == "mma":
                     os.environ["VSRB_WGRAD_MMA"] = "1"
                 if dbg:
@@ -60,8 +67,8 @@ def main():
                 us = sorted(ts)[len(ts) // 2]
                 row.append(f"{mode} {us:7.1f} us ({flops / us / 1e6:6.1f} TF/s)")
             print(f"{K}x{K} {cin:3d}->{cout:3d} {B}x{side}x{side}: " + " | ".join(row), flush=True)
-    os.environ.pop("VSRB_WGRAD_MMA", None)
-    os.environ.pop("VSRB_WG_DEBUG", None)
+    for k in ("VSRB_WGRAD_MMA", "VSRB_WG_DEBUG", "VSRB_WGRAD_TAPS_ALL"):
+        os.environ.pop(k, None)
 
 
 if __name__ == "__main__":

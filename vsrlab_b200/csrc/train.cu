@@ -523,7 +523,10 @@ int vsrb_conv2d_wgrad(const vsrb_conv_geom* g, const void* const* in, const int3
     // (co, ci) tile of the mma.sync kernel: as narrow as its segments allow (the FFMA kernels keep 64 x 64)
     int co_t = 64, ci_t = 64, cmax = 0;
     for (int s = 0; s < g->n_seg; ++s) {
-        on_tc[s] = tc_ok && g->seg_c[s] % 64 == 0 && (reinterpret_cast<uintptr_t>(in[s]) & 15) == 0;
+        // (a thin output - the 64 -> 3 image convs - would zero-fill 61 of wgrad_tc's 64 dz columns: the tap kernel takes dz as
+        // its narrow operand instead; VSRB_WGRAD_TAPS_ALL=1 sends every segment there, for A/B measurements)
+        on_tc[s] = tc_ok && g->seg_c[s] % 64 == 0 && (reinterpret_cast<uintptr_t>(in[s]) & 15) == 0 &&
+                   !(taps_ok && (g->cout <= 16 || getenv("VSRB_WGRAD_TAPS_ALL")));
         if (!on_tc[s] && g->seg_c[s] > cmax) cmax = g->seg_c[s];
     }
     if (g->dtype == VSRB_BF16 && !getenv("VSRB_WGRAD_FFMA")) {

@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + 192);
     const uint32_t stage0 = base + 1024;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = P.n0 + (int)blockIdx.y * 64;         // this CTA's 64-wide block of output channels
 
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < kWgStages; ++i) {
@@ -103,7 +104,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
             } else if (elect_one()) {
                 mbar_expect_tx(full0 + 8 * slot, kWgXBytes + kWgZBytes);
                 tma_load_4d(&P.xmap[chunk], full0 + 8 * slot, sa, P.c0, tx * kWgTW - 1, ty * kWgRows - 1, img);
-                tma_load_4d(&P.zmap[chunk], full0 + 8 * slot, sa + kWgCopyBytes, P.n0, tx * kWgTW, ty * kWgRows, img);
+                tma_load_4d(&P.zmap[chunk], full0 + 8 * slot, sa + kWgCopyBytes, n0, tx * kWgTW, ty * kWgRows, img);
             }
             __syncwarp();
             if (++slot == kWgStages) { slot = 0; phase ^= 1; }
@@ -181,8 +182,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
     // of dw[co][ci_off .. ci_off+63][0..8], 8x fewer L2 sector operations than one scattered atomic per (ci, tap) ----
     if (my_tiles > 0 && !(P.debug & 1)) {
         const float* stg = reinterpret_cast<const float*>(base_ptr + 1024);
-        for (int co = 0; co < 64 && P.n0 + co < P.cout; ++co) {
-            float* dst = P.dw + ((size_t)(P.n0 + co) * P.cin_total + P.ci_off) * 9;
+        for (int co = 0; co < 64 && n0 + co < P.cout; ++co) {
+            float* dst = P.dw + ((size_t)(n0 + co) * P.cin_total + P.ci_off) * 9;
             for (int i = threadIdx.x; i < 576; i += kWgThreads) atomicAdd(dst + i, stg[co * 576 + i]);
         }
     }
@@ -344,11 +345,11 @@ int launch_wgrad_tc_multi(const void* const* xs, int x_c, int c0, int ci_off, co
         const char* c = getenv("VSRB_WG_CTAS");
         if (c && atoi(c) > 0 && atoi(c) < ctas) ctas = atoi(c);
     }
-    for (int nb = 0; nb < n_blocks; ++nb) {          // one launch per 64-wide output block; they run concurrently-ish back to back
-        P.n0 = nb * 64;
-        wgrad_tc_kernel<<<ctas, kWgThreads, kWgSmem, stream>>>(P);
-        VSRB_LAUNCH_CHECK();
-    }
+    // blockIdx.y = 64-wide output block: all blocks of a wide layer (64 -> 256) share ONE launch.  (A launch per block on
+    // sms / n_blocks CTAs each ran them one after the other - same stream - on a quarter of the GPU: 560 -> 230 us.)
+    P.n0 = 0;
+    wgrad_tc_kernel<<<dim3(ctas, n_blocks), kWgThreads, kWgSmem, stream>>>(P);
+    VSRB_LAUNCH_CHECK();
     return VSRB_OK;
 }
 
