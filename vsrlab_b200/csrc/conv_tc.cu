@@ -332,6 +332,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         int slot = 0;
         uint32_t phase = 0;
         TileWalk tw(blockIdx.x, gridDim.x, P.tiles_x, P.tiles_per_img);
+        const bool stat = (P.debug & 32) && blockIdx.x == 0 && blockIdx.y == 0;      // VSRB_TC_DEBUG bit 32: wait-cycle accounting of CTA 0
+        long long st_t0 = stat ? clock64() : 0, st_wait = 0;
         // pair: the loop runs while the LEADER's tile exists; an odd tile count leaves the peer one dummy tile whose
         // loads fall outside the tensor (zero fill) and whose result is never stored
         for (int tile = blockIdx.x; tile - (int)crank < tiles_g; tile += gridDim.x, tw.next()) {
@@ -345,7 +347,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 int chunk = 0, kx = 0;
                 for (int local = 0; local < P.seg_stages[s]; ++local) {
                     const uint32_t sa = slots0 + slot * P.slot_bytes;
+                    const long long w0 = stat ? clock64() : 0;
                     mbar_wait(empty0 + 8 * slot, phase ^ 1, P.dbg, 1, dead);
+                    if (stat) st_wait += clock64() - w0;
                     if (elect_one()) {
                         if constexpr (kPair) {                 // both tiles' bytes are counted on the leader's barrier
                             if (P.debug & 1) {
@@ -392,6 +396,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 if (++slot == P.num_slots) { slot = 0; phase ^= 1; }
             }
         }
+        if (stat && lane == 0) { g_trace[300 * 8 + 0] = clock64() - st_t0; g_trace[300 * 8 + 1] = st_wait; }
     } else if (warp == 1) {
         // =============================== MMA issuer =================================
         // instruction descriptor: D=f32, A=B=bf16, K-major both, N>>3 @17, M>>4 @24
@@ -408,8 +413,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         int slot = 0, acc = 0;
         uint32_t phase = 0, acc_phase = 0;
         bool first_stage = true;
+        const bool stat = (P.debug & 32) && blockIdx.x == 0 && blockIdx.y == 0;
+        long long st_t0 = stat ? clock64() : 0, st_we = 0, st_wf = 0;
         for (int tile = blockIdx.x; tile < tiles_g && crank == 0; tile += gridDim.x) {
+            const long long w0 = stat ? clock64() : 0;
             mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1, P.dbg, 3, dead);
+            if (stat) st_we += clock64() - w0;
             tc_fence_after();
             const uint32_t d0 = tmem_base + acc * P.acc_cols;
             bool first = true;
@@ -424,7 +433,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 for (int local = 0; local < P.seg_stages[s]; ++local) {
                     const uint32_t sa = slots0 + slot * P.slot_bytes;
                     const uint32_t sb = kPair ? (wres + boff / 2) : (P.resident ? (wres + boff) : (sa + P.seg_abytes[s]));
+                    const long long w1 = stat ? clock64() : 0;
                     mbar_wait(full0 + 8 * slot, phase, P.dbg, 4, dead);
+                    if (stat) st_wf += clock64() - w1;
                     tc_fence_after();
                     if (first_stage && lane == 0) trace_stamp(P.debug, 3);
                     first_stage = false;
@@ -469,6 +480,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             __syncwarp();
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (stat && lane == 0) { g_trace[301 * 8 + 0] = clock64() - st_t0; g_trace[301 * 8 + 1] = st_we; g_trace[301 * 8 + 2] = st_wf; }
     }
     } else {
         if constexpr (kPair) asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
@@ -503,6 +515,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const int actm = act_k == 1.f ? 0 : (act_k == 0.f ? 1 : 2);
         const uint32_t tempty_lead = kPair ? mapa_rank(tempty0, 0) : 0u;
         TileWalk tw(blockIdx.x, gridDim.x, P.tiles_x, P.tiles_per_img);
+        const bool estat = (P.debug & 32) && blockIdx.x == 0 && blockIdx.y == 0 && warp == 4;
+        long long est_t0 = estat ? clock64() : 0, est_w = 0;
         for (int tile = blockIdx.x; tile - (int)crank < tiles_g; tile += gridDim.x, tw.next()) {
             const bool dummy = kPair && tile >= tiles_g;       // the pair's odd tile out: handshakes only
             if (alt && eh != acc) {                            // the twin warp's tile
@@ -531,7 +545,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                     }
                 }
             }
+            const long long w2 = estat ? clock64() : 0;
             mbar_wait(tfull0 + 8 * acc, acc_phase, P.dbg, 5, dead);
+            if (estat) est_w += clock64() - w2;
             tc_fence_after();
             if (tile == (int)blockIdx.x && warp == 4 && lane == 0) trace_stamp(P.debug, 4);
             for (int m = 0; m < (((P.debug & 8) || dummy) ? 0 : P.MT); ++m) {
@@ -682,6 +698,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (estat && lane == 0) { g_trace[302 * 8 + 0] = clock64() - est_t0; g_trace[302 * 8 + 1] = est_w; }
         if (warp == 4 && lane == 0) trace_stamp(P.debug, 5);
         if (kStaged && eh == 0 && lane == 0) bulk_wait_all();   // staged tiles must be read out before shared memory goes away
         if (warp == 4 && lane == 0) trace_stamp(P.debug, 6);
