@@ -415,6 +415,42 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         bool first_stage = true;
         const bool stat = (P.debug & 32) && blockIdx.x == 0 && blockIdx.y == 0;
         long long st_t0 = stat ? clock64() : 0, st_we = 0, st_wf = 0;
+        // One operand, one stage per tile, no residual stage (the thin image / flow convs, whose MMA warp is the bound): every
+        // per-op value is loop invariant and the tile body is two waits, the MMAs and two commits.
+        const bool simple = P.n_ops == 1 && P.seg_stages[P.op_wseg[0]] == 1 && !P.res_mma && kKW > 0 && !(P.debug & (4 | 32 | 128));     // (bit 128: A/B switch)
+        if (simple) {
+            const int s = P.op_wseg[0];
+            const uint32_t rb = P.seg_rowbytes[s];
+            const uint32_t desc_hi = ((rb * 8u) >> 4) | (1u << 14) | ((uint32_t)P.seg_layout[s] << 29);
+            const uint32_t a_ky = (P.TW * rb) >> 4, b_ky = ((kPair ? P.ns / 2 : P.ns) * rb) >> 4, a_m = (P.rows_sub * P.TW * rb) >> 4;
+            const int ksteps = P.seg_ck[s] >> 4, MT = P.MT, ns = P.ns;
+            const uint32_t sb_res = kPair ? (wres + P.seg_woff[s] / 2) : (wres + P.seg_woff[s]);
+            const uint32_t b_off = P.seg_abytes[s], slot_bytes = P.slot_bytes, acc_cols = P.acc_cols;
+            const bool resident = kPair || P.resident;
+            const int num_slots = P.num_slots;
+            for (int tile = blockIdx.x; tile < tiles_g && crank == 0; tile += gridDim.x) {
+                mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1, P.dbg, 3, dead);
+                mbar_wait(full0 + 8 * slot, phase, P.dbg, 4, dead);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t sa = slots0 + slot * slot_bytes;
+                    const uint32_t sb = resident ? sb_res : (sa + b_off);
+                    const uint32_t d0 = tmem_base + acc * acc_cols;
+                    const uint32_t a_lo = ((sa >> 4) & 0x3FFFu) | (1u << 16), b_lo = ((sb >> 4) & 0x3FFFu) | (1u << 16);
+                    issue_stage<kKW == 0 ? 1 : kKW, kPair>(d0, a_lo, b_lo, desc_hi, idesc, MT, ns, a_m, a_ky, b_ky, ksteps, true);
+                    if constexpr (kPair) {
+                        umma_commit_pair(empty0 + 8 * slot);
+                        umma_commit_pair(tfull0 + 8 * acc);
+                    } else {
+                        umma_commit(empty0 + 8 * slot);
+                        umma_commit(tfull0 + 8 * acc);
+                    }
+                }
+                __syncwarp();
+                if (++slot == num_slots) { slot = 0; phase ^= 1; }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        } else
         for (int tile = blockIdx.x; tile < tiles_g && crank == 0; tile += gridDim.x) {
             const long long w0 = stat ? clock64() : 0;
             mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1, P.dbg, 3, dead);
