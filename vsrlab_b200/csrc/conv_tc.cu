@@ -417,7 +417,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         long long st_t0 = stat ? clock64() : 0, st_we = 0, st_wf = 0;
         // One operand, one stage per tile, no residual stage (the thin image / flow convs, whose MMA warp is the bound): every
         // per-op value is loop invariant and the tile body is two waits, the MMAs and two commits.
-        const bool simple = P.n_ops == 1 && P.seg_stages[P.op_wseg[0]] == 1 && !P.res_mma && kKW > 0 && !(P.debug & (4 | 32 | 128));     // (bit 128: A/B switch)
+        const bool simple = P.n_ops == 1 && P.seg_stages[P.op_wseg[0]] == 1 && !P.res_mma && kKW > 0 && !(P.debug & (4 | 128));     // (bit 128: A/B switch)
         if (simple) {
             const int s = P.op_wseg[0];
             const uint32_t rb = P.seg_rowbytes[s];
@@ -429,8 +429,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             const bool resident = kPair || P.resident;
             const int num_slots = P.num_slots;
             for (int tile = blockIdx.x; tile < tiles_g && crank == 0; tile += gridDim.x) {
+                const long long w0 = stat ? clock64() : 0;
                 mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1, P.dbg, 3, dead);
+                const long long w1 = stat ? clock64() : 0;
                 mbar_wait(full0 + 8 * slot, phase, P.dbg, 4, dead);
+                if (stat) { st_we += w1 - w0; st_wf += clock64() - w1; }
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t sa = slots0 + slot * slot_bytes;
