@@ -177,3 +177,30 @@ def test_perceptual_loss_on_the_conv_kernels(dev):
     x = torch.randn(4, 1, 8, 8, device=dev)
     assert torch.allclose(adv(x, 1, False), F.binary_cross_entropy_with_logits(x, torch.ones_like(x)) * 2e-5)
     assert torch.allclose(adv(x, 0, True), F.binary_cross_entropy_with_logits(x, torch.zeros_like(x)))
+
+
+def test_two_forwards_before_backward_keep_their_own_weights(dev):
+    """train_gan.py:49-58: D(hr) and D(sr) are both called before the backward.  In training mode each call moves the
+    power-iteration vectors, so the two graphs hold different normalised weights - like torch, each backward must use its own."""
+    from vsrlab.core.modules.conv import SpectralConv
+    torch.manual_seed(4)
+    m = SpectralConv(64, 64, 3, 1, 1).to(dev).train()
+    ref = SpectralConv(64, 64, 3, 1, 1).to(dev).train()
+    ref.load_state_dict(m.state_dict())
+    x1 = torch.randn(2, 64, 16, 24, device=dev).to(torch.bfloat16).float()
+    x2 = torch.randn(2, 64, 16, 24, device=dev).to(torch.bfloat16).float()
+    a1, a2 = x1.clone().requires_grad_(True), x2.clone().requires_grad_(True)
+    (m(a1).sum() + 3.0 * m(a2).sum()).backward()
+    b1, b2 = x1.clone().requires_grad_(True), x2.clone().requires_grad_(True)
+    (ref.conv(b1).sum() + 3.0 * ref.conv(b2).sum()).backward()
+    assert rel(a1.grad, b1.grad) < 1e-2 and rel(a2.grad, b2.grad) < 1e-2
+    assert rel(m.conv.weight_orig.grad, ref.conv.weight_orig.grad) < 2e-2
+    # (the first call's input gradient must come from the FIRST normalised weight: at a random initialisation one power
+    # iteration changes the weight by far more than the tolerance above)
+    import gc
+    from vsrlab_b200 import functional as VF, autograd as A
+    n0 = (len(VF._packed), len(A._packed_t))
+    for _ in range(5):
+        m(x1).sum().backward()
+    gc.collect()
+    assert len(VF._packed) <= n0[0] + 1 and len(A._packed_t) <= n0[1] + 1          # per-call holders do not pile up

@@ -38,7 +38,7 @@ def _packed_transposed(conv) -> ops.PackedConvT:
     pc = _packed_t.get(key)
     if pc is None or pc.stamp != ops.PackedConv.stamp_of(convs) or any(r() is not c for r, c in zip(pc.owners_t, convs)):
         pc = ops.PackedConvT(convs, BF16)                       # (ids are recycled: the owners must be the same live modules)
-        pc.owners_t = [weakref.ref(c) for c in convs]
+        pc.owners_t = [weakref.ref(c, lambda _r, k=key: _packed_t.pop(k, None)) for c in convs]
         _packed_t[key] = pc
     return pc
 
@@ -474,21 +474,36 @@ def realbasicvsr(model, lr: torch.Tensor):
 # GAN discriminator: SpectralConv / UNetDiscriminator on the same conv kernels
 # --------------------------------------------------------------------------------------
 class _DerivedConv:
-    """What ConvFn / PackedConv read from an nn.Conv2d, for a weight that is DERIVED from the module's parameters on every
-    call (spectral normalisation; the 3x3 re-layout of a 4x4 stride-2 filter).  One holder lives on each module; bumping
-    `_vsrb_version` invalidates the packed image even when the fresh weight tensor reuses an old address."""
+    """What ConvFn / PackedConv read from an nn.Conv2d, for a weight that is DERIVED from the module's parameters (spectral
+    normalisation; the 3x3 re-layout of a 4x4 stride-2 filter).  Under autograd every forward call gets its OWN holder: the
+    node keeps it alive until its backward has run, so a second forward before that backward (train_gan.py:52-53 calls the
+    discriminator on hr and on sr, then backpropagates both) cannot swap the weight under the first one's input-gradient
+    conv.  The packed-weight caches drop an entry when its holder dies."""
 
     def __init__(self):
         self.weight = self.bias = None
         self.kernel_size = (3, 3)
         self.in_channels = self.out_channels = 0
-        self._vsrb_version = 0
+        self.stamp = None
 
     def set(self, weight):
         self.weight = weight
         self.out_channels, self.in_channels = weight.shape[0], weight.shape[1]
-        self._vsrb_version += 1
         return self
+
+
+def _holder(sc, conv, w: torch.Tensor, derive):
+    """Holder of derive(w): per call when a graph is recorded or the module is in training mode (u / v move every call);
+    otherwise one per module, rebuilt when the parameters or the power-iteration vectors changed."""
+    if conv.training or (torch.is_grad_enabled() and w.requires_grad):
+        return _DerivedConv().set(derive(w))
+    stamp = tuple((t.data_ptr(), t._version) for t in (conv.weight_orig, conv.weight_u, conv.weight_v))
+    h = sc.__dict__.get("_vsrb_holder")
+    if h is None or h.stamp != stamp:
+        h = _DerivedConv().set(derive(w))
+        h.stamp = stamp
+        sc.__dict__["_vsrb_holder"] = h
+    return h
 
 
 def _normalised_weight(conv):
@@ -527,15 +542,14 @@ def spectral_conv(sc, x: torch.Tensor, act: str, slope: float) -> torch.Tensor:
     pixel-unshuffle + 3x3 (exact)."""
     conv = sc.conv
     w = _normalised_weight(conv)
-    holder = sc.__dict__.setdefault("_vsrb_holder", _DerivedConv())
     cin = conv.in_channels
     if conv.kernel_size == (3, 3) and conv.stride == (1, 1) and conv.padding == (1, 1):
-        return globals()["conv"](holder.set(w), [x], [(0, cin)], act, slope)
+        return globals()["conv"](_holder(sc, conv, w, lambda t: t), [x], [(0, cin)], act, slope)
     if conv.kernel_size == (4, 4) and conv.stride == (2, 2) and conv.padding == (1, 1):
         if cin % 4:
             raise VsrbError("4x4 stride-2 SpectralConv: in_channels must be a multiple of 4 on this path")
         xs = _cl(F.pixel_unshuffle(x[:, :cin], 2))
-        return globals()["conv"](holder.set(_stride2_as_3x3(w)), [xs], [(0, 4 * cin)], act, slope)
+        return globals()["conv"](_holder(sc, conv, w, _stride2_as_3x3), [xs], [(0, 4 * cin)], act, slope)
     raise VsrbError(f"SpectralConv geometry k={conv.kernel_size} stride={conv.stride} pad={conv.padding} is not implemented "
                     "(3x3 s1 p1 and 4x4 s2 p1 are)")
 

@@ -112,7 +112,9 @@ def packed(convs: Sequence[torch.nn.Conv2d], segs: Sequence[Tuple[int, int]], dt
     pc = _packed.get(key)
     if pc is None or pc.stamp != ops.PackedConv.stamp_of(convs) or not _same_objects(pc.owners, convs):
         pc = ops.PackedConv(convs, segs, dt, pixshuf)
-        pc.owners = [weakref.ref(c) for c in convs]
+        # the entry dies with its owners (per-call holders of derived weights - spectral norm - would pile up otherwise; a
+        # recycled id whose new entry gets popped by a stale callback only costs one re-pack)
+        pc.owners = [weakref.ref(c, lambda _r, k=key: _packed.pop(k, None)) for c in convs]
         _packed[key] = pc
     return pc
 

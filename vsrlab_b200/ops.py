@@ -136,9 +136,7 @@ class PackedConv:
         """Identity + version of the parameters a packed image was built from.  In-place updates through `param.data`
         bypass `_version`: code that writes weights that way must call `functional.clear_caches()` afterwards
         (optimizers, `load_state_dict` and `.to()` all bump the version or replace the storage)."""
-        # `_vsrb_version`: bumped by holders of derived weights (spectral norm), whose fresh tensors can reuse an address
-        return tuple((c.weight.data_ptr(), c.weight._version, 0 if c.bias is None else c.bias._version, getattr(c, "_vsrb_version", 0))
-                     for c in convs)
+        return tuple((c.weight.data_ptr(), c.weight._version, 0 if c.bias is None else c.bias._version) for c in convs)
 
 
 def conv2d_fwd(pc: PackedConv, ins: Sequence, in_c: Sequence[int], batch: int, h: int, w: int, *,
