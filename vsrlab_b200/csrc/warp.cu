@@ -400,25 +400,52 @@ __global__ void pixel_unshuffle2_kernel(const uint4* __restrict__ src, uint4* __
 
 namespace vsrb {
 // 3x3 im2col of 3-channel frames: one thread per (pixel, 16-byte quarter of its 64-byte patch row): eight of the 27
-// neighbourhood values (+ 5 zeros at the end), so a warp's stores are 512 consecutive bytes
-__global__ void im2col3x3_c3_kernel(const float* __restrict__ src, uint4* __restrict__ dst, int n, int h, int w) {
-    const long long total = (long long)n * h * w * 4;
-    const long long plane = (long long)h * w;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int j = (int)(i & 3);
-        const long long pix = i >> 2;
-        const int x = (int)(pix % w);
-        const long long t = pix / w;
-        const int y = (int)(t % h);
-        const float* fp = src + (t / h) * 3 * plane;
+// neighbourhood values (+ 5 zeros at the end), so a warp's stores are 512 consecutive bytes.  blockIdx.x = image row
+// (img * h + y), threads run along the row: 32-bit index arithmetic, no divisions by w / h per element (the first version
+// spent most of its 235 us per 60 frames on three 64-bit div / mod per thread), neighbouring pixels' loads hit in L1.
+__global__ void __launch_bounds__(256) im2col3x3_c3_kernel(const float* __restrict__ src, uint4* __restrict__ dst, int h, int w) {
+    const int row = blockIdx.x;                         // img * h + y
+    const int img = row / h, y = row - img * h;
+    const int plane = h * w;
+    const float* fp = src + (size_t)img * 3 * plane;
+    uint4* out = dst + (size_t)row * w * 4;
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < 4 * w; i += gridDim.y * blockDim.x) {
+        const int j = i & 3, x = i >> 2;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int k = 8 * j + e, tap = k / 3, c = k - tap * 3;          // (j and e are small: constant-folded per j)
+            const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+            v[e] = (k < 27 && yy >= 0 && yy < h && xx >= 0 && xx < w) ? __ldg(fp + c * plane + yy * w + xx) : 0.f;
+        }
+        out[i] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    }
+}
+// The same through shared memory: a block stages the three input rows of its image row (3 channels x 3 rows x (w + 2)
+// floats, zero padded, coalesced loads) and builds the patches from there - the direct kernel's eight scattered 4-byte
+// loads per thread kept it at 1.4 TB/s; this one is bound by its 64 bytes of output per pixel.
+__global__ void __launch_bounds__(256) im2col3x3_c3_smem_kernel(const float* __restrict__ src, uint4* __restrict__ dst, int h, int w) {
+    extern __shared__ float rows_s[];                   // [c * 3 + dy][w + 2]
+    const int row = blockIdx.x;
+    const int img = row / h, y = row - img * h;
+    const int plane = h * w, pitch = w + 2;
+    const float* fp = src + (size_t)img * 3 * plane;
+    for (int idx = threadIdx.x; idx < 9 * pitch; idx += blockDim.x) {
+        const int r = idx / pitch, xx = idx - r * pitch - 1;
+        const int c = r / 3, yy = y + (r - c * 3) - 1;
+        rows_s[idx] = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? __ldg(fp + c * plane + yy * w + xx) : 0.f;
+    }
+    __syncthreads();
+    uint4* out = dst + (size_t)row * w * 4;
+    for (int i = threadIdx.x; i < 4 * w; i += blockDim.x) {
+        const int j = i & 3, x = i >> 2;
         float v[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const int k = 8 * j + e, tap = k / 3, c = k - tap * 3;
-            const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
-            v[e] = (k < 27 && yy >= 0 && yy < h && xx >= 0 && xx < w) ? __ldg(fp + c * plane + (long long)yy * w + xx) : 0.f;
+            v[e] = k < 27 ? rows_s[(c * 3 + tap / 3) * pitch + x + tap % 3] : 0.f;
         }
-        dst[i] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        out[i] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
     }
 }
 }  // namespace vsrb
@@ -428,8 +455,17 @@ extern "C" {
 int vsrb_im2col3x3_c3(const float* frames, void* patches, int32_t n, int32_t h, int32_t w, void* stream) {
     VSRB_CHECK_ARG(frames && patches && n >= 1 && h >= 1 && w >= 1, "im2col3x3_c3: bad arguments");
     VSRB_CHECK_ARG((reinterpret_cast<uintptr_t>(patches) & 15) == 0, "im2col3x3_c3: output must be 16-byte aligned");
-    const long long total = (long long)n * h * w * 4;
-    vsrb::im2col3x3_c3_kernel<<<vsrb::grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(frames, reinterpret_cast<uint4*>(patches), n, h, w);
+    const long long rows = (long long)n * h;
+    VSRB_CHECK_ARG((long long)h * w * 3 < (1LL << 31) && rows <= 0x7fffffffLL && w <= (1 << 22), "im2col3x3_c3: image too large");
+    const size_t smem = (size_t)9 * (w + 2) * sizeof(float);
+    if (smem <= 48 * 1024) {                            // rows up to 1 363 pixels: no opt-in needed
+        vsrb::im2col3x3_c3_smem_kernel<<<(unsigned)rows, 256, smem, (cudaStream_t)stream>>>(frames, reinterpret_cast<uint4*>(patches), h, w);
+    } else {
+        unsigned gy = (unsigned)((4 * w + 255) / 256);
+        if (gy > 65535u) gy = 65535u;
+        dim3 grid((unsigned)rows, gy);
+        vsrb::im2col3x3_c3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(frames, reinterpret_cast<uint4*>(patches), h, w);
+    }
     VSRB_LAUNCH_CHECK();
     return VSRB_OK;
 }
