@@ -713,6 +713,19 @@ def test_ring_walk_stems_with_im2col_patches(dev, case, monkeypatch):
     assert (outs[1] - y).abs().max().item() <= 2.0 ** -8 * scale
 
 
+@pytest.mark.parametrize("shape", [(3, 37, 53), (2, 180, 320), (1, 5, 1500), (2, 1, 1), (1, 3, 2)], ids=str)
+def test_im2col3x3_patches(dev, shape):
+    """vsrb_im2col3x3_c3 (the K = 32 operand of the image stems): bit-exact bf16 of the 3x3 neighbourhoods, zero padded, in
+    (ky, kx, c) order with five zero columns; rows wider than 1 363 pixels take the kernel without shared-memory staging."""
+    from vsrlab_b200 import ops
+    n, h, w = shape
+    x = torch.rand(n, 3, h, w, generator=torch.Generator().manual_seed(n * h + w)).to(dev)
+    p = torch.full((n, h, w, 32), float("nan"), dtype=torch.bfloat16, device=dev)
+    ops.im2col3x3(x, p, n, h, w)
+    want = F.unfold(x, 3, padding=1).view(n, 3, 9, h, w).permute(0, 3, 4, 2, 1).reshape(n, h, w, 27).to(torch.bfloat16)
+    assert torch.equal(p[..., :27], want) and (p[..., 27:] == 0).all()
+
+
 @pytest.mark.parametrize("case", [(2, 45, 64), (1, 180, 320), (3, 23, 61)], ids=lambda c: f"n{c[0]}_{c[1]}x{c[2]}")
 def test_fused_warp_stem_equals_warp_then_conv(dev, case, monkeypatch):
     """North-star part 2 (basicvsr.py:52-58,66-73: flow_warp -> cat([lr_i, feat]) -> stem conv): the ring-walk stem that
