@@ -538,3 +538,81 @@ def test_ddp_nccl_two_ranks_replicas_stay_identical():
     for rank, same_w, same_g, losses, finite in res:
         assert same_w and same_g and finite, (rank, same_w, same_g)
     assert res[0][3] != res[1][3]                       # the ranks really saw different data
+
+
+def test_training_forward_is_graphed_after_warmup_and_matches_eager(dev):
+    """vsrlab_b200.graphs.training_forward: after three eager calls with one shape the model's forward and backward replay
+    from CUDA graphs inside the caller's unchanged AMP loop (autocast + GradScaler + accumulation + clip + Adam).  Same
+    losses and weights as the eager path (the weight-gradient atomics make the two runs differ in the last bits only),
+    in-place refinement of the input kept, other shapes / no_grad calls unaffected."""
+    import warnings
+    from vsrlab.vsr.models.RealBasicVSR.realbasicvsr import RealBasicVSR
+    from vsrlab_b200 import graphs
+
+    def run(use_graphs):
+        graphs.TRAIN_GRAPHS = use_graphs
+        torch.manual_seed(0)
+        net = RealBasicVSR(cleaning_blocks=1, mid_channels=64, upscale=4, res_blocks=1, pretrained_flow=False, train_flow=True).to(dev).train()
+        opt = torch.optim.Adam(net.parameters(), lr=1e-4)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            scaler = torch.cuda.amp.GradScaler()
+        g = torch.Generator().manual_seed(1)
+        losses = []
+        for i in range(8):
+            lr = torch.rand(2, 5, 3, 32, 32, generator=g).to(dev)
+            hr = torch.rand(2, 5, 3, 128, 128, generator=g).to(dev)
+            lr0 = lr.clone()
+            with torch.autocast("cuda", dtype=torch.float16):
+                sr, lq = net(lr)
+                loss = torch.sqrt((sr - hr) ** 2 + 1e-9).mean() + torch.sqrt((lq - F.interpolate(hr.flatten(0, 1), size=(32, 32), mode="bilinear").view_as(lq)) ** 2 + 1e-9).mean()
+            assert torch.equal(lr, lq.detach()) and not torch.equal(lr, lr0)          # refined in place, as the reference
+            scaler.scale(loss / 2).backward()
+            if i % 2 == 1:
+                scaler.unscale_(opt)
+                torch.nn.utils.clip_grad_norm_(net.parameters(), 1.0)
+                scaler.step(opt)
+                scaler.update()
+                opt.zero_grad()
+            losses.append(loss.item())
+        entry = graphs._train_entries.get(id(net))
+        graphed = entry is not None and entry.graphed is not None
+        if graphed:
+            # two forwards before one backward: the second must not clobber what the graph saved for the first
+            xa, xb = torch.rand(2, 5, 3, 32, 32, device=dev), torch.rand(2, 5, 3, 32, 32, device=dev)
+            with torch.autocast("cuda", dtype=torch.float16):
+                sa, _ = net(xa.clone())
+                assert entry.graphed.pending
+                sb, _ = net(xb.clone())                     # runs eagerly
+            opt.zero_grad()
+            (sa.mean() + 2 * sb.mean()).backward()
+            ga = torch.cat([p.grad.flatten() for p in net.parameters()])
+            assert not entry.graphed.pending
+            graphs.TRAIN_GRAPHS = False
+            opt.zero_grad()
+            with torch.autocast("cuda", dtype=torch.float16):
+                sa2, _ = net(xa.clone())
+                sb2, _ = net(xb.clone())
+            (sa2.mean() + 2 * sb2.mean()).backward()
+            graphs.TRAIN_GRAPHS = True
+            ge = torch.cat([p.grad.flatten() for p in net.parameters()])
+            assert cos(ga, ge) > 0.9999 and rel(ga, ge) < 2e-2
+            opt.zero_grad()
+        # another shape and a no_grad call keep working
+        with torch.autocast("cuda", dtype=torch.float16):
+            sr2, _ = net(torch.rand(1, 3, 3, 16, 24, device=dev))
+        sr2.mean().backward()
+        net.eval()
+        with torch.no_grad():
+            sr3, _ = net(torch.rand(1, 3, 3, 16, 24, device=dev))
+        assert sr3.shape == (1, 3, 3, 64, 96)
+        return losses, torch.cat([p.detach().flatten() for p in net.parameters()]), graphed
+
+    try:
+        l_g, w_g, graphed = run(True)
+        l_e, w_e, not_graphed = run(False)
+    finally:
+        graphs.TRAIN_GRAPHS = True
+    assert graphed and not not_graphed
+    assert max(abs(a - b) / abs(b) for a, b in zip(l_g, l_e)) < 2e-3, (l_g, l_e)
+    assert cos(w_g, w_e) > 0.99999 and rel(w_g, w_e) < 1e-3

@@ -35,6 +35,9 @@ def _packed_transposed(conv) -> ops.PackedConvT:
     """`conv`: one module, or a tuple of same-shaped modules (weight groups)."""
     convs = tuple(conv) if isinstance(conv, (list, tuple)) else (conv,)
     key = tuple(id(c) for c in convs)
+    from . import functional as VF
+    if VF.REPACK_IN_CAPTURE and torch.cuda.is_current_stream_capturing():
+        return ops.PackedConvT(convs, BF16)                     # weights change between replays: the pack kernels are part of the graph
     pc = _packed_t.get(key)
     if pc is None or pc.stamp != ops.PackedConv.stamp_of(convs) or any(r() is not c for r, c in zip(pc.owners_t, convs)):
         pc = ops.PackedConvT(convs, BF16)                       # (ids are recycled: the owners must be the same live modules)
@@ -458,15 +461,17 @@ def basicvsr(bv, lrs: torch.Tensor) -> torch.Tensor:
     return (x + skip).view(n, t, c, h * scale, w * scale)
 
 
-def realbasicvsr(model, lr: torch.Tensor):
+def realbasicvsr(model, lr: torch.Tensor, write_back: bool = True):
     """(sr, lq) with gradients.  The cleaned clip is also written back into the caller's `lr`, which is what the
-    reference's in-place refinement leaves there (realbasicvsr.py:26-29)."""
+    reference's in-place refinement leaves there (realbasicvsr.py:26-29); `write_back=False` leaves that to the caller
+    (graphs.py replays this body on a static copy of the input)."""
     n, t, c, h, w = lr.shape
     with batched_wgrad():
         lq = cleaner(model.cleaner, lr.reshape(n * t, c, h, w).float()).view(n, t, c, h, w)
         sr = basicvsr(model.basicvsr, lq)
-    with torch.no_grad():
-        lr.copy_(lq)
+    if write_back:
+        with torch.no_grad():
+            lr.copy_(lq)
     return sr, lq
 
 

@@ -107,7 +107,15 @@ def _same_objects(refs, objs) -> bool:
     return len(refs) == len(objs) and all(r() is o for r, o in zip(refs, objs))
 
 
+# Set while graphs.py captures a TRAINING forward / backward: the weights change between replays, so the pack kernels
+# must be recorded in the graph instead of being skipped by the cache below.  (The inference graphs are re-captured when a
+# weight changes and keep using the cache.)
+REPACK_IN_CAPTURE = False
+
+
 def packed(convs: Sequence[torch.nn.Conv2d], segs: Sequence[Tuple[int, int]], dt: int, pixshuf: int = 0) -> ops.PackedConv:
+    if REPACK_IN_CAPTURE and torch.cuda.is_current_stream_capturing():
+        return ops.PackedConv(convs, segs, dt, pixshuf)
     key = (tuple(id(c) for c in convs), tuple(segs), dt, pixshuf)
     pc = _packed.get(key)
     if pc is None or pc.stamp != ops.PackedConv.stamp_of(convs) or not _same_objects(pc.owners, convs):
@@ -657,7 +665,9 @@ def realbasicvsr_forward(model, lr: torch.Tensor):
     """(sr, lq) = RealBasicVSR.forward; `lq` is `lr` itself, refined in place (realbasicvsr.py:11-15, 26-29)."""
     ops.require_cuda(lr, "lr")
     if _wants_grad(model, lr):
-        return _autograd().realbasicvsr(model, lr)
+        _autograd()
+        from . import graphs
+        return graphs.training_forward(model, lr)
     if lr.dtype != torch.float32:
         raise VsrbError("RealBasicVSR refines its input in place and needs an fp32 tensor (reference realbasicvsr.py:29)")
     if not lr.is_contiguous():
