@@ -347,8 +347,8 @@ def train_cfg4(a, dev, world, rank, local, steps: int = 8, warmup: int = 4, batc
            "grad_scale": float(scaler.get_scale()), "steps": steps, "warmup": warmup}
     from vsrlab_b200 import graphs as _graphs
     ent = _graphs._train_entries.get(id(model))
-    # single GPU: after three eager calls the model's forward / backward replay from CUDA graphs inside this unchanged loop
-    # (vsrlab_b200.graphs.training_forward); under torch.distributed the loop stays eager
+    # after three eager calls the model's forward / backward replay from CUDA graphs inside this unchanged loop
+    # (vsrlab_b200.graphs.training_forward), under DDP too
     out["fwd_bwd_graphed"] = bool(ent is not None and ent.graphed is not None)
     if world == 1:
         # the opt-in whole-step graph (vsrlab_b200.graphs.GraphedTrainStep: forward + backward + clip + Adam in ONE CUDA graph,

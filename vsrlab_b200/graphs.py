@@ -4,8 +4,8 @@
    issues ~2 000 launches per micro-step from Python; on 64x64 patches the GPU finishes them in 33 ms while the host needs
    36 - 60 ms to issue them, depending on the box.  After a few eager calls with the same input shape the forward and the
    backward of the model are captured once (the `torch.cuda.make_graphed_callables` recipe) and replayed: the caller's loop - autocast,
-   GradScaler, gradient accumulation, clipping, optimizer - stays what it is.  `VSRB_TRAIN_GRAPHS=0` switches it off; it is
-   not used under `torch.distributed` (DDP's bucket hooks want the eager autograd graph) nor inside someone else's capture.
+   GradScaler, gradient accumulation, clipping, optimizer, DDP wrapper - stays what it is.  `VSRB_TRAIN_GRAPHS=0` switches it
+   off (`VSRB_TRAIN_GRAPHS_DDP=0`: only under torch.distributed); it is not used inside someone else's capture.
 2. `GraphedTrainStep` (opt-in): whole-step capture for training loops that can afford static shapes.
 
 The reference's `train.py` launches ~1 500 kernels per step from Python; on 64x64 patches the B200 finishes them faster than
@@ -31,6 +31,10 @@ from typing import Callable, Dict, Optional, Sequence
 import torch
 
 TRAIN_GRAPHS = os.environ.get("VSRB_TRAIN_GRAPHS", "1") == "1"
+# Under torch.distributed (DDP): the parameters still receive their gradients through their own AccumulateGrad nodes, so
+# DDP's hooks fire as usual - all buckets after the backward graph instead of interleaved with it (12 MB of gradients:
+# tens of microseconds over NVLink).  The capture runs in thread-local error mode: NCCL's watchdog thread polls events.
+TRAIN_GRAPHS_DDP = os.environ.get("VSRB_TRAIN_GRAPHS_DDP", "1") == "1"
 TRAIN_GRAPH_AFTER = 3          # eager calls with one (shape, flags) key before the capture
 _auto_off = 0                  # > 0 while GraphedTrainStep warms up / captures its own whole-step graph
 
@@ -91,10 +95,10 @@ class _GraphedTraining:
         self.fwd, self.bwd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         VF.REPACK_IN_CAPTURE = True
         try:
-            with torch.cuda.graph(self.fwd, pool=pool):
+            with torch.cuda.graph(self.fwd, pool=pool, capture_error_mode="thread_local"):
                 self.static_out = run(self.static_in)
             self.static_gout = [torch.zeros_like(o) for o in self.static_out]
-            with torch.cuda.graph(self.bwd, pool=pool):
+            with torch.cuda.graph(self.bwd, pool=pool, capture_error_mode="thread_local"):
                 self.static_gin = torch.autograd.grad(self.static_out, aliases, self.static_gout, allow_unused=True)
         finally:
             VF.REPACK_IN_CAPTURE = False
@@ -144,7 +148,7 @@ def training_forward(model, lr: torch.Tensor):
     """(sr, lq) with gradients; replays a captured forward / backward once the call pattern has settled."""
     from . import autograd as AG
     from . import ops
-    dist_on = torch.distributed.is_available() and torch.distributed.is_initialized()
+    dist_on = torch.distributed.is_available() and torch.distributed.is_initialized() and not TRAIN_GRAPHS_DDP
     if (not TRAIN_GRAPHS or _auto_off or dist_on or lr.requires_grad or lr.dtype != torch.float32 or not lr.is_contiguous()
             or ops.PROFILE is not None or torch.cuda.is_current_stream_capturing()):
         return AG.realbasicvsr(model, lr)
