@@ -346,10 +346,10 @@ def train_cfg4(a, dev, world, rank, local, steps: int = 8, warmup: int = 4, batc
            "loss_first": float(losses[0]), "loss_last": float(losses[-1]), "replicas_identical": same,
            "grad_scale": float(scaler.get_scale()), "steps": steps, "warmup": warmup}
     from vsrlab_b200 import graphs as _graphs
-    ent = _graphs._train_entries.get(id(model))
+
     # after three eager calls the model's forward / backward replay from CUDA graphs inside this unchanged loop
     # (vsrlab_b200.graphs.training_forward), under DDP too
-    out["fwd_bwd_graphed"] = bool(ent is not None and ent.graphed is not None)
+    out["fwd_bwd_graphed"] = _graphs.graphed_patterns(model) > 0
     if world == 1:
         # the opt-in whole-step graph (vsrlab_b200.graphs.GraphedTrainStep: forward + backward + clip + Adam in ONE CUDA graph,
         # bf16 autocast, no GradScaler): what the same kernels cost when the host is out of the way.  The eager number above

@@ -35,7 +35,8 @@ TRAIN_GRAPHS = os.environ.get("VSRB_TRAIN_GRAPHS", "1") == "1"
 # DDP's hooks fire as usual - all buckets after the backward graph instead of interleaved with it (12 MB of gradients:
 # tens of microseconds over NVLink).  The capture runs in thread-local error mode: NCCL's watchdog thread polls events.
 TRAIN_GRAPHS_DDP = os.environ.get("VSRB_TRAIN_GRAPHS_DDP", "1") == "1"
-TRAIN_GRAPH_AFTER = 3          # eager calls with one (shape, flags) key before the capture
+TRAIN_GRAPH_AFTER = 3          # eager calls (with a backward) of one (shape, flags) key before the capture
+TRAIN_GRAPH_KEYS = 2           # captured call patterns kept per model (each owns the activations its backward needs)
 _auto_off = 0                  # > 0 while GraphedTrainStep warms up / captures its own whole-step graph
 
 
@@ -53,10 +54,19 @@ class _TrainBody(torch.nn.Module):
 
 class _TrainEntry:
     def __init__(self, model, key):
-        self.model_ref, self.key, self.seen, self.graphed, self.failed = weakref.ref(model), key, 0, None, False
+        self.model_ref, self.key, self.backwards, self.graphed, self.failed = weakref.ref(model), key, 0, None, False
+
+    def saw_backward(self, _grad):
+        self.backwards += 1               # (tensor hook on an eager call's `sr`: this call pattern does train)
 
 
-_train_entries: Dict[int, _TrainEntry] = {}
+_train_entries: Dict[int, dict] = {}
+
+
+def graphed_patterns(model) -> int:
+    """How many call patterns of `model` currently replay from CUDA graphs (tests, bench.py)."""
+    t = _train_entries.get(id(model))
+    return 0 if t is None or t["model"]() is not model else sum(e.graphed is not None for e in t["by_key"].values())
 
 
 class _GraphedTraining:
@@ -155,22 +165,32 @@ def training_forward(model, lr: torch.Tensor):
     params = list(model.parameters())
     key = (tuple(lr.shape), str(lr.device), model.training, torch.is_autocast_enabled("cuda"),
            tuple(p.requires_grad for p in params), tuple(p.data_ptr() for p in params))
-    e = _train_entries.get(id(model))
-    if e is None or e.model_ref() is not model or e.key != key:
-        e = _TrainEntry(model, key)
-        _train_entries[id(model)] = e
+    table = _train_entries.get(id(model))
+    if table is None or table["model"]() is not model:
+        table = {"model": weakref.ref(model), "by_key": {}}
+        _train_entries[id(model)] = table
         weakref.finalize(model, _train_entries.pop, id(model), None)
-    e.seen += 1
-    if e.graphed is None and not e.failed and e.seen > TRAIN_GRAPH_AFTER:
+    by_key = table["by_key"]
+    e = by_key.pop(key, None)
+    if e is None:
+        e = _TrainEntry(model, key)
+        while len(by_key) >= TRAIN_GRAPH_KEYS:            # (a training and an evaluation pattern; dicts keep insertion order)
+            by_key.pop(next(iter(by_key)))
+    by_key[key] = e                                       # most recently used last
+    if e.graphed is None and not e.failed and e.backwards >= TRAIN_GRAPH_AFTER:
         try:
             e.graphed = _capture_training(model, lr)
         except Exception as exc:          # keep training eagerly rather than fail the step
             e.failed = True
             warnings.warn(f"vsrlab_b200: training-graph capture failed ({type(exc).__name__}: {exc}); staying eager", RuntimeWarning)
     if e.graphed is None or e.graphed.pending:
-        # (a second forward before the first one's backward - two generator passes per step, an evaluation loop that
-        # leaves grad mode on - must not overwrite the activations the graph saved for that backward: eager)
-        return AG.realbasicvsr(model, lr)
+        # (a second forward before the first one's backward - two generator passes per step - must not overwrite the
+        # activations the graph saved for that backward: eager.  Patterns that never backpropagate - an evaluation loop that
+        # leaves grad mode on - are never captured: only eager calls whose `sr` received a gradient count.)
+        sr, lq = AG.realbasicvsr(model, lr)
+        if e.graphed is None and not e.failed and sr.requires_grad:
+            sr.register_hook(e.saw_backward)
+        return sr, lq
     sr, lq = e.graphed(lr)
     with torch.no_grad():
         lr.copy_(lq)                      # the reference refines its input in place (realbasicvsr.py:26-29)
