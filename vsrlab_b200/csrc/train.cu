@@ -451,12 +451,12 @@ static int launch_warp_bwd(const T* x, const float2* flow, const T* dout, float*
 }
 
 int launch_wgrad_tc(const void* x, int x_c, int c0, int ci_off, const void* dz, int dz_c, int batch, int h, int w, int cout,
-                    int cin_total, float* dw, cudaStream_t stream);
+                    int cin_total, float* dw, cudaStream_t stream, float* db = nullptr);
 int launch_bias_grad(const void* dz, int dz_c, long long pixels, int cout, int dtype, float* db, cudaStream_t s);
 int launch_bias_grad_multi(const void* const* dzs, int n_chunks, int dz_c, long long pixels, int cout, int dtype, float* db,
                            cudaStream_t s);
 int launch_wgrad_tc_multi(const void* const* xs, int x_c, int c0, int ci_off, const void* const* dzs, int dz_c, int n_chunks,
-                          int batch, int h, int w, int cout, int cin_total, float* dw, cudaStream_t stream);
+                          int batch, int h, int w, int cout, int cin_total, float* dw, cudaStream_t stream, float* db = nullptr);
 int launch_wgrad_taps(const void* x, int x_c, int x_c0, int ci_n, int ci_off, const void* dz, int dz_c, int z_c0, int co_n, int K,
                       int batch, int h, int w, int cin_total, float* dw, cudaStream_t stream);
 
@@ -477,18 +477,24 @@ int vsrb_conv2d_wgrad_multi(const vsrb_conv_geom* g, int32_t n_chunks, const voi
         VSRB_CHECK_ARG(g->seg_c[s] % 64 == 0 && in_c[s] % 8 == 0 && in_c[s] >= g->seg_c[s] && g->seg_off[s] + g->seg_c[s] <= cin_total,
                        "wgrad_multi: segment %d must have a multiple of 64 channels", s);
     cudaStream_t st = (cudaStream_t)stream;
+    // the bias gradient rides along with the first input-channel block of every group of chunks (the kernel's idle epilogue
+    // warps add up the dz tiles it streams anyway); VSRB_WGRAD_SEPARATE_BIAS=1 keeps the separate reduction kernel
+    const bool fuse_bias = db && !getenv("VSRB_WGRAD_SEPARATE_BIAS");
     for (int k0 = 0; k0 < n_chunks; k0 += 16) {
         const int nk = n_chunks - k0 < 16 ? n_chunks - k0 : 16;
+        bool first = true;
         for (int s = 0; s < g->n_seg; ++s) {
             const void* xs[16];
             for (int k = 0; k < nk; ++k) xs[k] = in[(size_t)(k0 + k) * g->n_seg + s];
             for (int c0 = 0; c0 < g->seg_c[s]; c0 += 64) {
-                int rc = launch_wgrad_tc_multi(xs, in_c[s], c0, g->seg_off[s] + c0, dz + k0, dz_c, nk, batch, h, w, g->cout, cin_total, dw, st);
+                int rc = launch_wgrad_tc_multi(xs, in_c[s], c0, g->seg_off[s] + c0, dz + k0, dz_c, nk, batch, h, w, g->cout, cin_total, dw, st,
+                                               (fuse_bias && first) ? db : nullptr);
                 if (rc != VSRB_OK) return rc;
+                first = false;
             }
         }
     }
-    if (db) {
+    if (db && !fuse_bias) {
         int rc = launch_bias_grad_multi(dz, n_chunks, dz_c, (long long)batch * h * w, g->cout, g->dtype, db, st);
         if (rc != VSRB_OK) return rc;
     }
@@ -520,6 +526,7 @@ int vsrb_conv2d_wgrad(const vsrb_conv_geom* g, const void* const* in, const int3
                          (reinterpret_cast<uintptr_t>(dz) & 15) == 0 && !getenv("VSRB_WGRAD_SIMT") && !getenv("VSRB_WGRAD_FFMA") &&
                          !getenv("VSRB_WGRAD_MMA");
     bool on_tc[4] = {false, false, false, false};
+    bool db_done = false;
     // (co, ci) tile of the mma.sync kernel: as narrow as its segments allow (the FFMA kernels keep 64 x 64)
     int co_t = 64, ci_t = 64, cmax = 0;
     for (int s = 0; s < g->n_seg; ++s) {
@@ -539,9 +546,11 @@ int vsrb_conv2d_wgrad(const vsrb_conv_geom* g, const void* const* in, const int3
         P.in[s] = in[s]; P.in_c[s] = in_c[s]; P.seg_c[s] = g->seg_c[s]; P.seg_off[s] = g->seg_off[s];
         if (on_tc[s]) {
             for (int c0 = 0; c0 < g->seg_c[s]; c0 += 64) {
+                const bool ride = db && !db_done && !getenv("VSRB_WGRAD_SEPARATE_BIAS");      // bias gradient from the same pass over dz
                 int rc = launch_wgrad_tc(in[s], in_c[s], c0, g->seg_off[s] + c0, dz, dz_c, batch, h, w, g->cout, cin_total, dw,
-                                         (cudaStream_t)stream);
+                                         (cudaStream_t)stream, ride ? db : nullptr);
                 if (rc != VSRB_OK) return rc;
+                db_done = db_done || ride;
             }
             continue;
         }
@@ -562,7 +571,7 @@ int vsrb_conv2d_wgrad(const vsrb_conv_geom* g, const void* const* in, const int3
             ++P.n_ci_blk;
         }
     }
-    if (db) {
+    if (db && !db_done) {
         int rc = launch_bias_grad(dz, dz_c, (long long)batch * h * w, g->cout * g->groups == g->cout ? g->cout : g->cout, g->dtype, db,
                                   (cudaStream_t)stream);
         if (rc != VSRB_OK) return rc;

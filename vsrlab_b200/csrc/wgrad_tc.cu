@@ -49,6 +49,8 @@ struct WgTcParams {
     int c0, n0;                 // channel offsets inside x / dz
     int cout, cin_total, ci_off;   // OIHW geometry of dw; ci_off = first input channel of this block on the OIHW axis
     float* dw;
+    float* db;                  // bias gradient (sum of dz over the pixels), or null: the epilogue warps, idle while the tiles stream
+                                // through, add up the dz tiles in shared memory - no second pass over dz
     int* dbg;
     int debug;                  // VSRB_WG_DEBUG: 1 / 2 / 4 = skip the final atomics / the MMAs / the loads (timing decomposition only)
 };
@@ -74,7 +76,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < kWgStages; ++i) {
             mbar_init(full0 + 8 * i, 1);
-            mbar_init(empty0 + 8 * i, 1);
+            mbar_init(empty0 + 8 * i, P.db ? 5 : 1);          // the MMAs' commit (+ the four bias warps)
         }
         mbar_init(done, 1);
         fence_barrier_init();
@@ -86,6 +88,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
     bool dead = false;
     const int my_tiles = (P.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    float bs0 = 0.f, bs1 = 0.f;                                // bias warps: this lane's channels 2*lane, 2*lane + 1
 
     if (warp == 0) {
         // ---- producer: one halo box of x and the dz tile per pixel tile ----
@@ -154,6 +157,28 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
         // ---- epilogue (once), part 1: TMEM -> shared memory in the OIHW order of the 64(co) x 64(ci) x 9 block.  Lanes
         // differ in ci, i.e. by 9 floats: conflict-free.  The pipeline stages are free once `done` has fired. ----
         const int wq = warp - 4;
+        if (P.db) {
+            // ---- bias gradient: every warp adds 16 of the 64 pixel rows of each dz tile; a row is 128 swizzled bytes, the
+            // lane's two channels sit in 16-byte chunk (lane / 4) ^ (row & 7): one conflict-free 4-byte load per row ----
+            int slot = 0;
+            uint32_t phase = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                const uint32_t zb = stage0 + slot * kWgStageBytes + kWgCopyBytes;
+                mbar_wait(full0 + 8 * slot, phase, P.dbg, 14, dead);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const uint32_t r = (uint32_t)(wq * 16 + i);
+                    uint32_t v;
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(zb + r * 128u + ((((uint32_t)lane >> 2) ^ (r & 7u)) << 4) + ((uint32_t)lane & 3u) * 4u));
+                    const float2 f = unpack_bf16(v);
+                    bs0 += f.x;
+                    bs1 += f.y;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty0 + 8 * slot);
+                if (++slot == kWgStages) { slot = 0; phase ^= 1; }
+            }
+        }
         mbar_wait(done, 0, P.dbg, 13, dead);
         tc_fence_after();
         if (my_tiles > 0) {
@@ -186,6 +211,16 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
             float* dst = P.dw + ((size_t)(n0 + co) * P.cin_total + P.ci_off) * 9;
             for (int i = threadIdx.x; i < 576; i += kWgThreads) atomicAdd(dst + i, stg[co * 576 + i]);
         }
+    }
+    if (P.db) {                                                // the four bias warps' partial sums -> one atomic per channel and CTA
+        float* bsum = reinterpret_cast<float*>(base_ptr + 256);
+        if (warp >= 4) {
+            bsum[(warp - 4) * 64 + 2 * lane] = bs0;
+            bsum[(warp - 4) * 64 + 2 * lane + 1] = bs1;
+        }
+        __syncthreads();
+        if (threadIdx.x < 64 && my_tiles > 0 && n0 + (int)threadIdx.x < P.cout && !(P.debug & 1))
+            atomicAdd(P.db + n0 + threadIdx.x, bsum[threadIdx.x] + bsum[64 + threadIdx.x] + bsum[128 + threadIdx.x] + bsum[192 + threadIdx.x]);
     }
     tc_fence_before();
     __syncthreads();
@@ -275,7 +310,7 @@ int launch_bias_grad(const void* dz, int dz_c, long long pixels, int cout, int d
 // one 64-input-channel block (x channels [c0, c0+64), OIHW offset ci_off) against all 64-wide output blocks, summed over
 // `n_chunks` (x, dz) pairs of `batch` images each
 int launch_wgrad_tc_multi(const void* const* xs, int x_c, int c0, int ci_off, const void* const* dzs, int dz_c, int n_chunks,
-                          int batch, int h, int w, int cout, int cin_total, float* dw, cudaStream_t stream) {
+                          int batch, int h, int w, int cout, int cin_total, float* dw, cudaStream_t stream, float* db) {
     static EncodeTiledFn encode = nullptr;
     static bool attr[64] = {false};                  // function attributes are per device
     static int sm_count[64] = {0};
@@ -309,7 +344,7 @@ int launch_wgrad_tc_multi(const void* const* xs, int x_c, int c0, int ci_off, co
     P.tiles_per_img = P.tiles_x * ceil_div(h, kWgRows);
     P.tiles_per_chunk = P.tiles_per_img * batch;
     P.total_tiles = P.tiles_per_chunk * n_chunks;
-    P.c0 = c0; P.cout = cout; P.cin_total = cin_total; P.ci_off = ci_off; P.dw = dw;
+    P.c0 = c0; P.cout = cout; P.cin_total = cin_total; P.ci_off = ci_off; P.dw = dw; P.db = db;
     P.dbg = debug_flag();
     cuuint32_t estr[4] = {1, 1, 1, 1};
     for (int k = 0; k < n_chunks; ++k) {
@@ -354,8 +389,8 @@ int launch_wgrad_tc_multi(const void* const* xs, int x_c, int c0, int ci_off, co
 }
 
 int launch_wgrad_tc(const void* x, int x_c, int c0, int ci_off, const void* dz, int dz_c, int batch, int h, int w, int cout,
-                    int cin_total, float* dw, cudaStream_t stream) {
-    return launch_wgrad_tc_multi(&x, x_c, c0, ci_off, &dz, dz_c, 1, batch, h, w, cout, cin_total, dw, stream);
+                    int cin_total, float* dw, cudaStream_t stream, float* db) {
+    return launch_wgrad_tc_multi(&x, x_c, c0, ci_off, &dz, dz_c, 1, batch, h, w, cout, cin_total, dw, stream, db);
 }
 
 }  // namespace vsrb
