@@ -430,22 +430,30 @@ __global__ void __launch_bounds__(256) im2col3x3_c3_smem_kernel(const float* __r
     const int img = row / h, y = row - img * h;
     const int plane = h * w, pitch = w + 2;
     const float* fp = src + (size_t)img * 3 * plane;
-    for (int idx = threadIdx.x; idx < 9 * pitch; idx += blockDim.x) {
-        const int r = idx / pitch, xx = idx - r * pitch - 1;
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {                       // (no division per element: the first version of this kernel was instruction bound)
         const int c = r / 3, yy = y + (r - c * 3) - 1;
-        rows_s[idx] = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? __ldg(fp + c * plane + yy * w + xx) : 0.f;
+        const bool row_ok = yy >= 0 && yy < h;
+        const float* rp = fp + c * plane + yy * w;
+        for (int xs = threadIdx.x; xs < pitch; xs += blockDim.x) {
+            const int xx = xs - 1;
+            rows_s[r * pitch + xs] = (row_ok && xx >= 0 && xx < w) ? __ldg(rp + xx) : 0.f;
+        }
     }
     __syncthreads();
     uint4* out = dst + (size_t)row * w * 4;
-    for (int i = threadIdx.x; i < 4 * w; i += blockDim.x) {
-        const int j = i & 3, x = i >> 2;
-        float v[8];
+    // one thread per pixel: its 27 values sit at compile-time offsets, the 64-byte patch row leaves as four 16-byte stores
+    for (int x = threadIdx.x; x < w; x += blockDim.x) {
+        float v[32];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int k = 8 * j + e, tap = k / 3, c = k - tap * 3;
-            v[e] = k < 27 ? rows_s[(c * 3 + tap / 3) * pitch + x + tap % 3] : 0.f;
+        for (int k = 0; k < 32; ++k) {
+            const int tap = k / 3, c = k - tap * 3;
+            v[k] = k < 27 ? rows_s[(c * 3 + tap / 3) * pitch + x + tap % 3] : 0.f;
         }
-        out[i] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            out[x * 4 + j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                                        pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
     }
 }
 }  // namespace vsrb
