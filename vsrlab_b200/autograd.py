@@ -157,10 +157,12 @@ class ConvFn(torch.autograd.Function):
         dy = _cl(dy)
         d_res = dy if ctx.has_res else None
         dz = dy
+        # one fused elementwise kernel each (compare + multiply + select were three passes: 7 GB of traffic on the HR
+        # LeakyReLU of conv_last.0 alone)
         if ctx.act == "relu":
-            dz = dy * (out > 0)
+            dz = torch.ops.aten.threshold_backward(dy, out, 0)
         elif ctx.act == "lrelu":
-            dz = torch.where(out > 0, dy, dy * ctx.slope)
+            dz = torch.ops.aten.leaky_relu_backward(dy, out, ctx.slope, True)
         cout = conv.out_channels
         if ctx.pixshuf:
             cq = cout // (ctx.pixshuf ** 2)
@@ -321,7 +323,7 @@ class ResBlockFn(torch.autograd.Function):
             park(1 + 2 * i, [x_in], dz1)
             g = dgrad(1 + 2 * i, dz1, residual=g)                     # + the skip connection's gradient, fused
         x0 = acts[0]
-        dz0 = torch.where(x0 > 0, g, g * 0.1)
+        dz0 = torch.ops.aten.leaky_relu_backward(g, x0, 0.1, True)   # LeakyReLU(0.1) of the stem, from its output
         park(0, ins, dz0)
         d_ins: List[Optional[torch.Tensor]] = [None] * n_in
         if any(ctx.needs_input_grad[4 + i] for i in range(n_in)):
