@@ -122,6 +122,12 @@ def main():
             torch.cuda.synchronize()
         print(prof_o.key_averages(group_by_input_shape=True).table(sort_by="self_cuda_time_total", row_limit=30, max_name_column_width=40,
                                                                     max_shapes_column_width=70), file=sys.stderr)
+        # the torch glue between the library's kernels: aten ops by input shape
+        rows = [e for e in prof_o.key_averages(group_by_input_shape=True) if e.key.startswith("aten::") and e.device_time_total > 0]
+        rows.sort(key=lambda e: -e.self_device_time_total)
+        print("aten ops by self CUDA time:", file=sys.stderr)
+        for e in rows[:45]:
+            print(f"  {e.self_device_time_total / 1e3:8.3f} ms {e.count:4d}x  {e.key:34s} {str(e.input_shapes)[:110]}", file=sys.stderr)
     if a.host_profile and rank == 0:
         import cProfile
         import pstats
