@@ -465,6 +465,42 @@ class _GatherFramesFn(torch.autograd.Function):
         return torch.cat([g_bk, g_fw], 0).index_select(0, inv), None, None
 
 
+class _GatherStepsFn(torch.autograd.Function):
+    """rows [R, ...] -> one tensor per propagation step (rows idx[k * per : (k + 1) * per] each), made by ONE gather; the
+    gradient is one stack + one index_add_ on a small tensor.  (Slicing the frames / flows of a step out of their clip
+    tensors inside the loop cost a zero-fill of the whole clip tensor plus an add per step in the backward pass.)"""
+
+    @staticmethod
+    def forward(ctx, rows, idx, steps):
+        ctx.save_for_backward(idx)
+        ctx.n_rows = rows.shape[0]
+        out = rows.index_select(0, idx)
+        return tuple(out.view(steps, -1, *rows.shape[1:]).unbind(0))
+
+    @staticmethod
+    def backward(ctx, *gs):
+        idx, = ctx.saved_tensors
+        ref = next(g for g in gs if g is not None)
+        g = torch.stack([torch.zeros_like(ref) if x is None else x for x in gs], 0).flatten(0, 1)
+        out = torch.zeros((ctx.n_rows, *g.shape[1:]), dtype=g.dtype, device=g.device)
+        return out.index_add_(0, idx, g), None, None
+
+
+_step_idx: dict = {}
+
+
+def _step_indices(n: int, t: int, device):
+    """(frame rows, flow rows) per step: step k runs frame t-1-k of the backward chain (images [0, n)) and frame k of the
+    forward chain (images [n, 2n)); from step 1 on it warps with backward flow t-1-k and forward flow k-1."""
+    key = (n, t, str(device))
+    if key not in _step_idx:
+        fr = [v for k in range(t) for v in ([nn * t + (t - 1 - k) for nn in range(n)] + [nn * t + k for nn in range(n)])]
+        m = n * (t - 1)
+        fw = [v for k in range(1, t) for v in ([nn * (t - 1) + (t - 1 - k) for nn in range(n)] + [m + nn * (t - 1) + (k - 1) for nn in range(n)])]
+        _step_idx[key] = (torch.tensor(fr).to(device), torch.tensor(fw, dtype=torch.long).to(device))
+    return _step_idx[key]
+
+
 def basicvsr(bv, lrs: torch.Tensor) -> torch.Tensor:
     """BasicVSR.forward with gradients (basicvsr.py:39-83)."""
     from . import functional as VF
@@ -476,27 +512,24 @@ def basicvsr(bv, lrs: torch.Tensor) -> torch.Tensor:
     if train_flow:
         # both directions as one batch (first the backward pairs, then the forward pairs), like the inference path
         fl = spynet(bv.spynet, torch.cat([a, b], 0), torch.cat([b, a], 0))
-        m = n * (t - 1)
-        fb = fl[:m].view(n, t - 1, 2, h, w).permute(0, 1, 3, 4, 2)
-        ff = fl[m:].view(n, t - 1, 2, h, w).permute(0, 1, 3, 4, 2)
+        flows = fl.permute(0, 2, 3, 1).contiguous()                          # [2m, h, w, 2]: backward pairs, then forward pairs
     else:
         with torch.no_grad():
             ref, supp = VF._pair_indices(n, t, lrs.device)
-            fl = VF._spynet_run(bv.spynet, lrs.detach().reshape(n * t, c, h, w).contiguous(), ref, supp, BF16)
-            m = n * (t - 1)
-            fb, ff = fl[:m].view(n, t - 1, h, w, 2), fl[m:].view(n, t - 1, h, w, 2)
-    lr16 = to_cl16(lrs.reshape(n * t, c, h, w)).view(n, t, 16, h, w)
+            flows = VF._spynet_run(bv.spynet, lrs.detach().reshape(n * t, c, h, w).contiguous(), ref, supp, BF16)
+    idx_frames, idx_flows = _step_indices(n, t, lrs.device)
+    lr_rows = to_cl16(lrs.reshape(n * t, c, h, w)).permute(0, 2, 3, 1)       # [n * t, h, w, 16], plain contiguous view
+    lr_steps = _GatherStepsFn.apply(lr_rows, idx_frames, t)
+    flow_steps = _GatherStepsFn.apply(flows, idx_flows, t - 1) if t > 1 else ()
     segs = [(3, mid), (0, 3)]
     # both directions advance together: step k runs frame t-1-k of the backward chain and frame k of the forward chain as
     # the two weight groups of one launch per layer (images [0, n) backward, [n, 2n) forward)
     feats: List[torch.Tensor] = []
     feat = torch.zeros((2 * n, mid, h, w), dtype=torch.bfloat16, device=lrs.device).contiguous(memory_format=CL)
     for k in range(t):
-        ib, jf = t - 1 - k, k
         if k > 0:
-            feat = WarpFn.apply(feat, torch.cat([fb[:, ib], ff[:, jf - 1]], 0), False)
-        lr_k = _cl(torch.cat([lr16[:, ib], lr16[:, jf]], 0))
-        feat = resblock((bv.backward_resblocks, bv.forward_resblocks), [feat, lr_k], segs)
+            feat = WarpFn.apply(feat, flow_steps[k - 1], False)
+        feat = resblock((bv.backward_resblocks, bv.forward_resblocks), [feat, lr_steps[k].permute(0, 3, 1, 2)], segs)
         feats.append(feat)
     # fusion + reconstruction, batched over frames in the output's (n, t) order: one gather per direction out of the
     # concatenated steps (slicing every step's `feat` in two cost five slow strided kernels per step in the backward pass)
