@@ -598,6 +598,22 @@ def test_training_forward_is_graphed_after_warmup_and_matches_eager(dev):
             ge = torch.cat([p.grad.flatten() for p in net.parameters()])
             assert cos(ga, ge) > 0.9999 and rel(ga, ge) < 2e-2
             opt.zero_grad()
+            # gradient accumulation over two REPLAYED micro-steps: p.grad must be g1 + g2 (not a view of the graph's static
+            # gradient buffer that the second replay overwrites)
+            def accumulate():
+                opt.zero_grad(set_to_none=True)
+                for xin, wgt in ((xa, 1.0), (xb, 3.0)):
+                    with torch.autocast("cuda", dtype=torch.float16):
+                        s_, _ = net(xin.clone())
+                    (wgt * s_.mean()).backward()
+                return torch.cat([p.grad.flatten() for p in net.parameters()])
+            g_acc = accumulate()
+            assert not entry.graphed.pending
+            graphs.TRAIN_GRAPHS = False
+            g_ref = accumulate()
+            graphs.TRAIN_GRAPHS = True
+            assert cos(g_acc, g_ref) > 0.9999 and rel(g_acc, g_ref) < 2e-2, (cos(g_acc, g_ref), rel(g_acc, g_ref))
+            opt.zero_grad()
         # another shape and a no_grad call keep working
         with torch.autocast("cuda", dtype=torch.float16):
             sr2, _ = net(torch.rand(1, 3, 3, 16, 24, device=dev))

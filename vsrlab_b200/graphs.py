@@ -139,7 +139,10 @@ class _ReplayFn(torch.autograd.Function):
                 sg.copy_(g)
         e.bwd.replay()
         e.pending = False
-        return (None, None) + tuple(None if g is None else g.detach() for g in e.static_gin)
+        # CLONES: AccumulateGrad may adopt an incoming gradient as `p.grad` without copying; a view of the graph's static
+        # buffer would then be overwritten by the next replay - with gradient accumulation the first micro-step's gradient
+        # would be lost and the second counted twice (12 MB of parameters: the copies cost microseconds)
+        return (None, None) + tuple(None if g is None else g.clone() for g in e.static_gin)
 
 
 def _capture_training(model, lr: torch.Tensor):
