@@ -204,6 +204,64 @@ class ConvFn(torch.autograd.Function):
                 *d_ins)
 
 
+class SrTailFn(torch.autograd.Function):
+    """sr = conv_last.2(x) + bilinear_up(lq) (basicvsr.py:81-82) with the inference path's image epilogue (EPI_SR): the conv
+    writes the fp32 NCHW frames with the skip term added.  (As separate torch ops the slice of the 3 real channels, its fp32
+    copy, the upsampling, the sum and - in the backward - a zero-filled 16-channel HR gradient were seven passes over HR maps.)
+    Backward: dz = the 3-channel gradient repacked to 16-channel NHWC bf16 by the library's layout kernel; weight / bias /
+    input gradients as in ConvFn; d lq = the bilinear kernel's transpose (aten)."""
+
+    @staticmethod
+    def forward(ctx, weight, bias, token, box, conv, x, lq):
+        from .functional import packed
+        from ._lib import EPI_SR
+        x = _cl(x)
+        n, xc, hh, ww = x.shape
+        pc = packed([conv], [(0, conv.in_channels)], BF16, 0)
+        lqc = lq.detach().to(torch.float32).contiguous()
+        sr = torch.empty((n, conv.out_channels, hh, ww), dtype=torch.float32, device=x.device)
+        ops.conv2d_fwd(pc, [x], [xc], n, hh, ww, act=ACT_NONE, epilogue=EPI_SR, f32_io=sr, f32_in=lqc, aux_hw=tuple(lq.shape[-2:]))
+        ctx.conv, ctx.box, ctx.lq_shape = conv, box, tuple(lq.shape)
+        ctx.save_for_backward(weight, x)
+        return sr
+
+    @staticmethod
+    def backward(ctx, dsr):
+        weight, x = ctx.saved_tensors
+        conv = ctx.conv
+        n, xc, hh, ww = x.shape
+        dsr = dsr.contiguous()
+        dz = torch.empty((n, 16, hh, ww), dtype=torch.bfloat16, device=x.device, memory_format=CL)
+        ops.nchw_to_nhwc(dsr, dz, n, conv.out_channels, hh, ww, 16, BF16)
+        segs = ((0, conv.in_channels),)
+        dw = db = None
+        if ctx.box is not None:
+            ctx.box.append(([x], dz))
+        elif ctx.needs_input_grad[0]:
+            dw = torch.zeros_like(weight, dtype=torch.float32)
+            db = torch.zeros(conv.out_channels, dtype=torch.float32, device=weight.device) if conv.bias is not None else None
+            ops.conv2d_wgrad(_wgrad_geom(conv, segs), [x], [xc], dz, 16, n, hh, ww, conv.in_channels, dw, db)
+        dx = None
+        if ctx.needs_input_grad[5]:
+            pt = _packed_transposed(conv)
+            dx = torch.empty((n, pt.cout_pad, hh, ww), dtype=torch.bfloat16, device=x.device, memory_format=CL)
+            ops.conv2d_fwd(pt, [dz], [16], n, hh, ww, act=ACT_NONE, out=dx, out_c=pt.cout_pad)
+            if pt.cout_pad != xc:
+                dx = F.pad(dx[:, :conv.in_channels], (0, 0, 0, 0, 0, xc - conv.in_channels))
+        dlq = None
+        if ctx.needs_input_grad[6]:
+            dlq = torch.ops.aten.upsample_bilinear2d_backward(dsr, [hh, ww], list(ctx.lq_shape), False, None, None)
+        return dw, (db if (conv.bias is not None and ctx.needs_input_grad[1]) else None), None, None, None, dx, dlq
+
+
+def sr_tail(mod, x: torch.Tensor, lq: torch.Tensor) -> torch.Tensor:
+    """conv_last.2 + skip; `lq` [N,3,h,w] fp32, the output is H / h times larger."""
+    token, box = _weight_token(mod, ((0, mod.in_channels),))
+    if token is not None:
+        return SrTailFn.apply(mod.weight.detach(), None if mod.bias is None else mod.bias.detach(), token, box, mod, x, lq)
+    return SrTailFn.apply(mod.weight, mod.bias, None, None, mod, x, lq)
+
+
 class WarpFn(torch.autograd.Function):
     """flow_warp on a channels_last tensor (bf16 or fp32); flow [B,h,w,2] fp32."""
 
@@ -542,10 +600,14 @@ def basicvsr(bv, lrs: torch.Tensor) -> torch.Tensor:
     for up in bv.upsample:
         x = conv(up.upconv, [x], [(0, mid)], "none", pixshuf=2)
     x = conv(bv.conv_last[0], [x], [(0, mid)], "lrelu")
-    x = conv(bv.conv_last[2], [x], [(0, bv.conv_last[2].in_channels)], "none")[:, :3].float()
     scale = 2 ** len(bv.upsample)
-    skip = F.interpolate(lrs.reshape(n * t, c, h, w), scale_factor=scale, mode="bilinear", align_corners=False)
-    return (x + skip).view(n, t, c, h * scale, w * scale)
+    last = bv.conv_last[2]
+    if last.out_channels == 3 and c == 3 and last.kernel_size == (3, 3) and last.in_channels % 16 == 0:
+        sr = sr_tail(last, x, lrs.reshape(n * t, c, h, w))                   # conv + bilinear skip in one kernel
+    else:
+        x = conv(last, [x], [(0, last.in_channels)], "none")[:, :c].float()
+        sr = x + F.interpolate(lrs.reshape(n * t, c, h, w), scale_factor=scale, mode="bilinear", align_corners=False)
+    return sr.view(n, t, c, h * scale, w * scale)
 
 
 def realbasicvsr(model, lr: torch.Tensor, write_back: bool = True):
